@@ -1,0 +1,361 @@
+// Small kernels around the column passes: partial-sum reduction, the shared
+// (population-level) latents, the hyper latents of the hierarchical models,
+// initialisation and the reference-order <-> device-layout permutations.
+#pragma once
+#include "bb_kernels.cuh"
+
+namespace bb {
+
+// sums layout: sums[((r * K + k) * 5 + q) * tmax + t]
+//   q = 0 Lambda_t | 1 neutral sum d_t | 2 neutral sum d_t^2 | 3 mutant sum w (d_t - s) | 4 mutant sum w
+enum { Q_LAM = 0, Q_DN = 1, Q_D2N = 2, Q_A = 3, Q_W = 4, NQ = 5 };
+
+struct ReduceArgs {
+    SegList segs;
+    int K, tmax, pv, nt;     // pv / nt of this launch group
+    int w_single;            // E == 1: mutant W stored once (slot 2nt-1)
+    unsigned rep_mask;       // replicates belonging to this launch group (bit r)
+    const double *part;      // [blocks][K][pv]
+    double *sums;
+};
+
+// one warp per output (r, k, q, t): fixed-order sum over the CTAs of the matching segments
+static __global__ void __launch_bounds__(128) reduce_kernel(const ReduceArgs a, int R) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nout = R * a.K * NQ * a.tmax;
+    if (warp >= nout) return;
+    const int t = warp % a.tmax, q = (warp / a.tmax) % NQ, k = (warp / (a.tmax * NQ)) % a.K,
+              r = warp / (a.tmax * NQ * a.K);
+    const int nt = a.nt;
+    if (t >= (q == Q_LAM ? nt : nt - 1)) return;
+    if (!((a.rep_mask >> r) & 1u)) return;      // replicate handled by another launch group (ragged T)
+    double s = 0.0;
+    for (int si = 0; si < a.segs.nseg; ++si) {
+        const Seg &sg = a.segs.seg[si];
+        if (sg.rep != r) continue;
+        int v;
+        if (q == Q_LAM) v = t;
+        else if (q == Q_DN || q == Q_D2N) { if (!sg.neutral) continue; v = (q == Q_DN ? nt : 2 * nt - 1) + t; }
+        else { if (sg.neutral) continue; v = q == Q_A ? nt + t : (a.w_single ? 2 * nt - 1 : 2 * nt - 1 + t); }
+        for (int b = sg.blk0 + lane; b < sg.blk1; b += 32) s += a.part[((size_t)b * a.K + k) * a.pv + v];
+    }
+    s = warp_sum<double>(s);
+    if (lane == 0) a.sums[((size_t)(r * a.K + k) * NQ + q) * a.tmax + t] = s;
+}
+
+// ------------------------------------------------------------------ shared latents
+template <typename real> struct SharedArgs {
+    int R, K, tmax, nst;          // nst = sum_r (T_r - 1)
+    int nt[MAX_SEG], sh0[MAX_SEG];
+    double n_neutral;             // N over all shards
+    const double *sums;           // all-reduced
+    double2 *sh_th, *sh_acc, *sh_ring;   // [2 nst] (s-bar block, then log-sigma-bar block); ring [n][2 nst]
+    const double2 *sh_pr;         // (mean, 1/var)
+    uint32_t seed0, seed1, step;
+    const double *eps_sh;         // supplied noise [K][2 nst] or nullptr
+    int z_direct;
+    real *ctx;                    // [R][K][3][tmax]
+    double *scratch;              // [K][2 nst] per-sample gradients
+    double2 *gout;                // [2 nst] (dELBO/dmu, dELBO/domega) when !opt.update
+    double *dump;                 // [K][2 nst] per-sample d log pi/dz or nullptr
+    double *elbo_sh;              // [K+1]: neutral-likelihood + shared-prior log-density per k; sum log sigma
+    OptArgs opt;
+    int leader;                   // 1: this rank reports the shared latents' ELBO terms (rank 0)
+};
+
+__device__ __forceinline__ double softplus_d(double w) { return fmax(w, 0.0) + log1p(exp(-fabs(w))); }
+
+template <typename real>
+__global__ void __launch_bounds__(128) shared_kernel(const SharedArgs<real> a) {
+    const int tid = threadIdx.x;
+    const int n2 = 2 * a.nst;
+    __shared__ double s_lp[MAX_K_SHARED];
+    for (int k = tid; k < a.K; k += blockDim.x) s_lp[k] = 0.0;
+    __syncthreads();
+    // ---- phase A: one thread per (replicate, sample)
+    for (int rk = tid; rk < a.R * a.K; rk += blockDim.x) {
+        const int r = rk / a.K, k = rk % a.K;
+        const int nt = a.nt[r], sh0 = a.sh0[r];
+        const double *S = a.sums + (size_t)(r * a.K + k) * NQ * a.tmax;
+        real *ctx = a.ctx + (size_t)(r * a.K + k) * 3 * a.tmax;
+        double uprev = 0.0, lp = 0.0;
+        for (int t = 0; t < nt; ++t) {
+            double u = 0.0;
+            if (t < nt - 1) {
+                const int is = sh0 + t, il = a.nst + sh0 + t;
+                double es, el;
+                if (a.eps_sh) { es = a.eps_sh[(size_t)k * n2 + is]; el = a.eps_sh[(size_t)k * n2 + il]; }
+                else {
+                    es = stream_normal<double>(STREAM_SHARED, (uint32_t)is, (uint32_t)k, a.step, a.seed0, a.seed1);
+                    el = stream_normal<double>(STREAM_SHARED, (uint32_t)il, (uint32_t)k, a.step, a.seed0, a.seed1);
+                }
+                const double2 ths = a.sh_th[is], thl = a.sh_th[il];
+                const double zs = a.z_direct ? es : ths.x + softplus_d(ths.y) * es;   // s-bar_t
+                const double zl = a.z_direct ? el : thl.x + softplus_d(thl.y) * el;   // log-sigma-bar_t
+                const double c = log(S[Q_LAM * a.tmax + t + 1]) - log(S[Q_LAM * a.tmax + t]);
+                const double wbar = exp(-2.0 * zl);
+                const double av = zs - c;
+                const double dn = S[Q_DN * a.tmax + t], d2n = S[Q_D2N * a.tmax + t];
+                const double am = S[Q_A * a.tmax + t], wm = S[Q_W * a.tmax + t];
+                const double qn = d2n + 2.0 * av * dn + a.n_neutral * av * av;   // sum_neutral res^2
+                u = wbar * (dn + a.n_neutral * av) + (am + av * wm);            // sum_all w res
+                const double2 ps = a.sh_pr[is], pl = a.sh_pr[il];
+                a.scratch[(size_t)k * n2 + is] = -u - (zs - ps.x) * ps.y;
+                a.scratch[(size_t)k * n2 + il] = wbar * qn - a.n_neutral - (zl - pl.x) * pl.y;
+                lp += -a.n_neutral * zl - 0.5 * wbar * qn
+                      - 0.5 * (zs - ps.x) * (zs - ps.x) * ps.y - 0.5 * (zl - pl.x) * (zl - pl.x) * pl.y;
+                ctx[0 * a.tmax + t] = (real)(c - zs);
+                ctx[2 * a.tmax + t] = (real)wbar;
+            }
+            ctx[1 * a.tmax + t] = (real)((uprev - u) / S[Q_LAM * a.tmax + t]);
+            uprev = u;
+        }
+        atomicAdd(&s_lp[k], lp);      // R <= MAX_SEG terms per k; order-insensitive to ~1e-16, reporting only
+    }
+    __threadfence_block();
+    __syncthreads();
+    // ---- phase B: one thread per shared latent
+    const double invK = 1.0 / a.K;
+    double lsig = 0.0;
+    for (int i = tid; i < n2; i += blockDim.x) {
+        double2 th = a.sh_th[i];
+        const double sigma = softplus_d(th.y);
+        double sg = 0.0, sge = 0.0;
+        for (int k = 0; k < a.K; ++k) {
+            const double g = a.scratch[(size_t)k * n2 + i];
+            const double e = a.eps_sh ? a.eps_sh[(size_t)k * n2 + i]
+                                      : stream_normal<double>(STREAM_SHARED, (uint32_t)i, (uint32_t)k, a.step,
+                                                              a.seed0, a.seed1);
+            sg += g; sge += g * e;
+            if (a.dump) a.dump[(size_t)k * n2 + i] = g;
+        }
+        lsig += log(sigma);
+        const double gm = sg * invK;
+        const double go = (sge * invK + 1.0 / sigma) / (1.0 + exp(-th.y));
+        if (a.opt.update) {
+            double2 ac = a.sh_acc[i];
+            double2 rg = make_double2(0.0, 0.0);
+            double2 *rp = a.opt.kind == 0 ? a.sh_ring + (size_t)a.opt.slot * n2 + i : nullptr;
+            if (rp) rg = *rp;
+            opt_apply<double>(a.opt, -gm, th.x, ac.x, rg.x);
+            opt_apply<double>(a.opt, -go, th.y, ac.y, rg.y);
+            a.sh_th[i] = th; a.sh_acc[i] = ac;
+            if (rp) *rp = rg;
+        } else if (a.gout) {
+            a.gout[i] = make_double2(gm, go);
+        }
+    }
+    if (a.elbo_sh) {
+        __shared__ double s_ls[128];
+        s_ls[tid] = lsig;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int j = 0; j < blockDim.x; ++j) s += s_ls[j];
+            a.elbo_sh[a.K] = a.leader ? s : 0.0;
+            for (int k = 0; k < a.K; ++k) a.elbo_sh[k] = a.leader ? s_lp[k] : 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ hyper latents (theta of the hierarchical models)
+template <typename real> struct HyperArgs {
+    int H, K;
+    uint32_t gid0;               // global hyper index of local hyper 0 (noise lattice slot)
+    vec2<real> *hy_th, *hy_acc, *hy_ring;   // [H]; ring [n][H]
+    const vec2<real> *hy_pr;     // (mean, 1/var) [H]
+    vec2<real> *zeps;            // [K][H] (z, eps)
+    uint32_t seed0, seed1, step;
+    const real *eps_hy;          // supplied noise [K][H] or nullptr
+    int z_direct;
+    // update
+    const int *csr_off;          // [H+1]
+    const int *csr_mem;          // contribution slots (e * cpad + c)
+    const vec2<real> *hcontrib;  // [E][cpad]
+    const real *dump_hcontrib;   // [K][E * cpad] per-sample contributions or nullptr
+    long long dump_stride;       // E * cpad
+    real *dump;                  // [K][H] per-sample d log pi / d theta or nullptr
+    vec2<real> *gout;            // [H]
+    double *epart;               // [gridDim.x][K+1] or nullptr
+    OptArgs opt;
+};
+
+template <typename real>
+__global__ void __launch_bounds__(BLOCK) hyper_prep_kernel(const HyperArgs<real> a) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= a.H) return;
+    const vec2<real> th = a.hy_th[h];
+    const real sigma = softplus(th.y);
+    for (int k = 0; k < a.K; ++k) {
+        const real e = a.eps_hy ? a.eps_hy[(size_t)k * a.H + h]
+                                : stream_normal<real>(STREAM_HYPER, a.gid0 + (uint32_t)h, (uint32_t)k, a.step,
+                                                      a.seed0, a.seed1);
+        const real z = a.z_direct ? e : fma(sigma, e, th.x);
+        a.zeps[(size_t)k * a.H + h] = mk2<real>(z, e);
+    }
+}
+
+template <typename real>
+__global__ void __launch_bounds__(BLOCK) hyper_update_kernel(const HyperArgs<real> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sel = reinterpret_cast<double *>(smem_raw);      // [K+1][BLOCK]
+    const int tid = threadIdx.x;
+    const int h = blockIdx.x * blockDim.x + tid;
+    const bool want_elbo = a.epart != nullptr;
+    if (want_elbo)
+        for (int k = 0; k <= a.K; ++k) sel[k * BLOCK + tid] = 0.0;
+    if (h < a.H) {
+        vec2<real> th = a.hy_th[h];
+        const real sigma = softplus(th.y);
+        const vec2<real> pr = a.hy_pr[h];
+        real sg = real(0), sge = real(0);
+        const int m0 = a.csr_off[h], m1 = a.csr_off[h + 1];
+        for (int m = m0; m < m1; ++m) {                       // fixed member order -> deterministic
+            const vec2<real> cb = a.hcontrib[a.csr_mem[m]];
+            sg += cb.x; sge += cb.y;
+        }
+        for (int k = 0; k < a.K; ++k) {
+            const vec2<real> ze = a.zeps[(size_t)k * a.H + h];
+            const real dz = ze.x - pr.x;
+            const real gp = -dz * pr.y;
+            sg += gp; sge = fma(gp, ze.y, sge);
+            if (want_elbo) sel[k * BLOCK + tid] += (double)(real(-0.5) * dz * dz * pr.y);
+            if (a.dump) {
+                real gk = gp;
+                for (int m = m0; m < m1; ++m) gk += a.dump_hcontrib[(size_t)k * a.dump_stride + a.csr_mem[m]];
+                a.dump[(size_t)k * a.H + h] = gk;
+            }
+        }
+        if (want_elbo) sel[a.K * BLOCK + tid] = (double)bb_log(sigma);
+        const real invK = real(1) / real(a.K);
+        finish_latent<real>(a.opt, invK, sg, sge, sigma, a.hy_th + h, a.hy_acc + h,
+                            a.hy_ring ? a.hy_ring + (size_t)a.opt.slot * a.H + h : nullptr,
+                            a.gout ? a.gout + h : nullptr, th.x, th.y);
+    }
+    if (want_elbo) {
+        __syncthreads();
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int row = warp; row <= a.K; row += BLOCK / 32) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < BLOCK / 32; ++j) s += sel[row * BLOCK + j * 32 + lane];
+            s = warp_sum<double>(s);
+            if (lane == 0) a.epart[(size_t)blockIdx.x * (a.K + 1) + row] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ ELBO assembly
+// out[k] = sum of the variable log-density parts of sample k; out[K] = sum log sigma
+static __global__ void elbo_sum_kernel(const double *p2part, int n2, const double *hypart, int nh, const double *elbo_sh,
+                                int K, double *out) {
+    const int k = blockIdx.x;        // one block per output row
+    double s = 0.0;
+    for (int b = threadIdx.x; b < n2; b += blockDim.x) s += p2part[(size_t)b * (K + 1) + k];
+    for (int b = threadIdx.x; b < nh; b += blockDim.x) s += hypart[(size_t)b * (K + 1) + k];
+    __shared__ double sm[128];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int j = 0; j < blockDim.x; ++j) t += sm[j];
+        out[k] = t + (elbo_sh ? elbo_sh[k] : 0.0);
+    }
+}
+
+// ------------------------------------------------------------------ layout permutations (map = reference index, -1 = padding)
+template <typename real>
+__global__ void scatter_pairs_kernel(vec2<real> *dst, const int *map, long long n, const double *x, const double *y,
+                                     double fill_x, double fill_y) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int m = map[i];
+    dst[i] = m >= 0 ? mk2<real>((real)x[m], (real)y[m]) : mk2<real>((real)fill_x, (real)fill_y);
+}
+
+template <typename real>
+__global__ void gather_pairs_kernel(const vec2<real> *src, const int *map, long long n, double *x, double *y,
+                                    int softplus_y) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int m = map[i];
+    if (m < 0) return;
+    const vec2<real> v = src[i];
+    if (x) x[m] = (double)v.x;
+    if (y) y[m] = softplus_y ? softplus_d((double)v.y) : (double)v.y;
+}
+
+// K rows of scalars: dst[k][i] = src[k * D + map[i]]
+template <typename real>
+__global__ void scatter_rows_kernel(real *dst, const int *map, long long n, int K, const double *src, long long D) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int m = map[i];
+    for (int k = 0; k < K; ++k) dst[(size_t)k * n + i] = m >= 0 ? (real)src[(size_t)k * D + m] : real(0);
+}
+
+template <typename real>
+__global__ void gather_rows_kernel(const real *src, const int *map, long long n, int K, double *dst, long long D) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int m = map[i];
+    if (m < 0) return;
+    for (int k = 0; k < K; ++k) dst[(size_t)k * D + m] = (double)src[(size_t)k * n + i];
+}
+
+// mean-field initialisation: mu_j = n(INIT, j), omega_j = n(INIT, D + j) with j the reference index
+template <typename real>
+__global__ void init_params_kernel(vec2<real> *dst, const int *map, long long n, long long D, uint32_t seed0,
+                                   uint32_t seed1) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int m = map[i];
+    if (m < 0) { dst[i] = mk2<real>(0, 0); return; }
+    const double mu = stream_normal<double>(STREAM_INIT, (uint32_t)m, 0u, 0u, seed0, seed1);
+    const double om = stream_normal<double>(STREAM_INIT, (uint32_t)(D + m), 0u, 0u, seed0, seed1);
+    dst[i] = mk2<real>((real)mu, (real)om);
+}
+
+template <typename T> __global__ void fill_kernel(T *p, long long n, T v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// the lattice's draws, reference order: eps[k * D + map[i]] for the column latents of one class row
+template <typename real>
+__global__ void noise_columns_kernel(const SegList segs, int cpad, int row, int is_bc, const uint32_t *col_id,
+                                     const int *map_row, int K, long long D, uint32_t step, uint32_t seed0,
+                                     uint32_t seed1, double *eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cpad) return;
+    const int m = map_row[c];
+    if (m < 0) return;
+    int si = 0;
+    for (int i = 1; i < segs.nseg; ++i) if (c >= segs.seg[i].col0) si = i;
+    const Seg &sg = segs.seg[si];
+    const uint32_t colid = col_id ? col_id[c] : sg.colid0 + (uint32_t)(c - sg.col0);
+    const int slot = is_bc ? sg.nt + row : row;
+    for (int k = 0; k < K; ++k) {
+        real n[4];
+        normals4<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)(slot >> 2), (uint32_t)k, step, seed0, seed1, n);
+        const int l = slot & 3;
+        eps[(size_t)k * D + m] = (double)(l == 0 ? n[0] : l == 1 ? n[1] : l == 2 ? n[2] : n[3]);
+    }
+}
+
+template <typename real>
+__global__ void noise_stream_kernel(uint32_t stream, uint32_t slot0, const int *map, int n, int K, long long D,
+                                    uint32_t step, uint32_t seed0, uint32_t seed1, int as_double, double *eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int m = map[i];
+    if (m < 0) return;
+    for (int k = 0; k < K; ++k) {
+        const double e = as_double ? stream_normal<double>(stream, slot0 + (uint32_t)i, (uint32_t)k, step, seed0, seed1)
+                                   : (double)stream_normal<real>(stream, slot0 + (uint32_t)i, (uint32_t)k, step,
+                                                                 seed0, seed1);
+        eps[(size_t)k * D + m] = e;
+    }
+}
+
+}  // namespace bb

@@ -1,0 +1,151 @@
+// extern "C" surface declared in include/barbay_b200.h.  Every entry point catches,
+// records the message for bb_last_error() and returns a non-zero code: there is no
+// CPU fallback -- without a B200 and this library the path fails loudly.
+#include <cstring>
+#include <string>
+
+#include "../../include/barbay_b200.h"
+#include "bb_engine.cuh"
+
+struct bb_handle {
+    bb::EngineBase *eng = nullptr;
+    std::string err;
+};
+
+namespace {
+thread_local std::string g_create_error;
+
+template <typename F> int guarded(bb_handle *h, F &&f) {
+    if (!h || !h->eng) return 2;
+    try {
+        f(*h->eng);
+        h->err.clear();
+        return 0;
+    } catch (const std::exception &e) {
+        h->err = e.what();
+        cudaGetLastError();   // clear the sticky-free error state
+        return 1;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int32_t bb_abi_version(void) { return BB_ABI_VERSION; }
+
+int bb_create(const bb_desc *desc, bb_handle **out) {
+    if (!desc || !out) { g_create_error = "bb_create: NULL argument"; return 2; }
+    *out = nullptr;
+    try {
+        int ndev = 0;
+        cudaError_t ce = cudaGetDeviceCount(&ndev);
+        if (ce != cudaSuccess || ndev == 0)
+            throw std::runtime_error(std::string("no CUDA device available (") + cudaGetErrorString(ce) +
+                                     "); barbay_b200 has no CPU fallback");
+        bb_handle *h = new bb_handle;
+        h->eng = desc->dtype == BB_F64 ? bb::make_engine_f64(*desc) : bb::make_engine_f32(*desc);
+        *out = h;
+        g_create_error.clear();
+        return 0;
+    } catch (const std::exception &e) {
+        g_create_error = e.what();
+        cudaGetLastError();
+        return 1;
+    }
+}
+
+void bb_destroy(bb_handle *h) {
+    if (!h) return;
+    delete h->eng;
+    delete h;
+}
+
+const char *bb_last_error(const bb_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t bb_n_latent(const bb_handle *h) { return h && h->eng ? h->eng->L.D : -1; }
+
+int bb_init_params(bb_handle *h, uint64_t seed) {
+    return guarded(h, [&](bb::EngineBase &e) { e.init_params(seed); });
+}
+int bb_set_params(bb_handle *h, const double *mu, const double *omega) {
+    return guarded(h, [&](bb::EngineBase &e) {
+        if (!mu || !omega) throw std::runtime_error("bb_set_params: NULL argument");
+        e.set_params(mu, omega);
+    });
+}
+int bb_get_params(bb_handle *h, double *mu, double *omega) {
+    return guarded(h, [&](bb::EngineBase &e) { e.get_params(mu, omega, false); });
+}
+int bb_get_posterior(bb_handle *h, double *m, double *sigma) {
+    return guarded(h, [&](bb::EngineBase &e) { e.get_params(m, sigma, true); });
+}
+int bb_logjoint_grad(bb_handle *h, const double *x, int32_t n_samples, int32_t eps_is_noise, double *logp,
+                     double *grad) {
+    return guarded(h, [&](bb::EngineBase &e) {
+        if (!x || !logp || !grad) throw std::runtime_error("bb_logjoint_grad: NULL argument");
+        e.logjoint_grad(x, n_samples, eps_is_noise, logp, grad);
+    });
+}
+int bb_elbo_grad(bb_handle *h, const double *eps, int64_t step, double *elbo, double *grad) {
+    return guarded(h, [&](bb::EngineBase &e) { e.elbo_grad(eps, step, elbo, grad); });
+}
+int bb_get_noise(bb_handle *h, int64_t step, double *eps) {
+    return guarded(h, [&](bb::EngineBase &e) { e.get_noise(step, eps); });
+}
+int bb_set_optimizer(bb_handle *h, const bb_opt *opt) {
+    return guarded(h, [&](bb::EngineBase &e) {
+        if (!opt) throw std::runtime_error("bb_set_optimizer: NULL argument");
+        e.set_optimizer(*opt);
+    });
+}
+int bb_step(bb_handle *h, int32_t n_steps, double *elbo_trace) {
+    return guarded(h, [&](bb::EngineBase &e) {
+        if (n_steps < 0) throw std::runtime_error("bb_step: n_steps < 0");
+        e.step(n_steps, elbo_trace);
+    });
+}
+int bb_step_with_noise(bb_handle *h, const double *eps) {
+    return guarded(h, [&](bb::EngineBase &e) {
+        if (!eps) throw std::runtime_error("bb_step_with_noise: NULL argument");
+        e.step_with_noise(eps);
+    });
+}
+int64_t bb_step_count(const bb_handle *h) { return h && h->eng ? h->eng->step_count : -1; }
+int64_t bb_state_size(const bb_handle *h) { return h && h->eng ? h->eng->state_size() : -1; }
+int bb_get_state(bb_handle *h, double *s) {
+    return guarded(h, [&](bb::EngineBase &e) { e.get_state(s); });
+}
+int bb_set_state(bb_handle *h, const double *s) {
+    return guarded(h, [&](bb::EngineBase &e) { e.set_state(s); });
+}
+int bb_set_stream(bb_handle *h, void *stream) {
+    return guarded(h, [&](bb::EngineBase &e) { e.set_stream(stream); });
+}
+int bb_sync(bb_handle *h) {
+    return guarded(h, [&](bb::EngineBase &e) { e.sync(); });
+}
+int64_t bb_launch_count(const bb_handle *h) { return h && h->eng ? h->eng->launches : -1; }
+int bb_use_graph(bb_handle *h, int32_t enable) {
+    return guarded(h, [&](bb::EngineBase &e) { e.use_graph(enable); });
+}
+double bb_algorithmic_bytes_per_step(const bb_handle *h) { return h && h->eng ? h->eng->alg_bytes : -1.0; }
+int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_main) {
+    return guarded(h, [&](bb::EngineBase &e) { e.time_steps(n_steps, ms_total, ms_main); });
+}
+int bb_comm_unique_id(char id[128]) {
+    try {
+        bb::NcclApi::UniqueId uid;
+        int rc = bb::NcclApi::get().GetUniqueId(&uid);
+        if (rc != 0) { g_create_error = "ncclGetUniqueId failed"; return 1; }
+        std::memcpy(id, uid.internal, 128);
+        return 0;
+    } catch (const std::exception &e) {
+        g_create_error = e.what();
+        return 1;
+    }
+}
+int bb_comm_init(bb_handle *h, const char id[128]) {
+    return guarded(h, [&](bb::EngineBase &e) { e.comm_init(id); });
+}
+
+}  // extern "C"

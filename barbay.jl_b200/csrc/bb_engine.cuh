@@ -1,0 +1,806 @@
+// Host engine: owns the device-resident shard, orchestrates one ADVI step as
+// pass 1 -> reduce -> (NCCL all-reduce) -> shared kernel -> pass 2 (-> hyper kernels),
+// and implements the parity entry points.  One Engine = one GPU = one host thread.
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "bb_aux_kernels.cuh"
+#include "bb_layout.h"
+
+namespace bb {
+
+#define BB_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e__) +       \
+                                     " at " __FILE__ ":" + std::to_string(__LINE__));              \
+    } while (0)
+
+// ------------------------------------------------------------------ NCCL through dlopen
+// The library binds the NCCL that torch already loaded in the process (libnccl.so.2), so
+// no link-time dependency exists and single-GPU use needs no NCCL at all.
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;
+    typedef void *Comm;
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    void *lib = nullptr;
+    static NcclApi &get() {
+        static NcclApi api;
+        if (!api.lib) {
+            api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+            if (!api.lib) api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (!api.lib) throw std::runtime_error(std::string("cannot load libnccl.so.2: ") + dlerror());
+            auto sym = [&](const char *n) {
+                void *p = dlsym(api.lib, n);
+                if (!p) throw std::runtime_error(std::string("NCCL symbol missing: ") + n);
+                return p;
+            };
+            api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+            api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+            api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+            api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+            api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+        }
+        return api;
+    }
+};
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+
+template <typename T> struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DBuf() = default;
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    ~DBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t count, bool zero = true) {
+        release();
+        n = count;
+        if (count == 0) return;
+        BB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        if (zero) BB_CUDA(cudaMemset(p, 0, count * sizeof(T)));
+    }
+    void ensure(size_t count) { if (n < count) alloc(count); }
+    void upload(const std::vector<T> &h) {
+        alloc(h.size(), false);
+        if (!h.empty()) BB_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+};
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+class EngineBase {
+  public:
+    virtual ~EngineBase() {}
+    std::string err;
+    Layout L;
+    virtual void init_params(uint64_t seed) = 0;
+    virtual void set_params(const double *mu, const double *omega) = 0;
+    virtual void get_params(double *mu, double *omega, bool posterior) = 0;
+    virtual void logjoint_grad(const double *x, int K, int eps_is_noise, double *logp, double *grad) = 0;
+    virtual void elbo_grad(const double *eps, long long step, double *elbo, double *grad) = 0;
+    virtual void get_noise(long long step, double *eps) = 0;
+    virtual void set_optimizer(const bb_opt &o) = 0;
+    virtual void step(int n, double *trace) = 0;
+    virtual void step_with_noise(const double *eps) = 0;
+    virtual long long state_size() const = 0;
+    virtual void get_state(double *s) = 0;
+    virtual void set_state(const double *s) = 0;
+    virtual void set_stream(void *s) = 0;
+    virtual void sync() = 0;
+    virtual void time_steps(int n, float *ms_total, float *ms_main) = 0;
+    virtual void comm_init(const char id[128]) = 0;
+    virtual void use_graph(int enable) = 0;
+    long long launches = 0;
+    long long step_count = 0;
+    double alg_bytes = 0.0;
+};
+
+EngineBase *make_engine_f32(const bb_desc &d);
+EngineBase *make_engine_f64(const bb_desc &d);
+
+// =====================================================================================
+template <typename real> class Engine : public EngineBase {
+    using r2 = vec2<real>;
+
+  public:
+    explicit Engine(const bb_desc &d);
+    ~Engine() override;
+    void init_params(uint64_t seed) override;
+    void set_params(const double *mu, const double *omega) override;
+    void get_params(double *mu, double *omega, bool posterior) override;
+    void logjoint_grad(const double *x, int K, int eps_is_noise, double *logp, double *grad) override;
+    void elbo_grad(const double *eps, long long step, double *elbo, double *grad) override;
+    void get_noise(long long step, double *eps) override;
+    void set_optimizer(const bb_opt &o) override;
+    void step(int n, double *trace) override;
+    void step_with_noise(const double *eps) override;
+    long long state_size() const override;
+    void get_state(double *s) override;
+    void set_state(const double *s) override;
+    void set_stream(void *s) override { stream_ = s ? (cudaStream_t)s : own_stream_; }
+    void sync() override { BB_CUDA(cudaStreamSynchronize(stream_)); }
+    void time_steps(int n, float *ms_total, float *ms_main) override;
+    void comm_init(const char id[128]) override;
+    void use_graph(int) override {}
+
+  private:
+    struct Group {                 // replicates sharing one T: one launch of each column kernel
+        int nt = 0;
+        unsigned rep_mask = 0;
+        SegList p1segs, p2segs;
+        int p1blocks = 0, p2blocks = 0;
+        KernelSet<real> ks, ks_sup;
+        int pv = 0, kchunk = 0;
+        size_t p1smem = 0, p2smem = 0;
+        size_t part_off = 0, epart_off = 0;     // block offsets into part_ / epart_
+    };
+    struct RunMode {
+        bool sup = false;          // caller-supplied noise
+        bool z_direct = false;
+        bool update = false;
+        bool want_elbo = false;
+        bool dump = false;         // per-sample gradients
+        bool gout = false;         // (dELBO/dmu, dELBO/domega)
+        uint32_t step = 0;
+    };
+
+    void build_groups();
+    void assign_blocks(SegList &sl, int nt, int budget, int *nblocks);
+    void run_pipeline(const RunMode &m);
+    void upload_supplied(const double *x, int K);
+    void ensure_supplied(bool dump);
+    ColArrays<real> col_arrays() const;
+    OptArgs opt_args(bool update) const;
+    void zero_like_init_acc();
+    double finish_elbo(double *logp_k);
+    void gather_to_ref(const r2 *lam, const r2 *bc, const r2 *hy, const double2 *sh, double *x, double *y, bool sp);
+    template <typename F> void launch_count(F &&f) { f(); ++launches; }
+
+    int device_ = 0, nsm_ = 148;
+    cudaStream_t stream_ = nullptr, own_stream_ = nullptr;
+    uint64_t seed_ = 0;
+    bb_opt opt_{BB_OPT_TRUNCATED_ADAGRAD, 0.1, 1.0, 0.9, 100};
+    bool opt_ready_ = false;
+    int ring_slot_ = 0;
+    std::vector<Group> groups_;
+    int p1blocks_total_ = 0, p2blocks_total_ = 0, hyblocks_ = 0;
+
+    // device state
+    DBuf<r2> lam_th_, lam_acc_, bc_th_, bc_acc_, hy_th_, hy_acc_, lam_ring_, bc_ring_, hy_ring_;
+    DBuf<double2> sh_th_, sh_acc_, sh_ring_, sh_pr_, sh_gout_;
+    DBuf<r2> lam_pr_, bc_pr_, hy_pr_;
+    DBuf<int> cnt_, map_lam_, map_bc_, map_hy_, map_sh_, hgroup_, csr_off_, csr_mem_;
+    DBuf<uint32_t> col_id_;
+    DBuf<double> part_, sums_, epart_, hy_epart_, elbo_sh_, elbo_out_, sh_scratch_;
+    DBuf<real> ctx_;
+    DBuf<r2> zeps_, hcontrib_;
+    // parity / gradient outputs
+    DBuf<real> sup_lam_, sup_bc_, sup_hy_, dump_lam_, dump_bc_, dump_hy_, dump_hc_;
+    DBuf<double> sup_sh_, dump_sh_, hostvec_a_, hostvec_b_;
+    DBuf<r2> gout_lam_, gout_bc_, gout_hy_;
+    DBuf<double> trace_;
+    // comm
+    NcclApi::Comm comm_ = nullptr;
+    cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+// ------------------------------------------------------------------ construction
+template <typename real> Engine<real>::Engine(const bb_desc &d) {
+    build_layout(d, L);
+    seed_ = d.seed;
+    if (d.device >= 0) BB_CUDA(cudaSetDevice(d.device));
+    BB_CUDA(cudaGetDevice(&device_));
+    cudaDeviceProp prop;
+    BB_CUDA(cudaGetDeviceProperties(&prop, device_));
+    if (prop.major != 10)
+        throw std::runtime_error("barbay_b200 is built for sm_100a (B200) only; device reports sm_" +
+                                 std::to_string(prop.major) + std::to_string(prop.minor));
+    nsm_ = prop.multiProcessorCount;
+    BB_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+    stream_ = own_stream_;
+    for (auto &e : ev_) BB_CUDA(cudaEventCreate(&e));
+
+    const size_t nlam = (size_t)L.tmax * L.cpad, nbc = (size_t)L.nj * L.cpad;
+    lam_th_.alloc(nlam); lam_acc_.alloc(nlam);
+    bc_th_.alloc(nbc); bc_acc_.alloc(nbc);
+    cnt_.upload(L.cnt);
+    map_lam_.upload(L.map_lam); map_bc_.upload(L.map_bc); map_sh_.upload(L.map_sh);
+    if (!L.perm_identity) col_id_.upload(L.col_id);
+    sh_th_.alloc(2 * L.nst); sh_acc_.alloc(2 * L.nst); sh_gout_.alloc(2 * L.nst);
+    {
+        std::vector<double2> p(2 * L.nst);
+        for (int i = 0; i < 2 * L.nst; ++i) p[i] = make_double2(L.pr_sh[2 * i], L.pr_sh[2 * i + 1]);
+        sh_pr_.upload(p);
+    }
+    auto to_r2 = [](const std::vector<double> &v) {
+        std::vector<r2> o(v.size() / 2);
+        for (size_t i = 0; i < o.size(); ++i) o[i] = r2{(real)v[2 * i], (real)v[2 * i + 1]};
+        return o;
+    };
+    if (L.lam_pr_matrix) lam_pr_.upload(to_r2(L.pr_lam));
+    if (L.bc_pr_matrix) bc_pr_.upload(to_r2(L.pr_bc));
+    if (L.hier) {
+        hy_th_.alloc(L.H); hy_acc_.alloc(L.H);
+        hy_pr_.upload(to_r2(L.pr_hy));
+        map_hy_.upload(L.map_hy);
+        hgroup_.upload(L.hgroup);
+        csr_off_.upload(L.csr_off); csr_mem_.upload(L.csr_mem);
+        zeps_.alloc((size_t)L.K * std::max(L.H, 1));
+        hcontrib_.alloc((size_t)L.E * L.cpad);
+        hyblocks_ = cdiv(std::max(L.H, 1), BLOCK);
+        hy_epart_.alloc((size_t)hyblocks_ * (L.K + 1));
+    }
+    sums_.alloc((size_t)L.R * L.K * NQ * L.tmax);
+    ctx_.alloc((size_t)L.R * L.K * 3 * L.tmax);
+    sh_scratch_.alloc((size_t)L.K * 2 * L.nst);
+    elbo_sh_.alloc(L.K + 1);
+    elbo_out_.alloc(L.K + 1);
+    build_groups();
+    part_.alloc((size_t)p1blocks_total_ * L.K * (3 * L.tmax));
+    epart_.alloc((size_t)p2blocks_total_ * (L.K + 1));
+
+    // algorithmic bytes per step of this shard: theta + accumulators read and written
+    // once, int32 counts read once; matrix priors read once.
+    const double w = sizeof(real);
+    double dloc = 0;   // latents owned by the shard
+    for (int m : L.map_lam) dloc += m >= 0;
+    for (int m : L.map_bc) dloc += m >= 0;
+    dloc += L.H + (L.rank == 0 ? 2.0 * L.nst : 0.0);
+    double ncnt = 0;
+    for (const HostSeg &s : L.segs) ncnt += (double)s.ncol * s.nt;
+    alg_bytes = 8.0 * w * dloc + 4.0 * ncnt;
+    if (L.lam_pr_matrix) alg_bytes += 2.0 * w * ncnt;
+    bb_opt def{BB_OPT_TRUNCATED_ADAGRAD, 0.1, 1.0, 0.9, 100};
+    opt_ = def;
+}
+
+template <typename real> Engine<real>::~Engine() {
+    if (comm_) NcclApi::get().CommDestroy(comm_);
+    for (auto &e : ev_) if (e) cudaEventDestroy(e);
+    if (own_stream_) cudaStreamDestroy(own_stream_);
+}
+
+template <typename real> void Engine<real>::assign_blocks(SegList &sl, int nt, int budget, int *nblocks) {
+    // proportional split of the persistent grid among the segments of this launch
+    long long tiles_total = 0;
+    std::vector<int> tiles;
+    for (const HostSeg &s : L.segs)
+        if (s.nt == nt) { tiles.push_back(cdiv(s.ncol, BLOCK)); tiles_total += tiles.back(); }
+    sl.nseg = 0;
+    int blk = 0, idx = 0;
+    for (const HostSeg &s : L.segs) {
+        if (s.nt != nt) continue;
+        Seg g;
+        g.col0 = s.col0; g.ncol = s.ncol; g.rep = s.rep; g.nt = s.nt; g.neutral = s.neutral;
+        g.colid0 = s.colid0; g.sh0 = s.sh0;
+        long long want = tiles_total ? (long long)budget * tiles[idx] / tiles_total : 1;
+        int nb = (int)std::max<long long>(1, std::min<long long>(want, tiles[idx]));
+        g.blk0 = blk; g.blk1 = blk + nb;
+        blk += nb;
+        sl.seg[sl.nseg++] = g;
+        ++idx;
+    }
+    *nblocks = blk;
+}
+
+template <typename real> void Engine<real>::build_groups() {
+    std::vector<int> distinct;
+    for (int r = 0; r < L.R; ++r)
+        if (std::find(distinct.begin(), distinct.end(), L.nt[r]) == distinct.end()) distinct.push_back(L.nt[r]);
+    const size_t smem_limit = 112 * 1024;
+    size_t part_off = 0, epart_off = 0;
+    for (int nt : distinct) {
+        Group g;
+        g.nt = nt;
+        for (int r = 0; r < L.R; ++r) if (L.nt[r] == nt) g.rep_mask |= 1u << r;
+        if (!lookup_kernels<real>(nt, L.E, L.hier, false, &g.ks) ||
+            !lookup_kernels<real>(nt, L.E, L.hier, true, &g.ks_sup))
+            throw std::runtime_error("no kernel instantiation for this shape");
+        g.pv = nt + 2 * (nt - 1);
+        const size_t per_k = (size_t)g.pv * BLOCK * sizeof(real);
+        const int sweeps = (int)((L.K * per_k + smem_limit - 1) / smem_limit);
+        g.kchunk = (L.K + sweeps - 1) / sweeps;
+        g.p1smem = (size_t)g.kchunk * per_k;
+        const size_t ctx_b = (((size_t)L.K * 3 * L.tmax * sizeof(real)) + 15) / 16 * 16;
+        g.p2smem = ctx_b + (size_t)(L.K + 1) * BLOCK * sizeof(double);
+        for (auto *fn : {(const void *)g.ks.pass1, (const void *)g.ks_sup.pass1})
+            BB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p1smem));
+        for (auto *fn : {(const void *)g.ks.pass2, (const void *)g.ks_sup.pass2})
+            BB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p2smem));
+        int occ1 = 1, occ2 = 1;
+        BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, g.ks.pass1, BLOCK, g.p1smem));
+        BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, g.ks.pass2, BLOCK, g.p2smem));
+        occ1 = std::max(occ1, 1); occ2 = std::max(occ2, 1);
+        assign_blocks(g.p1segs, nt, nsm_ * occ1, &g.p1blocks);
+        assign_blocks(g.p2segs, nt, nsm_ * occ2, &g.p2blocks);
+        g.part_off = part_off; g.epart_off = epart_off;
+        part_off += g.p1blocks; epart_off += g.p2blocks;
+        groups_.push_back(g);
+    }
+    p1blocks_total_ = (int)part_off;
+    p2blocks_total_ = (int)epart_off;
+}
+
+template <typename real> ColArrays<real> Engine<real>::col_arrays() const {
+    ColArrays<real> C;
+    C.cpad = L.cpad; C.tmax = L.tmax; C.nj = L.nj;
+    C.lam_th = lam_th_.p; C.lam_acc = lam_acc_.p; C.cnt = cnt_.p;
+    C.bc_th = bc_th_.p; C.bc_acc = bc_acc_.p;
+    C.lam_pr = lam_pr_.p; C.bc_pr = bc_pr_.p;
+    C.lam_pr_s = r2{(real)L.pr_lam_s[0], (real)L.pr_lam_s[1]};
+    for (int k = 0; k < 3; ++k) C.bc_pr_s[k] = r2{(real)L.pr_bc_s[k][0], (real)L.pr_bc_s[k][1]};
+    C.hgroup = hgroup_.p; C.col_id = col_id_.p;
+    C.lam_ring = lam_ring_.p; C.bc_ring = bc_ring_.p;
+    return C;
+}
+
+template <typename real> OptArgs Engine<real>::opt_args(bool update) const {
+    OptArgs o;
+    o.kind = opt_.kind; o.update = update ? 1 : 0;
+    o.eta = opt_.eta; o.tau = opt_.tau; o.post = opt_.post;
+    o.slot = ring_slot_;
+    o.ring_stride_lam = (long long)L.tmax * L.cpad;
+    o.ring_stride_bc = (long long)L.nj * L.cpad;
+    return o;
+}
+
+// ------------------------------------------------------------------ parameters
+template <typename real> void Engine<real>::init_params(uint64_t seed) {
+    const uint32_t s0 = (uint32_t)seed, s1 = (uint32_t)(seed >> 32);
+    auto run = [&](r2 *dst, const int *map, size_t n) {
+        if (!n) return;
+        init_params_kernel<real><<<cdiv(n, 256), 256, 0, stream_>>>(dst, map, (long long)n, L.D, s0, s1);
+        ++launches;
+    };
+    run(lam_th_.p, map_lam_.p, lam_th_.n);
+    run(bc_th_.p, map_bc_.p, bc_th_.n);
+    if (L.hier) run(hy_th_.p, map_hy_.p, hy_th_.n);
+    // shared latents are replicated on every rank: generate from the identity map
+    std::vector<double2> sh(2 * L.nst);
+    {
+        DBuf<int> idm;
+        std::vector<int> id(2 * L.nst);
+        for (int i = 0; i < 2 * L.nst; ++i) id[i] = i;
+        idm.upload(id);
+        DBuf<double2> tmp;
+        tmp.alloc(2 * L.nst);
+        init_params_kernel<double><<<cdiv(2 * L.nst, 128), 128, 0, stream_>>>(tmp.p, idm.p, 2 * L.nst, L.D, s0, s1);
+        ++launches;
+        BB_CUDA(cudaMemcpyAsync(sh_th_.p, tmp.p, sizeof(double2) * 2 * L.nst, cudaMemcpyDeviceToDevice, stream_));
+        BB_CUDA(cudaStreamSynchronize(stream_));
+    }
+    BB_CUDA(cudaGetLastError());
+}
+
+template <typename real> void Engine<real>::set_params(const double *mu, const double *omega) {
+    hostvec_a_.ensure(L.D); hostvec_b_.ensure(L.D);
+    BB_CUDA(cudaMemcpyAsync(hostvec_a_.p, mu, sizeof(double) * L.D, cudaMemcpyHostToDevice, stream_));
+    BB_CUDA(cudaMemcpyAsync(hostvec_b_.p, omega, sizeof(double) * L.D, cudaMemcpyHostToDevice, stream_));
+    auto run = [&](r2 *dst, const int *map, size_t n) {
+        if (!n) return;
+        scatter_pairs_kernel<real><<<cdiv(n, 256), 256, 0, stream_>>>(dst, map, (long long)n, hostvec_a_.p,
+                                                                      hostvec_b_.p, 0.0, 0.0);
+        ++launches;
+    };
+    run(lam_th_.p, map_lam_.p, lam_th_.n);
+    run(bc_th_.p, map_bc_.p, bc_th_.n);
+    if (L.hier) run(hy_th_.p, map_hy_.p, hy_th_.n);
+    // shared latents: first 2 nst reference entries, on every rank
+    std::vector<double2> sh(2 * L.nst);
+    for (int i = 0; i < 2 * L.nst; ++i) sh[i] = make_double2(mu[i], omega[i]);
+    BB_CUDA(cudaMemcpyAsync(sh_th_.p, sh.data(), sizeof(double2) * sh.size(), cudaMemcpyHostToDevice, stream_));
+    BB_CUDA(cudaStreamSynchronize(stream_));
+    BB_CUDA(cudaGetLastError());
+}
+
+template <typename real>
+void Engine<real>::gather_to_ref(const r2 *lam, const r2 *bc, const r2 *hy, const double2 *sh, double *x, double *y,
+                                 bool sp) {
+    // x, y: device vectors of length D, zero-filled here; entries not owned by this shard stay 0
+    if (x) BB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * L.D, stream_));
+    if (y) BB_CUDA(cudaMemsetAsync(y, 0, sizeof(double) * L.D, stream_));
+    auto run = [&](const r2 *src, const int *map, size_t n) {
+        if (!n || !src) return;
+        gather_pairs_kernel<real><<<cdiv(n, 256), 256, 0, stream_>>>(src, map, (long long)n, x, y, sp ? 1 : 0);
+        ++launches;
+    };
+    run(lam, map_lam_.p, lam_th_.n);
+    run(bc, map_bc_.p, bc_th_.n);
+    if (L.hier) run(hy, map_hy_.p, hy_th_.n);
+    if (sh && L.nst) {
+        gather_pairs_kernel<double><<<cdiv(2 * L.nst, 128), 128, 0, stream_>>>(sh, map_sh_.p, 2 * L.nst, x, y,
+                                                                               sp ? 1 : 0);
+        ++launches;
+    }
+}
+
+template <typename real> void Engine<real>::get_params(double *mu, double *omega, bool posterior) {
+    hostvec_a_.ensure(L.D); hostvec_b_.ensure(L.D);
+    gather_to_ref(lam_th_.p, bc_th_.p, hy_th_.p, sh_th_.p, hostvec_a_.p, hostvec_b_.p, posterior);
+    BB_CUDA(cudaMemcpyAsync(mu, hostvec_a_.p, sizeof(double) * L.D, cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaMemcpyAsync(omega, hostvec_b_.p, sizeof(double) * L.D, cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaStreamSynchronize(stream_));
+    BB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ optimiser
+template <typename real> void Engine<real>::set_optimizer(const bb_opt &o) {
+    if (o.kind != BB_OPT_TRUNCATED_ADAGRAD && o.kind != BB_OPT_DECAYED_ADAGRAD)
+        throw std::runtime_error("opt must be TruncatedADAGrad or DecayedADAGrad");
+    if (o.kind == BB_OPT_TRUNCATED_ADAGRAD && o.n < 1) throw std::runtime_error("TruncatedADAGrad needs n >= 1");
+    opt_ = o;
+    step_count = 0;
+    ring_slot_ = 0;
+    const size_t nlam = lam_th_.n, nbc = bc_th_.n, nhy = hy_th_.n, nsh = sh_th_.n;
+    if (o.kind == BB_OPT_TRUNCATED_ADAGRAD) {
+        lam_ring_.alloc(nlam * o.n); bc_ring_.alloc(nbc * o.n);
+        if (L.hier) hy_ring_.alloc(nhy * o.n);
+        sh_ring_.alloc(nsh * o.n);
+        BB_CUDA(cudaMemsetAsync(lam_acc_.p, 0, sizeof(r2) * nlam, stream_));
+        BB_CUDA(cudaMemsetAsync(bc_acc_.p, 0, sizeof(r2) * nbc, stream_));
+        if (nhy) BB_CUDA(cudaMemsetAsync(hy_acc_.p, 0, sizeof(r2) * nhy, stream_));
+        BB_CUDA(cudaMemsetAsync(sh_acc_.p, 0, sizeof(double2) * nsh, stream_));
+    } else {
+        lam_ring_.release(); bc_ring_.release(); hy_ring_.release(); sh_ring_.release();
+        const r2 e{(real)1e-8, (real)1e-8};                 // acc = fill(1e-8) (AdvancedVI optimisers.jl)
+        fill_kernel<r2><<<cdiv(nlam, 256), 256, 0, stream_>>>(lam_acc_.p, (long long)nlam, e);
+        fill_kernel<r2><<<cdiv(nbc, 256), 256, 0, stream_>>>(bc_acc_.p, (long long)nbc, e);
+        if (nhy) fill_kernel<r2><<<cdiv(nhy, 256), 256, 0, stream_>>>(hy_acc_.p, (long long)nhy, e);
+        fill_kernel<double2><<<cdiv(nsh, 128), 128, 0, stream_>>>(sh_acc_.p, (long long)nsh, make_double2(1e-8, 1e-8));
+        launches += 3 + (nhy ? 1 : 0);
+    }
+    BB_CUDA(cudaStreamSynchronize(stream_));
+    BB_CUDA(cudaGetLastError());
+    opt_ready_ = true;
+    // TruncatedADAGrad (running-sum form) adds an evicted-slot read and a new-slot write per component
+    const double w = sizeof(real);
+    double dloc = 0;
+    for (int m : L.map_lam) dloc += m >= 0;
+    for (int m : L.map_bc) dloc += m >= 0;
+    dloc += L.H + (L.rank == 0 ? 2.0 * L.nst : 0.0);
+    double ncnt = 0;
+    for (const HostSeg &s : L.segs) ncnt += (double)s.ncol * s.nt;
+    alg_bytes = (o.kind == BB_OPT_TRUNCATED_ADAGRAD ? 12.0 : 8.0) * w * dloc + 4.0 * ncnt;
+    if (L.lam_pr_matrix) alg_bytes += 2.0 * w * ncnt;
+}
+
+// ------------------------------------------------------------------ supplied noise plumbing
+template <typename real> void Engine<real>::ensure_supplied(bool dump) {
+    const size_t K = L.K;
+    sup_lam_.ensure(K * lam_th_.n); sup_bc_.ensure(K * std::max<size_t>(bc_th_.n, 1));
+    sup_sh_.ensure(K * 2 * L.nst);
+    if (L.hier) sup_hy_.ensure(K * std::max<size_t>(hy_th_.n, 1));
+    if (dump) {
+        dump_lam_.ensure(K * lam_th_.n); dump_bc_.ensure(K * std::max<size_t>(bc_th_.n, 1));
+        dump_sh_.ensure(K * 2 * L.nst);
+        if (L.hier) { dump_hy_.ensure(K * std::max<size_t>(hy_th_.n, 1)); dump_hc_.ensure(K * (size_t)L.E * L.cpad); }
+    }
+}
+
+template <typename real> void Engine<real>::upload_supplied(const double *x, int K) {
+    // x: host [K][D] reference order -> device layout rows
+    hostvec_a_.ensure((size_t)K * L.D);
+    BB_CUDA(cudaMemcpyAsync(hostvec_a_.p, x, sizeof(double) * K * L.D, cudaMemcpyHostToDevice, stream_));
+    auto run = [&](real *dst, const int *map, size_t n) {
+        if (!n) return;
+        scatter_rows_kernel<real><<<cdiv(n, 256), 256, 0, stream_>>>(dst, map, (long long)n, K, hostvec_a_.p, L.D);
+        ++launches;
+    };
+    run(sup_lam_.p, map_lam_.p, lam_th_.n);
+    run(sup_bc_.p, map_bc_.p, bc_th_.n);
+    if (L.hier) run(sup_hy_.p, map_hy_.p, hy_th_.n);
+    // shared: the first 2 nst entries of each row (every rank)
+    BB_CUDA(cudaMemcpy2DAsync(sup_sh_.p, sizeof(double) * 2 * L.nst, hostvec_a_.p, sizeof(double) * L.D,
+                              sizeof(double) * 2 * L.nst, K, cudaMemcpyDeviceToDevice, stream_));
+}
+
+// ------------------------------------------------------------------ the step pipeline
+template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
+    const uint32_t s0 = (uint32_t)seed_, s1 = (uint32_t)(seed_ >> 32);
+    const ColArrays<real> C = col_arrays();
+    SupArgs<real> sup{};
+    if (m.sup) {
+        sup.eps_lam = sup_lam_.p; sup.eps_bc = sup_bc_.p; sup.z_direct = m.z_direct ? 1 : 0;
+        if (m.dump) { sup.dump_lam = dump_lam_.p; sup.dump_bc = dump_bc_.p; sup.dump_hcontrib = L.hier ? dump_hc_.p : nullptr; }
+    }
+    HyperArgs<real> ha{};
+    if (L.hier) {
+        ha.H = L.H; ha.K = L.K; ha.gid0 = L.hy_gid0;
+        ha.hy_th = hy_th_.p; ha.hy_acc = hy_acc_.p; ha.hy_ring = hy_ring_.p; ha.hy_pr = hy_pr_.p;
+        ha.zeps = zeps_.p; ha.seed0 = s0; ha.seed1 = s1; ha.step = m.step;
+        ha.eps_hy = m.sup ? sup_hy_.p : nullptr; ha.z_direct = m.z_direct ? 1 : 0;
+        ha.csr_off = csr_off_.p; ha.csr_mem = csr_mem_.p; ha.hcontrib = hcontrib_.p;
+        ha.dump_hcontrib = m.dump ? dump_hc_.p : nullptr; ha.dump_stride = (long long)L.E * L.cpad;
+        ha.dump = m.dump ? dump_hy_.p : nullptr;
+        ha.gout = m.gout ? gout_hy_.p : nullptr;
+        ha.epart = m.want_elbo ? hy_epart_.p : nullptr;
+        ha.opt = opt_args(m.update);
+        if (L.H > 0) {
+            hyper_prep_kernel<real><<<hyblocks_, BLOCK, 0, stream_>>>(ha);
+            ++launches;
+        }
+    }
+    // ---- pass 1
+    for (Group &g : groups_) {
+        P1Args<real> a{};
+        a.segs = g.p1segs; a.cols = C; a.K = L.K; a.kchunk = g.kchunk; a.ne = L.E;
+        for (int t = 0; t < MAX_NT_DYN; ++t) a.env_of_t[t] = L.env_of_t[t];
+        a.seed0 = s0; a.seed1 = s1; a.step = m.step;
+        a.hy_zeps = zeps_.p; a.H = L.H;
+        a.part = part_.p + (size_t)g.part_off * L.K * (3 * L.tmax);
+        a.pv = g.pv; a.sup = sup;
+        (m.sup ? g.ks_sup.pass1 : g.ks.pass1)<<<g.p1blocks, BLOCK, g.p1smem, stream_>>>(a);
+        ++launches;
+        ReduceArgs ra{};
+        ra.segs = g.p1segs; ra.K = L.K; ra.tmax = L.tmax; ra.pv = g.pv; ra.nt = g.nt;
+        ra.w_single = L.E == 1 ? 1 : 0; ra.rep_mask = g.rep_mask;
+        ra.part = a.part; ra.sums = sums_.p;
+        const int nwarps = L.R * L.K * NQ * L.tmax;
+        reduce_kernel<<<cdiv((long long)nwarps * 32, 128), 128, 0, stream_>>>(ra, L.R);
+        ++launches;
+    }
+    if (comm_) {
+        int rc = NcclApi::get().AllReduce(sums_.p, sums_.p, sums_.n, kNcclFloat64, kNcclSum, comm_, stream_);
+        if (rc != 0) throw std::runtime_error(std::string("ncclAllReduce: ") + NcclApi::get().GetErrorString(rc));
+    }
+    // ---- shared latents
+    {
+        SharedArgs<real> sa{};
+        sa.R = L.R; sa.K = L.K; sa.tmax = L.tmax; sa.nst = L.nst;
+        for (int r = 0; r < L.R; ++r) { sa.nt[r] = L.nt[r]; sa.sh0[r] = L.sh0[r]; }
+        sa.n_neutral = (double)L.N;
+        sa.sums = sums_.p; sa.sh_th = sh_th_.p; sa.sh_acc = sh_acc_.p; sa.sh_ring = sh_ring_.p; sa.sh_pr = sh_pr_.p;
+        sa.seed0 = s0; sa.seed1 = s1; sa.step = m.step;
+        sa.eps_sh = m.sup ? sup_sh_.p : nullptr; sa.z_direct = m.z_direct ? 1 : 0;
+        sa.ctx = ctx_.p; sa.scratch = sh_scratch_.p;
+        sa.gout = m.gout ? sh_gout_.p : nullptr;
+        sa.dump = m.dump ? dump_sh_.p : nullptr;
+        sa.elbo_sh = m.want_elbo ? elbo_sh_.p : nullptr;
+        sa.opt = opt_args(m.update);
+        sa.leader = L.rank == 0 ? 1 : 0;
+        shared_kernel<real><<<1, 128, 0, stream_>>>(sa);
+        ++launches;
+    }
+    // ---- pass 2
+    for (Group &g : groups_) {
+        P2Args<real> a{};
+        a.segs = g.p2segs; a.cols = C; a.K = L.K; a.ne = L.E;
+        for (int t = 0; t < MAX_NT_DYN; ++t) a.env_of_t[t] = L.env_of_t[t];
+        a.seed0 = s0; a.seed1 = s1; a.step = m.step;
+        a.hy_zeps = zeps_.p; a.H = L.H;
+        a.ctx = ctx_.p; a.tmax_ctx = L.tmax;
+        a.opt = opt_args(m.update);
+        a.gout_lam = m.gout ? gout_lam_.p : nullptr; a.gout_bc = m.gout ? gout_bc_.p : nullptr;
+        a.hcontrib = hcontrib_.p;
+        a.epart = m.want_elbo ? epart_.p + (size_t)g.epart_off * (L.K + 1) : nullptr;
+        a.sup = sup;
+        (m.sup ? g.ks_sup.pass2 : g.ks.pass2)<<<g.p2blocks, BLOCK, g.p2smem, stream_>>>(a);
+        ++launches;
+    }
+    if (L.hier && L.H > 0) {
+        hyper_update_kernel<real><<<hyblocks_, BLOCK, (size_t)(L.K + 1) * BLOCK * sizeof(double), stream_>>>(ha);
+        ++launches;
+    }
+    if (m.want_elbo) {
+        elbo_sum_kernel<<<L.K + 1, 128, 0, stream_>>>(epart_.p, p2blocks_total_, (L.hier && L.H > 0) ? hy_epart_.p : nullptr,
+                                                     (L.hier && L.H > 0) ? hyblocks_ : 0, elbo_sh_.p, L.K, elbo_out_.p);
+        ++launches;
+    }
+    BB_CUDA(cudaGetLastError());
+}
+
+// ELBO from elbo_out_ (device): (1/K) sum_k (logp_k) + sum log sigma + D (1 + log 2 pi) / 2
+template <typename real> double Engine<real>::finish_elbo(double *logp_k) {
+    std::vector<double> out(L.K + 1);
+    if (comm_) {
+        int rc = NcclApi::get().AllReduce(elbo_out_.p, elbo_out_.p, L.K + 1, kNcclFloat64, kNcclSum, comm_, stream_);
+        if (rc != 0) throw std::runtime_error("ncclAllReduce (elbo) failed");
+    }
+    BB_CUDA(cudaMemcpyAsync(out.data(), elbo_out_.p, sizeof(double) * (L.K + 1), cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaStreamSynchronize(stream_));
+    double mean = 0.0;
+    for (int k = 0; k < L.K; ++k) {
+        const double lp = out[k] + L.logp_const;
+        if (logp_k) logp_k[k] = lp;
+        mean += lp / L.K;
+    }
+    return mean + out[L.K] + 0.5 * (double)L.D * (1.0 + std::log(2.0 * M_PI));
+}
+
+template <typename real>
+void Engine<real>::logjoint_grad(const double *x, int K, int eps_is_noise, double *logp, double *grad) {
+    if (K != L.K) throw std::runtime_error("n_samples must equal the handle's samples_per_step");
+    ensure_supplied(true);
+    upload_supplied(x, K);
+    RunMode m; m.sup = true; m.z_direct = !eps_is_noise; m.want_elbo = true; m.dump = true;
+    run_pipeline(m);
+    finish_elbo(logp);
+    // gather the per-sample gradients to reference order
+    hostvec_b_.ensure((size_t)K * L.D);
+    BB_CUDA(cudaMemsetAsync(hostvec_b_.p, 0, sizeof(double) * K * L.D, stream_));
+    auto run = [&](const real *src, const int *map, size_t n) {
+        if (!n) return;
+        gather_rows_kernel<real><<<cdiv(n, 256), 256, 0, stream_>>>(src, map, (long long)n, K, hostvec_b_.p, L.D);
+        ++launches;
+    };
+    run(dump_lam_.p, map_lam_.p, lam_th_.n);
+    run(dump_bc_.p, map_bc_.p, bc_th_.n);
+    if (L.hier) run(dump_hy_.p, map_hy_.p, hy_th_.n);
+    if (L.rank == 0)
+        BB_CUDA(cudaMemcpy2DAsync(hostvec_b_.p, sizeof(double) * L.D, dump_sh_.p, sizeof(double) * 2 * L.nst,
+                                  sizeof(double) * 2 * L.nst, K, cudaMemcpyDeviceToDevice, stream_));
+    BB_CUDA(cudaMemcpyAsync(grad, hostvec_b_.p, sizeof(double) * K * L.D, cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaStreamSynchronize(stream_));
+    BB_CUDA(cudaGetLastError());
+}
+
+template <typename real> void Engine<real>::elbo_grad(const double *eps, long long step, double *elbo, double *grad) {
+    gout_lam_.ensure(lam_th_.n); gout_bc_.ensure(std::max<size_t>(bc_th_.n, 1));
+    if (L.hier) gout_hy_.ensure(std::max<size_t>(hy_th_.n, 1));
+    RunMode m; m.want_elbo = true; m.gout = true; m.step = (uint32_t)step;
+    if (eps) { ensure_supplied(false); upload_supplied(eps, L.K); m.sup = true; }
+    run_pipeline(m);
+    const double e = finish_elbo(nullptr);
+    if (elbo) *elbo = e;
+    if (grad) {
+        hostvec_a_.ensure(L.D); hostvec_b_.ensure(L.D);
+        gather_to_ref(gout_lam_.p, gout_bc_.p, gout_hy_.p, sh_gout_.p, hostvec_a_.p, hostvec_b_.p, false);
+        BB_CUDA(cudaMemcpyAsync(grad, hostvec_a_.p, sizeof(double) * L.D, cudaMemcpyDeviceToHost, stream_));
+        BB_CUDA(cudaMemcpyAsync(grad + L.D, hostvec_b_.p, sizeof(double) * L.D, cudaMemcpyDeviceToHost, stream_));
+        BB_CUDA(cudaStreamSynchronize(stream_));
+    }
+    BB_CUDA(cudaGetLastError());
+}
+
+template <typename real> void Engine<real>::get_noise(long long step, double *eps) {
+    const uint32_t s0 = (uint32_t)seed_, s1 = (uint32_t)(seed_ >> 32);
+    const size_t n = (size_t)L.K * L.D;
+    hostvec_a_.ensure(n);
+    BB_CUDA(cudaMemsetAsync(hostvec_a_.p, 0, sizeof(double) * n, stream_));
+    SegList sl{};
+    for (const HostSeg &s : L.segs) {
+        Seg g{}; g.col0 = s.col0; g.ncol = s.ncol; g.rep = s.rep; g.nt = s.nt; g.neutral = s.neutral; g.colid0 = s.colid0;
+        sl.seg[sl.nseg++] = g;
+    }
+    for (int t = 0; t < L.tmax; ++t) {
+        noise_columns_kernel<real><<<cdiv(L.cpad, 128), 128, 0, stream_>>>(sl, L.cpad, t, 0, col_id_.p,
+            map_lam_.p + (size_t)t * L.cpad, L.K, L.D, (uint32_t)step, s0, s1, hostvec_a_.p);
+        ++launches;
+    }
+    for (int j = 0; j < L.nj; ++j) {
+        noise_columns_kernel<real><<<cdiv(L.cpad, 128), 128, 0, stream_>>>(sl, L.cpad, j, 1, col_id_.p,
+            map_bc_.p + (size_t)j * L.cpad, L.K, L.D, (uint32_t)step, s0, s1, hostvec_a_.p);
+        ++launches;
+    }
+    if (L.hier && L.H > 0) {
+        noise_stream_kernel<real><<<cdiv(L.H, 128), 128, 0, stream_>>>(STREAM_HYPER, L.hy_gid0, map_hy_.p, L.H, L.K,
+                                                                       L.D, (uint32_t)step, s0, s1, 0, hostvec_a_.p);
+        ++launches;
+    }
+    if (L.nst) {
+        noise_stream_kernel<real><<<cdiv(2 * L.nst, 128), 128, 0, stream_>>>(STREAM_SHARED, 0u, map_sh_.p, 2 * L.nst,
+                                                                             L.K, L.D, (uint32_t)step, s0, s1, 1,
+                                                                             hostvec_a_.p);
+        ++launches;
+    }
+    BB_CUDA(cudaMemcpyAsync(eps, hostvec_a_.p, sizeof(double) * n, cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaStreamSynchronize(stream_));
+    BB_CUDA(cudaGetLastError());
+}
+
+template <typename real> void Engine<real>::step(int n, double *trace) {
+    if (!opt_ready_) set_optimizer(opt_);
+    if (trace) trace_.ensure((size_t)n * (L.K + 1));
+    for (int i = 0; i < n; ++i) {
+        RunMode m; m.update = true; m.want_elbo = trace != nullptr; m.step = (uint32_t)step_count;
+        run_pipeline(m);
+        if (trace)
+            BB_CUDA(cudaMemcpyAsync(trace_.p + (size_t)i * (L.K + 1), elbo_out_.p, sizeof(double) * (L.K + 1),
+                                    cudaMemcpyDeviceToDevice, stream_));
+        ++step_count;
+        if (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD) ring_slot_ = (int)(step_count % opt_.n);
+    }
+    if (trace) {
+        if (comm_) {
+            int rc = NcclApi::get().AllReduce(trace_.p, trace_.p, (size_t)n * (L.K + 1), kNcclFloat64, kNcclSum, comm_, stream_);
+            if (rc != 0) throw std::runtime_error("ncclAllReduce (trace) failed");
+        }
+        std::vector<double> h((size_t)n * (L.K + 1));
+        BB_CUDA(cudaMemcpyAsync(h.data(), trace_.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, stream_));
+        BB_CUDA(cudaStreamSynchronize(stream_));
+        for (int i = 0; i < n; ++i) {
+            double mean = 0.0;
+            for (int k = 0; k < L.K; ++k) mean += (h[(size_t)i * (L.K + 1) + k] + L.logp_const) / L.K;
+            trace[i] = mean + h[(size_t)i * (L.K + 1) + L.K] + 0.5 * (double)L.D * (1.0 + std::log(2.0 * M_PI));
+        }
+    }
+}
+
+template <typename real> void Engine<real>::step_with_noise(const double *eps) {
+    if (!opt_ready_) set_optimizer(opt_);
+    ensure_supplied(false);
+    upload_supplied(eps, L.K);
+    RunMode m; m.sup = true; m.update = true; m.step = (uint32_t)step_count;
+    run_pipeline(m);
+    ++step_count;
+    if (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD) ring_slot_ = (int)(step_count % opt_.n);
+    BB_CUDA(cudaStreamSynchronize(stream_));
+}
+
+template <typename real> void Engine<real>::time_steps(int n, float *ms_total, float *ms_main) {
+    if (!opt_ready_) set_optimizer(opt_);
+    BB_CUDA(cudaEventRecord(ev_[0], stream_));
+    step(n, nullptr);
+    BB_CUDA(cudaEventRecord(ev_[1], stream_));
+    BB_CUDA(cudaEventSynchronize(ev_[1]));
+    BB_CUDA(cudaEventElapsedTime(ms_total, ev_[0], ev_[1]));
+    if (ms_main) *ms_main = 0.f;
+}
+
+// ------------------------------------------------------------------ state
+template <typename real> long long Engine<real>::state_size() const { return 2 + 4 * L.D; }
+
+template <typename real> void Engine<real>::get_state(double *s) {
+    // [step_count, ring_slot, mu[D], omega[D], acc_mu[D], acc_omega[D]]; the TruncatedADAGrad ring
+    // (n x 2D) is not serialised -- a restored run restarts its window (documented in DESIGN.md).
+    s[0] = (double)step_count; s[1] = (double)ring_slot_;
+    get_params(s + 2, s + 2 + L.D, false);
+    hostvec_a_.ensure(L.D); hostvec_b_.ensure(L.D);
+    gather_to_ref(lam_acc_.p, bc_acc_.p, hy_acc_.p, sh_acc_.p, hostvec_a_.p, hostvec_b_.p, false);
+    BB_CUDA(cudaMemcpyAsync(s + 2 + 2 * L.D, hostvec_a_.p, sizeof(double) * L.D, cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaMemcpyAsync(s + 2 + 3 * L.D, hostvec_b_.p, sizeof(double) * L.D, cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaStreamSynchronize(stream_));
+}
+
+template <typename real> void Engine<real>::set_state(const double *s) {
+    if (!opt_ready_) set_optimizer(opt_);
+    set_params(s + 2, s + 2 + L.D);
+    const double *am = s + 2 + 2 * L.D, *ao = s + 2 + 3 * L.D;
+    hostvec_a_.ensure(L.D); hostvec_b_.ensure(L.D);
+    BB_CUDA(cudaMemcpyAsync(hostvec_a_.p, am, sizeof(double) * L.D, cudaMemcpyHostToDevice, stream_));
+    BB_CUDA(cudaMemcpyAsync(hostvec_b_.p, ao, sizeof(double) * L.D, cudaMemcpyHostToDevice, stream_));
+    auto run = [&](r2 *dst, const int *map, size_t n) {
+        if (!n) return;
+        scatter_pairs_kernel<real><<<cdiv(n, 256), 256, 0, stream_>>>(dst, map, (long long)n, hostvec_a_.p,
+                                                                      hostvec_b_.p, 0.0, 0.0);
+        ++launches;
+    };
+    run(lam_acc_.p, map_lam_.p, lam_acc_.n);
+    run(bc_acc_.p, map_bc_.p, bc_acc_.n);
+    if (L.hier) run(hy_acc_.p, map_hy_.p, hy_acc_.n);
+    std::vector<double2> sh(2 * L.nst);
+    for (int i = 0; i < 2 * L.nst; ++i) sh[i] = make_double2(am[i], ao[i]);
+    BB_CUDA(cudaMemcpyAsync(sh_acc_.p, sh.data(), sizeof(double2) * sh.size(), cudaMemcpyHostToDevice, stream_));
+    BB_CUDA(cudaStreamSynchronize(stream_));
+    step_count = (long long)s[0];
+    ring_slot_ = (int)s[1];
+}
+
+// ------------------------------------------------------------------ comm
+template <typename real> void Engine<real>::comm_init(const char id[128]) {
+    if (L.world == 1) return;
+    NcclApi &api = NcclApi::get();
+    NcclApi::UniqueId uid;
+    std::memcpy(uid.internal, id, 128);
+    BB_CUDA(cudaSetDevice(device_));
+    int rc = api.CommInitRank(&comm_, L.world, uid, L.rank);
+    if (rc != 0) throw std::runtime_error(std::string("ncclCommInitRank: ") + api.GetErrorString(rc));
+}
+
+}  // namespace bb

@@ -1,0 +1,465 @@
+// Column kernels of the ADVI step (sm_100a).
+//
+// One ADVI step = pass 1 (per-(replicate, time, sample) partial sums over all
+// columns: Lambda_t and the weighted log-ratio sums) -> reduce (+ NCCL all-reduce)
+// -> shared kernel (c_t, residual sums, population-latent gradient + update) ->
+// pass 2 (per-column analytic gradient of the log-joint for all K samples, fused
+// with the AdaGrad-family update of (mu, omega)).  The algebra is derived in
+// DESIGN.md §3; it restates the log-joint of src/model_fitness_normal.jl:131-271
+// (and the replicate / multienv / genotype variants) of the reference.
+//
+// Both passes regenerate the same eps from the Philox lattice instead of storing
+// z: storing would add 2*K*w bytes per latent to a step whose algorithmic traffic
+// is 8*w bytes per latent.
+#pragma once
+#include "bb_types.cuh"
+
+namespace bb {
+
+template <int NT> struct TD { static constexpr int MAX = NT > 0 ? NT : MAX_NT_DYN; };
+template <int NE> struct ED { static constexpr int MAX = NE > 0 ? NE : MAX_NE_DYN; };
+
+template <int NT, int NE, bool HIER> struct Shape {
+    static constexpr int PER = HIER ? 3 : 2;
+    static constexpr int MAXT = TD<NT>::MAX;
+    static constexpr int MAXE = ED<NE>::MAX;
+    static constexpr int MAXJ = PER * MAXE;
+    static constexpr int MAXC = ((MAXT + MAXJ + 3) / 4) * 4;   // noise slots, padded to whole Philox quads
+};
+
+__device__ __forceinline__ int find_segment(const SegList &sl, int blk) {
+    int s = 0;
+    for (int i = 1; i < sl.nseg; ++i)
+        if (blk >= sl.seg[i].blk0) s = i;
+    return s;
+}
+
+// eps for every latent of one column and one MC sample
+template <typename real, int MAXC, bool SUP>
+__device__ __forceinline__ void column_noise(real (&eps)[MAXC], int nclass, int nt, uint32_t colid, uint32_t k,
+                                             uint32_t step, uint32_t k0, uint32_t k1, const SupArgs<real> &sup,
+                                             int c, int cpad, int tmax, int nj) {
+    if constexpr (SUP) {
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            if (i >= nclass) break;
+            eps[i] = (i < nt) ? sup.eps_lam[((size_t)k * tmax + i) * cpad + c]
+                              : sup.eps_bc[((size_t)k * nj + (i - nt)) * cpad + c];
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < MAXC / 4; ++q) {
+            if (q * 4 >= nclass) break;
+            real n[4];
+            normals4<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k, step, k0, k1, n);
+            eps[4 * q + 0] = n[0]; eps[4 * q + 1] = n[1]; eps[4 * q + 2] = n[2]; eps[4 * q + 3] = n[3];
+        }
+    }
+}
+
+// ===================================================================== pass 1
+// Slots per sample (pv = nt + 2 (nt-1)):
+//   [0, nt)              Lambda_t partial            (both populations)
+//   [nt, 2nt-1)          neutral: sum d_t            mutant: sum w (d_t - s)
+//   [2nt-1, 3nt-2)       neutral: sum d_t^2          mutant: sum w        (E == 1: slot 2nt-1 only)
+template <typename real, int NT, int NE, bool HIER, bool SUP>
+__global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
+    using S = Shape<NT, NE, HIER>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    real *sacc = reinterpret_cast<real *>(smem_raw);        // [kchunk][pv][BLOCK] thread-private columns
+
+    const int tid = threadIdx.x;
+    const int sidx = find_segment(a.segs, blockIdx.x);
+    const Seg seg = a.segs.seg[sidx];
+    const int nt = NT > 0 ? NT : seg.nt;
+    const int ne = NE > 0 ? NE : a.ne;
+    const int nj = S::PER * ne;
+    const int pv = a.pv;
+    const ColArrays<real> &C = a.cols;
+    const int cpad = C.cpad;
+    const int nblk = seg.blk1 - seg.blk0;
+    const int ntile = (seg.ncol + BLOCK - 1) / BLOCK;
+
+    for (int kc0 = 0; kc0 < a.K; kc0 += a.kchunk) {
+        const int kc1 = min(a.K, kc0 + a.kchunk);
+        for (int i = tid; i < (kc1 - kc0) * pv * BLOCK; i += BLOCK) sacc[i] = real(0);
+        __syncthreads();
+
+        for (int tile = blockIdx.x - seg.blk0; tile < ntile; tile += nblk) {
+            const int i = tile * BLOCK + tid;
+            if (i >= seg.ncol) continue;
+            const int c = seg.col0 + i;
+            const uint32_t colid = C.col_id ? C.col_id[c] : seg.colid0 + (uint32_t)i;
+
+            real mu[S::MAXT], sg[S::MAXT];
+#pragma unroll
+            for (int t = 0; t < S::MAXT; ++t) {
+                if (t >= nt) break;
+                const vec2<real> th = C.lam_th[(size_t)t * cpad + c];
+                mu[t] = th.x; sg[t] = softplus(th.y);
+                if constexpr (SUP) if (a.sup.z_direct) { mu[t] = real(0); sg[t] = real(1); }
+            }
+            real mub[S::MAXJ], sgb[S::MAXJ];
+            int hbase = 0;
+            if (!seg.neutral) {
+#pragma unroll
+                for (int j = 0; j < S::MAXJ; ++j) {
+                    if (j >= nj) break;
+                    const vec2<real> th = C.bc_th[(size_t)j * cpad + c];
+                    mub[j] = th.x; sgb[j] = softplus(th.y);
+                    if constexpr (SUP) if (a.sup.z_direct) { mub[j] = real(0); sgb[j] = real(1); }
+                }
+                if constexpr (HIER) hbase = C.hgroup[c];
+            }
+            const int nclass = seg.neutral ? nt : nt + nj;
+
+            for (int k = kc0; k < kc1; ++k) {
+                real eps[S::MAXC];
+                column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.seed0, a.seed1,
+                                                 a.sup, c, cpad, C.tmax, C.nj);
+                real *acc = sacc + (size_t)(k - kc0) * pv * BLOCK + tid;
+                real z[S::MAXT];
+#pragma unroll
+                for (int t = 0; t < S::MAXT; ++t) {
+                    if (t >= nt) break;
+                    z[t] = fma(sg[t], eps[t], mu[t]);
+                    acc[t * BLOCK] += bb_exp(z[t]);
+                }
+                if (seg.neutral) {
+#pragma unroll
+                    for (int t = 0; t < S::MAXT - 1; ++t) {
+                        if (t >= nt - 1) break;
+                        const real d = z[t + 1] - z[t];
+                        acc[(nt + t) * BLOCK] += d;
+                        acc[(2 * nt - 1 + t) * BLOCK] += d * d;
+                    }
+                } else {
+                    real zs[S::MAXE], w[S::MAXE];
+#pragma unroll
+                    for (int e = 0; e < S::MAXE; ++e) {
+                        if (e >= ne) break;
+                        if constexpr (HIER) {
+                            const real zth = a.hy_zeps[(size_t)k * a.H + hbase + e].x;
+                            const real ztt = fma(sgb[3 * e], eps[nt + 3 * e], mub[3 * e]);
+                            const real ztau = fma(sgb[3 * e + 1], eps[nt + 3 * e + 1], mub[3 * e + 1]);
+                            zs[e] = fma(bb_exp(ztau), ztt, zth);
+                            w[e] = bb_exp(real(-2) * fma(sgb[3 * e + 2], eps[nt + 3 * e + 2], mub[3 * e + 2]));
+                        } else {
+                            zs[e] = fma(sgb[2 * e], eps[nt + 2 * e], mub[2 * e]);
+                            w[e] = bb_exp(real(-2) * fma(sgb[2 * e + 1], eps[nt + 2 * e + 1], mub[2 * e + 1]));
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < S::MAXT - 1; ++t) {
+                        if (t >= nt - 1) break;
+                        const int e = NE == 1 ? 0 : a.env_of_t[t + 1];
+                        acc[(nt + t) * BLOCK] += w[e] * (z[t + 1] - z[t] - zs[e]);
+                        if (NE != 1) acc[(2 * nt - 1 + t) * BLOCK] += w[e];
+                    }
+                    if (NE == 1) acc[(2 * nt - 1) * BLOCK] += w[0];
+                }
+            }
+        }
+        __syncthreads();
+        // block reduction of the private columns, in double, fixed order
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int row = warp; row < (kc1 - kc0) * pv; row += BLOCK / 32) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < BLOCK / 32; ++j) s += (double)sacc[(size_t)row * BLOCK + j * 32 + lane];
+            s = warp_sum<double>(s);
+            if (lane == 0) {
+                const int kl = row / pv, v = row % pv;
+                a.part[((size_t)blockIdx.x * a.K + kc0 + kl) * pv + v] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ===================================================================== optimiser
+// AdvancedVI 0.2 optimisers.jl (restated in oracle/advi_ref.py):
+//   DecayedADAGrad   acc = post*acc + pre*g^2 ; delta = eta*g / (sqrt(acc) + 1e-8)
+//   TruncatedADAGrad s   = sum of the last n g^2 (running form: s - evicted + g^2);
+//                    delta = eta*g / (tau + sqrt(s) + 1e-8)
+template <typename real>
+__device__ __forceinline__ void opt_apply(const OptArgs &o, real g, real &theta, real &acc, real &ring_slot) {
+    const real g2 = g * g;
+    real denom;
+    if (o.kind == 1) {
+        acc = fma(real(o.post), acc, real(o.tau) * g2);
+        denom = bb_sqrt(acc) + real(1e-8);
+    } else {
+        acc = fmax(acc - ring_slot + g2, real(0));
+        ring_slot = g2;
+        denom = real(o.tau) + bb_sqrt(acc) + real(1e-8);
+    }
+    theta -= real(o.eta) * g / denom;
+}
+
+// finish one latent: gradients of the objective, update (or emit), in place
+template <typename real>
+__device__ __forceinline__ void finish_latent(const OptArgs &o, real invK, real sgrad, real sgrade, real sigma,
+                                              vec2<real> *th_ptr, vec2<real> *acc_ptr, vec2<real> *ring_ptr,
+                                              vec2<real> *gout_ptr, real mu, real om) {
+    // d ELBO / d mu = mean_k g ; d ELBO / d omega = (mean_k g eps + 1/sigma) sigmoid(omega)
+    const real gm = sgrad * invK;
+    const real go = (sgrade * invK + real(1) / sigma) * sigmoid(om);
+    if (o.update) {
+        vec2<real> ac = *acc_ptr;
+        vec2<real> rg = mk2<real>(0, 0);
+        if (o.kind == 0) rg = *ring_ptr;
+        opt_apply<real>(o, -gm, mu, ac.x, rg.x);      // the engine minimises -ELBO
+        opt_apply<real>(o, -go, om, ac.y, rg.y);
+        *th_ptr = mk2<real>(mu, om);
+        *acc_ptr = ac;
+        if (o.kind == 0) *ring_ptr = rg;
+    } else if (gout_ptr) {
+        *gout_ptr = mk2<real>(gm, go);
+    }
+}
+
+// ===================================================================== pass 2
+template <typename real, int NT, int NE, bool HIER, bool SUP>
+__global__ void __launch_bounds__(BLOCK) pass2_kernel(const P2Args<real> a) {
+    using S = Shape<NT, NE, HIER>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // smem: ctx [K][3][tmax_ctx] for this block's replicate, then ELBO private columns [K+1][BLOCK] (double)
+    real *sctx = reinterpret_cast<real *>(smem_raw);
+    const int ctx_n = a.K * 3 * a.tmax_ctx;
+    double *sel = reinterpret_cast<double *>(smem_raw + ((ctx_n * sizeof(real) + 15) / 16) * 16);
+
+    const int tid = threadIdx.x;
+    const int sidx = find_segment(a.segs, blockIdx.x);
+    const Seg seg = a.segs.seg[sidx];
+    const int nt = NT > 0 ? NT : seg.nt;
+    const int ne = NE > 0 ? NE : a.ne;
+    const int nj = S::PER * ne;
+    const ColArrays<real> &C = a.cols;
+    const int cpad = C.cpad;
+    const int nblk = seg.blk1 - seg.blk0;
+    const int ntile = (seg.ncol + BLOCK - 1) / BLOCK;
+    const bool want_elbo = a.epart != nullptr;
+    const real invK = real(1) / real(a.K);
+
+    for (int i = tid; i < ctx_n; i += BLOCK) sctx[i] = a.ctx[(size_t)seg.rep * ctx_n + i];
+    if (want_elbo)
+        for (int k = 0; k <= a.K; ++k) sel[k * BLOCK + tid] = 0.0;
+    __syncthreads();
+
+    // ratio terms per environment (the "-1" of d/dlog-sigma and the -log-sigma of the density)
+    int n_of_e[S::MAXE];
+#pragma unroll
+    for (int e = 0; e < S::MAXE; ++e) n_of_e[e] = 0;
+    if (NE == 1) n_of_e[0] = nt - 1;
+    else for (int t = 1; t < nt; ++t) n_of_e[a.env_of_t[t]] += 1;
+
+    for (int tile = blockIdx.x - seg.blk0; tile < ntile; tile += nblk) {
+        const int i = tile * BLOCK + tid;
+        if (i >= seg.ncol) continue;
+        const int c = seg.col0 + i;
+        const uint32_t colid = C.col_id ? C.col_id[c] : seg.colid0 + (uint32_t)i;
+
+        real mu[S::MAXT], om[S::MAXT], sg[S::MAXT], sgr[S::MAXT], sge[S::MAXT], cnt[S::MAXT];
+        real pm[S::MAXT], piv[S::MAXT];
+        double lsig_sum = 0.0;
+#pragma unroll
+        for (int t = 0; t < S::MAXT; ++t) {
+            if (t >= nt) break;
+            const vec2<real> th = C.lam_th[(size_t)t * cpad + c];
+            mu[t] = th.x; om[t] = th.y; sg[t] = softplus(th.y);
+            if constexpr (SUP) if (a.sup.z_direct) { mu[t] = real(0); sg[t] = real(1); }
+            cnt[t] = (real)C.cnt[(size_t)t * cpad + c];
+            const vec2<real> p = C.lam_pr ? C.lam_pr[(size_t)t * cpad + c] : C.lam_pr_s;
+            pm[t] = p.x; piv[t] = p.y;
+            sgr[t] = real(0); sge[t] = real(0);
+            if (want_elbo) lsig_sum += (double)bb_log(sg[t]);
+        }
+        real mub[S::MAXJ], omb[S::MAXJ], sgb[S::MAXJ], sgrb[S::MAXJ], sgeb[S::MAXJ], pmb[S::MAXJ], pivb[S::MAXJ];
+        real hc[S::MAXE], hce[S::MAXE];
+        int hbase = 0;
+        if (!seg.neutral) {
+#pragma unroll
+            for (int j = 0; j < S::MAXJ; ++j) {
+                if (j >= nj) break;
+                const vec2<real> th = C.bc_th[(size_t)j * cpad + c];
+                mub[j] = th.x; omb[j] = th.y; sgb[j] = softplus(th.y);
+                if constexpr (SUP) if (a.sup.z_direct) { mub[j] = real(0); sgb[j] = real(1); }
+                const vec2<real> p = C.bc_pr ? C.bc_pr[(size_t)j * cpad + c] : C.bc_pr_s[j % S::PER];
+                pmb[j] = p.x; pivb[j] = p.y;
+                sgrb[j] = real(0); sgeb[j] = real(0);
+                if (want_elbo) lsig_sum += (double)bb_log(sgb[j]);
+            }
+            if constexpr (HIER) {
+                hbase = C.hgroup[c];
+#pragma unroll
+                for (int e = 0; e < S::MAXE; ++e) { hc[e] = real(0); hce[e] = real(0); }
+            }
+        }
+        const int nclass = seg.neutral ? nt : nt + nj;
+
+        for (int k = 0; k < a.K; ++k) {
+            real eps[S::MAXC];
+            column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.seed0, a.seed1, a.sup,
+                                             c, cpad, C.tmax, C.nj);
+            const real *cE = sctx + (size_t)(k * 3 + 0) * a.tmax_ctx;   // c_t - sbar_t
+            const real *cG = sctx + (size_t)(k * 3 + 1) * a.tmax_ctx;   // (U_{t-1} - U_t) / Lambda_t
+            const real *cW = sctx + (size_t)(k * 3 + 2) * a.tmax_ctx;   // exp(-2 logsigma-bar_t)
+            real z[S::MAXT], g[S::MAXT];
+            real lp = real(0);
+#pragma unroll
+            for (int t = 0; t < S::MAXT; ++t) {
+                if (t >= nt) break;
+                z[t] = fma(sg[t], eps[t], mu[t]);
+                const real lam = bb_exp(z[t]);
+                const real dz = z[t] - pm[t];
+                // Poisson (collapsed Poisson x Multinomial) + logLambda coupling + Normal prior
+                g[t] = (cnt[t] - lam) + lam * cG[t] - dz * piv[t];
+                if (want_elbo) lp += cnt[t] * z[t] - lam - real(0.5) * dz * dz * piv[t];
+            }
+            if (seg.neutral) {
+                real uprev = real(0);
+#pragma unroll
+                for (int t = 0; t < S::MAXT - 1; ++t) {
+                    if (t >= nt - 1) break;
+                    const real res = z[t + 1] - z[t] - cE[t];
+                    const real u = cW[t] * res;
+                    g[t] += u - uprev;
+                    uprev = u;
+                }
+                g[nt - 1] -= uprev;
+            } else {
+                real zb[S::MAXJ], zs[S::MAXE], zl[S::MAXE], w[S::MAXE], gs[S::MAXE], gq[S::MAXE], extau[S::MAXE];
+                real epsth[S::MAXE];
+#pragma unroll
+                for (int j = 0; j < S::MAXJ; ++j) {
+                    if (j >= nj) break;
+                    zb[j] = fma(sgb[j], eps[nt + j], mub[j]);
+                }
+#pragma unroll
+                for (int e = 0; e < S::MAXE; ++e) {
+                    if (e >= ne) break;
+                    if constexpr (HIER) {
+                        const vec2<real> hz = a.hy_zeps[(size_t)k * a.H + hbase + e];
+                        extau[e] = bb_exp(zb[3 * e + 1]);
+                        zs[e] = fma(extau[e], zb[3 * e], hz.x);
+                        epsth[e] = hz.y;
+                        zl[e] = zb[3 * e + 2];
+                    } else {
+                        zs[e] = zb[2 * e];
+                        zl[e] = zb[2 * e + 1];
+                    }
+                    w[e] = bb_exp(real(-2) * zl[e]);
+                    gs[e] = real(0); gq[e] = real(0);
+                }
+                real uprev = real(0);
+#pragma unroll
+                for (int t = 0; t < S::MAXT - 1; ++t) {
+                    if (t >= nt - 1) break;
+                    const int e = NE == 1 ? 0 : a.env_of_t[t + 1];
+                    const real res = z[t + 1] - z[t] - zs[e] - cE[t];
+                    const real u = w[e] * res;
+                    gs[e] += u;
+                    gq[e] += u * res;
+                    g[t] += u - uprev;
+                    uprev = u;
+                }
+                g[nt - 1] -= uprev;
+                real gb[S::MAXJ];
+#pragma unroll
+                for (int e = 0; e < S::MAXE; ++e) {
+                    if (e >= ne) break;
+                    const real gls = gq[e] - (real)n_of_e[e];
+                    if constexpr (HIER) {
+                        gb[3 * e] = gs[e] * extau[e];
+                        gb[3 * e + 1] = gs[e] * extau[e] * zb[3 * e];
+                        gb[3 * e + 2] = gls;
+                        hc[e] += gs[e];
+                        hce[e] += gs[e] * epsth[e];
+                        if constexpr (SUP) if (a.sup.dump_hcontrib)
+                            a.sup.dump_hcontrib[((size_t)k * ne + e) * cpad + c] = gs[e];
+                    } else {
+                        gb[2 * e] = gs[e];
+                        gb[2 * e + 1] = gls;
+                    }
+                    if (want_elbo) lp += -(real)n_of_e[e] * zl[e] - real(0.5) * gq[e];
+                }
+#pragma unroll
+                for (int j = 0; j < S::MAXJ; ++j) {
+                    if (j >= nj) break;
+                    const real dz = zb[j] - pmb[j];
+                    gb[j] -= dz * pivb[j];
+                    if (want_elbo) lp -= real(0.5) * dz * dz * pivb[j];
+                    sgrb[j] += gb[j];
+                    sgeb[j] = fma(gb[j], eps[nt + j], sgeb[j]);
+                    if constexpr (SUP) if (a.sup.dump_bc) a.sup.dump_bc[((size_t)k * C.nj + j) * cpad + c] = gb[j];
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < S::MAXT; ++t) {
+                if (t >= nt) break;
+                sgr[t] += g[t];
+                sge[t] = fma(g[t], eps[t], sge[t]);
+                if constexpr (SUP) if (a.sup.dump_lam) a.sup.dump_lam[((size_t)k * C.tmax + t) * cpad + c] = g[t];
+            }
+            if (want_elbo) sel[k * BLOCK + tid] += (double)lp;
+        }
+        if (want_elbo) sel[a.K * BLOCK + tid] += lsig_sum;
+
+        // fused optimiser update of every latent of the column
+#pragma unroll
+        for (int t = 0; t < S::MAXT; ++t) {
+            if (t >= nt) break;
+            const size_t o = (size_t)t * cpad + c;
+            finish_latent<real>(a.opt, invK, sgr[t], sge[t], sg[t], C.lam_th + o, C.lam_acc + o,
+                                C.lam_ring ? C.lam_ring + (size_t)a.opt.slot * a.opt.ring_stride_lam + o : nullptr,
+                                a.gout_lam ? a.gout_lam + o : nullptr, mu[t], om[t]);
+        }
+        if (!seg.neutral) {
+#pragma unroll
+            for (int j = 0; j < S::MAXJ; ++j) {
+                if (j >= nj) break;
+                const size_t o = (size_t)j * cpad + c;
+                finish_latent<real>(a.opt, invK, sgrb[j], sgeb[j], sgb[j], C.bc_th + o, C.bc_acc + o,
+                                    C.bc_ring ? C.bc_ring + (size_t)a.opt.slot * a.opt.ring_stride_bc + o : nullptr,
+                                    a.gout_bc ? a.gout_bc + o : nullptr, mub[j], omb[j]);
+            }
+            if constexpr (HIER) {
+#pragma unroll
+                for (int e = 0; e < S::MAXE; ++e) {
+                    if (e >= ne) break;
+                    a.hcontrib[(size_t)e * cpad + c] = mk2<real>(hc[e], hce[e]);
+                }
+            }
+        }
+    }
+    if (want_elbo) {
+        __syncthreads();
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int row = warp; row <= a.K; row += BLOCK / 32) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < BLOCK / 32; ++j) s += sel[row * BLOCK + j * 32 + lane];
+            s = warp_sum<double>(s);
+            if (lane == 0) a.epart[(size_t)blockIdx.x * (a.K + 1) + row] = s;
+        }
+    }
+}
+
+// function-pointer bundle of one (real, NT, NE, HIER, SUP) instantiation
+template <typename real> struct KernelSet {
+    void (*pass1)(const P1Args<real>);
+    void (*pass2)(const P2Args<real>);
+};
+
+template <typename real, int NT, int NE, bool HIER, bool SUP> KernelSet<real> make_kernel_set() {
+    KernelSet<real> ks;
+    ks.pass1 = pass1_kernel<real, NT, NE, HIER, SUP>;
+    ks.pass2 = pass2_kernel<real, NT, NE, HIER, SUP>;
+    return ks;
+}
+
+// lookup implemented by the instantiation units (bb_inst_*.cu); nt / ne of 0 select the runtime-size kernels
+template <typename real> bool lookup_kernels(int nt, int ne, bool hier, bool sup, KernelSet<real> *out);
+
+}  // namespace bb

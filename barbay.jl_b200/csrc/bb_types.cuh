@@ -1,0 +1,103 @@
+// Host/device shared argument structs of the column kernels.
+//
+// Device layout ("column space").  A *column* is one barcode time series of one
+// replicate: T_r log-lambda latents plus, for mutant columns, the barcode-level
+// latents (per environment e: (s, log-sigma), or (theta-tilde, log-tau, log-sigma)
+// for hierarchical models).  Columns of one (replicate, population) pair form a
+// *segment*; segments are laid back to back in a padded column index space of
+// stride `cpad`, every segment start a multiple of 32.  All per-latent arrays are
+// class-major SoA of (mu, omega) pairs: lam[t][c], bc[j][c] -- a warp reads 32
+// consecutive pairs (256 B in fp32) per class.
+#pragma once
+#include "bb_device.cuh"
+
+namespace bb {
+
+struct Seg {
+    int col0;        // first padded column index of the segment
+    int ncol;        // valid columns (this shard)
+    int rep;         // replicate index r
+    int nt;          // time points T_r
+    int neutral;     // 1 = neutral population
+    uint32_t colid0; // canonical column id (noise lattice) of local column 0 when col_id == nullptr
+    int blk0, blk1;  // CTAs [blk0, blk1) of the launch own this segment
+    int sh0;         // offset of s-bar[r][0] inside the shared s-bar block
+};
+
+struct SegList {
+    int nseg;
+    Seg seg[MAX_SEG];
+};
+
+template <typename real> struct ColArrays {
+    int cpad;                         // padded column count = row stride of every [class][c] array
+    int tmax;                         // rows of the lam arrays
+    int nj;                           // rows of the bc arrays = per * E
+    vec2<real> *lam_th;               // [tmax][cpad] (mu, omega)
+    vec2<real> *lam_acc;              // [tmax][cpad] optimiser accumulators (a_mu, a_omega)
+    const int *cnt;                   // [tmax][cpad] barcode counts r_tb
+    vec2<real> *bc_th;                // [nj][cpad]
+    vec2<real> *bc_acc;               // [nj][cpad]
+    const vec2<real> *lam_pr;         // per-latent prior (mean, 1/var) [tmax][cpad], or nullptr -> lam_pr_s
+    const vec2<real> *bc_pr;          // [nj][cpad] or nullptr -> bc_pr_s[kind]
+    vec2<real> lam_pr_s;
+    vec2<real> bc_pr_s[3];            // by kind: direct {s, logsigma}; hier {theta-tilde, log-tau, log-sigma}
+    const int *hgroup;                // [cpad] hyper-latent base index of the column (hier), else nullptr
+    const uint32_t *col_id;           // [cpad] canonical column ids, or nullptr -> seg.colid0 + i
+    vec2<real> *lam_ring;             // TruncatedADAGrad ring [n][tmax][cpad] of (g_mu^2, g_omega^2)
+    vec2<real> *bc_ring;              // [n][nj][cpad]
+};
+
+struct OptArgs {
+    int kind;        // bb_opt_kind
+    int update;      // 1: apply the optimiser; 0: only emit gradients
+    double eta, tau, post;   // tau doubles as `pre` for DecayedADAGrad
+    int slot;        // ring slot written this step (Truncated)
+    long long ring_stride_lam, ring_stride_bc;   // elements between ring slots
+};
+
+// caller-supplied noise / per-sample dumps, device layout (SUPPLIED kernels only)
+template <typename real> struct SupArgs {
+    const real *eps_lam;   // [K][tmax][cpad]
+    const real *eps_bc;    // [K][nj][cpad]
+    int z_direct;          // 1: the supplied values are z themselves (mu, sigma ignored)
+    real *dump_lam;        // d log pi / dz per sample [K][tmax][cpad], or nullptr
+    real *dump_bc;         // [K][nj][cpad]
+    real *dump_hcontrib;   // per-sample hyper contributions [K][E][cpad] (hier)
+};
+
+template <typename real> struct P1Args {
+    SegList segs;
+    ColArrays<real> cols;
+    int K;
+    int kchunk;            // MC samples accumulated per sweep (smem budget)
+    int ne;                // E
+    int env_of_t[MAX_NT_DYN];   // 0-based environment of time point t
+    uint32_t seed0, seed1, step;
+    const vec2<real> *hy_zeps;  // [K][H] (z, eps) of the hyper latents (hier)
+    int H;
+    double *part;          // [gridDim.x][K][pv] block partial sums (double)
+    int pv;                // slots per sample: nt + 2 (nt - 1)
+    SupArgs<real> sup;
+};
+
+template <typename real> struct P2Args {
+    SegList segs;
+    ColArrays<real> cols;
+    int K;
+    int ne;
+    int env_of_t[MAX_NT_DYN];
+    uint32_t seed0, seed1, step;
+    const vec2<real> *hy_zeps;
+    int H;
+    const real *ctx;       // [R][K][3][tmax]: (c_t - sbar_t), G_Lambda_t, wbar_t
+    int tmax_ctx;
+    OptArgs opt;
+    vec2<real> *gout_lam;  // (dELBO/dmu, dELBO/domega) [tmax][cpad] when !opt.update, else nullptr
+    vec2<real> *gout_bc;   // [nj][cpad]
+    vec2<real> *hcontrib;  // [E][cpad] (sum_k g_s, sum_k g_s eps_theta) (hier)
+    double *epart;         // [gridDim.x][K+1] ELBO partials (log pi variable part per k; sum log sigma), or nullptr
+    SupArgs<real> sup;
+};
+
+}  // namespace bb

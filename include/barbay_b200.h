@@ -1,0 +1,144 @@
+/*
+ * barbay_b200.h -- C ABI of the B200-native ADVI backend for BarBay.jl.
+ *
+ * Drop-in boundary: the one statement of the reference this library replaces is
+ *     q = Turing.vi(bayes_model, advi; optimizer=opt)            (src/vi.jl:201)
+ * together with the Turing model bodies it evaluates (src/model_*.jl).  The
+ * caller (BarBay.vi.advi, src/vi.jl:86-235) packs its tidy DataFrame with
+ * utils.data_to_arrays (src/utils.jl:996-1033), hands the packed arrays to
+ * bb_create(), runs bb_step() for `max_iters` iterations and reads back
+ * (q.dist.m, q.dist.sigma) with bb_get_posterior() for the unchanged
+ * utils.advi_to_df (src/utils.jl:1409-1462).
+ *
+ * Conventions
+ *  - plain C, no torch / CUDA types in any signature; every pointer is a HOST
+ *    pointer owned by the caller unless stated otherwise; the library copies in
+ *    bb_create and owns all device memory until bb_destroy.
+ *  - latent vectors (mu, omega, m, sigma, z, eps, grad) are in the reference's
+ *    VarInfo order, length D = bb_n_latent().
+ *  - every function returns 0 on success, non-zero on error; bb_last_error()
+ *    gives the message (the Julia glue raises it with error(msg), matching the
+ *    reference's ErrorException convention, src/vi.jl:107,112,117).
+ *  - one handle = one GPU = one host thread (the reference call is synchronous
+ *    and single-threaded).  Multi-GPU: one process per GPU, each creating a handle
+ *    with its (rank, world); bb_comm_* wires the per-step NCCL all-reduce.
+ */
+#ifndef BARBAY_B200_H
+#define BARBAY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_ABI_VERSION 1
+
+typedef struct bb_handle bb_handle;
+
+/* Model variant <- name of the Turing model function (src/vi.jl:111-169 dispatches
+ * on substrings of the function name). */
+enum bb_model {
+    BB_MODEL_FITNESS_NORMAL = 0,            /* src/model_fitness_normal.jl:120-272 */
+    BB_MODEL_REPLICATE = 1,                 /* src/model_fitness_normal_hierarchical_replicates.jl:145-332, 407-638 */
+    BB_MODEL_MULTIENV = 2,                  /* src/model_multienv_fitness_normal.jl:133-303 */
+    BB_MODEL_GENOTYPE = 3,                  /* src/model_fitness_normal_hierarchical_genotypes.jl:151-330 */
+    BB_MODEL_MULTIENV_REPLICATE = 4         /* src/model_multienv_fitness_normal_hierarchical_replicates.jl:158-363 */
+};
+
+enum bb_dtype { BB_F32 = 0, BB_F64 = 1 };
+
+/* opt::Union{TruncatedADAGrad,DecayedADAGrad} (src/vi.jl:99) */
+enum bb_opt_kind { BB_OPT_TRUNCATED_ADAGRAD = 0, BB_OPT_DECAYED_ADAGRAD = 1 };
+
+/* One prior keyword (src/model_fitness_normal.jl:125-129): either the 2-vector
+ * [mean, std] (is_matrix = 0, data[0..1]) or an n x 2 Julia Matrix{Float64} in
+ * column-major memory order (is_matrix = 1: data[0..n) means, data[n..2n) stds). */
+typedef struct bb_prior {
+    const double *data;
+    int64_t n;
+    int32_t is_matrix;
+} bb_prior;
+
+typedef struct bb_opt {
+    int32_t kind;        /* enum bb_opt_kind */
+    double eta;          /* both: learning rate (default 0.1) */
+    double tau;          /* Truncated: tau (1.0)   | Decayed: pre  (1.0) */
+    double post;         /* Decayed: post (0.9)    | Truncated: unused */
+    int32_t n;           /* Truncated: window length (100) */
+} bb_opt;
+
+/* Everything data_to_arrays produced (DataArrays, src/utils.jl:48-61) plus the
+ * model keyword arguments and the ADVI settings. */
+typedef struct bb_desc {
+    int32_t abi_version;          /* BB_ABI_VERSION */
+    int32_t model;                /* enum bb_model */
+    int32_t dtype;                /* enum bb_dtype: arithmetic of the kernels */
+    int32_t n_rep;                /* R; 1 for non-replicate models */
+    const int32_t *n_time;        /* [n_rep] time points per replicate (DataArrays.n_time) */
+    int32_t n_neutral;            /* N (DataArrays.n_neutral) */
+    int32_t n_bc;                 /* M (DataArrays.n_bc) */
+    /* DataArrays.bc_count in Julia memory order: Matrix T x B, Array{Int64,3} T x B x R,
+     * or the R matrices T_r x B of a Vector{Matrix{Int64}} back to back; neutral columns first. */
+    const int64_t *bc_count;
+    int32_t n_env;                /* E; 1 unless multienv */
+    const int32_t *env_idx;       /* [n_time[0]] 1-based indexin(envs, unique(envs)) (multienv.jl:151-155) or NULL */
+    int32_t n_geno;               /* G; 0 unless genotype model */
+    const int32_t *geno_idx;      /* [n_bc] 1-based indexin(genotypes, unique(genotypes)) (genotypes.jl:170-174) or NULL */
+    bb_prior s_pop_prior, logsig_pop_prior, s_bc_prior, logsig_bc_prior, loglam_prior, logtau_prior;
+    int32_t ragged_as_written;    /* 1: reproduce the neutral pairing of replicates.jl:599-605 for unequal T (default of the reference) */
+    int32_t n_samples;            /* K = advi.samples_per_step (src/vi.jl:98) */
+    uint64_t seed;                /* key of the Philox noise lattice */
+    int32_t device;               /* CUDA ordinal, -1 = current device */
+    int32_t rank, world;          /* this handle owns shard `rank` of `world` of the barcode axis */
+} bb_desc;
+
+/* ---- lifecycle ---- */
+int bb_create(const bb_desc *desc, bb_handle **out);
+void bb_destroy(bb_handle *h);
+const char *bb_last_error(const bb_handle *h);   /* h may be NULL: error of the last failed bb_create on this thread */
+int64_t bb_n_latent(const bb_handle *h);          /* D */
+int32_t bb_abi_version(void);
+
+/* ---- variational parameters theta = (mu, omega), sigma = softplus(omega) ---- */
+int bb_init_params(bb_handle *h, uint64_t seed);                         /* meanfield(): mu, omega ~ N(0,1) */
+int bb_set_params(bb_handle *h, const double *mu, const double *omega);  /* [D] each */
+int bb_get_params(bb_handle *h, double *mu, double *omega);
+int bb_get_posterior(bb_handle *h, double *m, double *sigma);            /* q.dist.m, q.dist.sigma (utils.jl:1060) */
+
+/* ---- parity entry points (caller-supplied noise) ---- */
+/* logp[k] = log pi(z_k), grad[k*D + i] = d log pi / d z_i (z_k); z_k = eps_is_noise ? mu + sigma.*x_k : x_k. */
+int bb_logjoint_grad(bb_handle *h, const double *z_or_eps, int32_t n_samples, int32_t eps_is_noise,
+                     double *logp, double *grad);
+/* ELBO estimate and gradient of +ELBO w.r.t. (mu, omega) -> grad[2D]; eps == NULL -> Philox lattice at `step`. */
+int bb_elbo_grad(bb_handle *h, const double *eps, int64_t step, double *elbo, double *grad);
+/* The lattice's draws for `step`: eps[k*D + i]. */
+int bb_get_noise(bb_handle *h, int64_t step, double *eps);
+
+/* ---- optimisation: AdvancedVI.optimize! ---- */
+int bb_set_optimizer(bb_handle *h, const bb_opt *opt);                   /* resets accumulators and the step counter */
+int bb_step(bb_handle *h, int32_t n_steps, double *elbo_trace);          /* elbo_trace: [n_steps] or NULL */
+int bb_step_with_noise(bb_handle *h, const double *eps);                 /* one step with caller noise eps[K*D] */
+int64_t bb_step_count(const bb_handle *h);
+
+/* ---- state (checkpoint / resume; the reference keeps none) ---- */
+int64_t bb_state_size(const bb_handle *h);                               /* doubles needed by get/set_state */
+int bb_get_state(bb_handle *h, double *state);
+int bb_set_state(bb_handle *h, const double *state);
+
+/* ---- plumbing ---- */
+int bb_set_stream(bb_handle *h, void *cuda_stream);     /* run on the caller's cudaStream_t (NULL -> library stream) */
+int bb_sync(bb_handle *h);
+int64_t bb_launch_count(const bb_handle *h);            /* kernels launched by this handle so far */
+int bb_use_graph(bb_handle *h, int32_t enable);         /* capture the step sequence in a CUDA graph */
+double bb_algorithmic_bytes_per_step(const bb_handle *h);   /* SURVEY §8d figure for this shard */
+int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_main_kernels);
+
+/* ---- multi-GPU: one process per GPU; id is an ncclUniqueId (128 bytes) ---- */
+int bb_comm_unique_id(char id[128]);
+int bb_comm_init(bb_handle *h, const char id[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BARBAY_B200_H */
