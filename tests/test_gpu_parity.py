@@ -1,0 +1,152 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the reference's fixtures.
+
+Tolerances (north_star): fp64 log-joint and gradient within rel 1e-5 of the oracle for
+caller-supplied noise (we hold them to 1e-9); fp32 stated tolerance: log-joint rel 1e-4,
+gradient 2e-3 of the gradient's max-norm.
+"""
+import numpy as np
+import pytest
+
+from helpers import load_fixture, oracle_problem, plausible_latents, plausible_theta, rel_err, uneven_replicates
+
+pytestmark = pytest.mark.gpu
+
+MODELS = ["fitness_normal", "replicate_fitness_normal", "multienv_fitness_normal", "genotype_fitness_normal"]
+TOL = {"f64": dict(logp=1e-9, grad=1e-9), "f32": dict(logp=1e-4, grad=2e-3)}
+
+
+def _setup(bb, model, K, dtype, uneven=False, kwargs=None):
+    df, cols = load_fixture(model)
+    if uneven:
+        df = uneven_replicates(df)
+    da = bb.utils.data_to_arrays(df, **cols)
+    kw = dict(kwargs or {})
+    eng = bb.Engine(da, model, kw, n_samples=K, dtype=dtype, seed=1234)
+    return da, eng
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("model", MODELS)
+def test_logjoint_and_gradient_match_oracle(bb, model, dtype):
+    from oracle import model_ref
+    K = 3
+    da, eng = _setup(bb, model, K, dtype)
+    rng = np.random.default_rng(7)
+    z = plausible_latents(eng.layout, da, rng, K)
+    logp, grad = eng.logjoint_grad(z, eps_is_noise=False)
+    prob = oracle_problem(da, model)
+    assert model_ref.n_latent(model, prob) == eng.D
+    for k in range(K):
+        lp_ref, g_ref = model_ref.logjoint_and_grad(model, z[k], prob)
+        assert abs(logp[k] - lp_ref) <= TOL[dtype]["logp"] * abs(lp_ref), (k, logp[k], lp_ref)
+        assert rel_err(grad[k], g_ref) <= TOL[dtype]["grad"], (k, rel_err(grad[k], g_ref))
+    eng.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("model", MODELS)
+def test_elbo_gradient_with_supplied_noise(bb, model, dtype):
+    from oracle import advi_ref
+    K = 4
+    da, eng = _setup(bb, model, K, dtype)
+    rng = np.random.default_rng(11)
+    mu, omega = plausible_theta(eng.layout, da, rng)
+    eps = rng.standard_normal((K, eng.D))
+    eng.set_params(mu, omega)
+    elbo, g_mu, g_om = eng.elbo_grad(eps)
+    prob = oracle_problem(da, model)
+    e_ref, gm_ref, go_ref, _ = advi_ref.elbo_value_and_grad(model, prob, mu, omega, eps)
+    tol = TOL[dtype]
+    assert abs(elbo - e_ref) <= tol["logp"] * abs(e_ref), (elbo, e_ref)
+    assert rel_err(g_mu, gm_ref) <= tol["grad"], rel_err(g_mu, gm_ref)
+    assert rel_err(g_om, go_ref) <= tol["grad"], rel_err(g_om, go_ref)
+    eng.close()
+
+
+def test_uneven_replicates_corrected_pairing(bb):
+    from oracle import model_ref
+    model, K = "replicate_fitness_normal", 2
+    da, eng = _setup(bb, model, K, "f64", uneven=True)
+    assert isinstance(da.bc_count, list) and da.n_time == [5, 4]
+    rng = np.random.default_rng(3)
+    z = plausible_latents(eng.layout, da, rng, K)
+    logp, grad = eng.logjoint_grad(z)
+    prob = oracle_problem(da, model, corrected=True)
+    for k in range(K):
+        lp_ref, g_ref = model_ref.logjoint_and_grad(model, z[k], prob)
+        assert abs(logp[k] - lp_ref) <= 1e-9 * abs(lp_ref)
+        assert rel_err(grad[k], g_ref) <= 1e-9
+    eng.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("model", MODELS)
+def test_philox_lattice_matches_oracle(bb, model, dtype):
+    from oracle import philox_ref
+    K = 2
+    da, eng = _setup(bb, model, K, dtype)
+    prob = oracle_problem(da, model)
+    for step in (0, 5):
+        eps = eng.get_noise(step)
+        ref = philox_ref.noise(model, prob, K, step, 1234)
+        # fp32: MUFU lg2/sin/cos in the kernel's Box-Muller -> absolute tolerance on N(0,1) draws
+        atol = 1e-12 if dtype == "f64" else 2e-5
+        assert np.max(np.abs(eps - ref)) <= atol, np.max(np.abs(eps - ref))
+    eng.close()
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_init_params_match_oracle(bb, model):
+    from oracle import philox_ref
+    da, eng = _setup(bb, model, 1, "f64")
+    eng.init_params(99)
+    mu, om = eng.get_params()
+    mu_ref, om_ref = philox_ref.init_params(eng.D, 99)
+    assert np.max(np.abs(mu - mu_ref)) < 1e-12 and np.max(np.abs(om - om_ref)) < 1e-12
+    m, s = eng.get_posterior()
+    assert np.allclose(m, mu) and np.allclose(s, np.log1p(np.exp(om)))
+    eng.close()
+
+
+@pytest.mark.parametrize("opt", ["decayed", "truncated"])
+@pytest.mark.parametrize("model", MODELS)
+def test_optimizer_trajectory_with_supplied_noise(bb, model, opt):
+    """theta after a few steps of both AdaGrad variants == restated AdvancedVI.optimize! (fp64)."""
+    from oracle import advi_ref
+    K, n_steps = 2, 5
+    da, eng = _setup(bb, model, K, "f64")
+    rng = np.random.default_rng(21)
+    mu, omega = plausible_theta(eng.layout, da, rng)
+    noise = rng.standard_normal((n_steps, K, eng.D))
+    eng.set_params(mu, omega)
+    if opt == "decayed":
+        eng.set_optimizer("decayed", eta=0.1, pre=1.0, post=0.9)
+        ref_opt = advi_ref.DecayedADAGrad(0.1, 1.0, 0.9)
+    else:
+        eng.set_optimizer("truncated", eta=0.1, tau=1.0, n=3)     # window shorter than the run -> eviction path
+        ref_opt = advi_ref.TruncatedADAGrad(0.1, 1.0, 3)
+    for i in range(n_steps):
+        eng.step_with_noise(noise[i])
+    mu_g, om_g = eng.get_params()
+    prob = oracle_problem(da, model)
+    tr = advi_ref.advi_run(model, prob, n_steps, K, ref_opt, mu, omega, eps_fn=lambda s: noise[s])
+    assert rel_err(mu_g, tr.mu) < 1e-8, rel_err(mu_g, tr.mu)
+    assert rel_err(om_g, tr.omega) < 1e-8, rel_err(om_g, tr.omega)
+    eng.close()
+
+
+def test_philox_steps_match_oracle_trajectory(bb):
+    """bb_step (in-kernel Philox) == oracle ADVI driven by the oracle's own lattice, incl. ELBO trace."""
+    from oracle import advi_ref
+    model, K, n_steps = "fitness_normal", 2, 4
+    da, eng = _setup(bb, model, K, "f64")
+    eng.init_params(5)
+    mu0, om0 = eng.get_params()
+    eng.set_optimizer("decayed")
+    trace = eng.step(n_steps, elbo_trace=True)
+    mu_g, om_g = eng.get_params()
+    prob = oracle_problem(da, model)
+    tr = advi_ref.advi_run(model, prob, n_steps, K, advi_ref.DecayedADAGrad(), mu0, om0, seed=1234)
+    assert rel_err(trace, np.asarray(tr.elbo)) < 1e-9
+    assert rel_err(mu_g, tr.mu) < 1e-8 and rel_err(om_g, tr.omega) < 1e-8
+    eng.close()
