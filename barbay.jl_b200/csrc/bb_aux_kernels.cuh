@@ -51,7 +51,8 @@ template <typename real> struct SharedArgs {
     const double *sums;           // all-reduced
     double2 *sh_th, *sh_acc, *sh_ring;   // [2 nst] (s-bar block, then log-sigma-bar block); ring [n][2 nst]
     const double2 *sh_pr;         // (mean, 1/var)
-    uint32_t seed0, seed1, step;
+    PhiloxKey key;
+    uint32_t step;
     const double *eps_sh;         // supplied noise [K][2 nst] or nullptr
     int z_direct;
     real *ctx;                    // [R][K][3][tmax]
@@ -86,8 +87,8 @@ __global__ void __launch_bounds__(128) shared_kernel(const SharedArgs<real> a) {
                 double es, el;
                 if (a.eps_sh) { es = a.eps_sh[(size_t)k * n2 + is]; el = a.eps_sh[(size_t)k * n2 + il]; }
                 else {
-                    es = stream_normal<double>(STREAM_SHARED, (uint32_t)is, (uint32_t)k, a.step, a.seed0, a.seed1);
-                    el = stream_normal<double>(STREAM_SHARED, (uint32_t)il, (uint32_t)k, a.step, a.seed0, a.seed1);
+                    es = stream_normal<double>(STREAM_SHARED, (uint32_t)is, (uint32_t)k, a.step, a.key);
+                    el = stream_normal<double>(STREAM_SHARED, (uint32_t)il, (uint32_t)k, a.step, a.key);
                 }
                 const double2 ths = a.sh_th[is], thl = a.sh_th[il];
                 const double zs = a.z_direct ? es : ths.x + softplus_d(ths.y) * es;   // s-bar_t
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(128) shared_kernel(const SharedArgs<real> a) {
             const double g = a.scratch[(size_t)k * n2 + i];
             const double e = a.eps_sh ? a.eps_sh[(size_t)k * n2 + i]
                                       : stream_normal<double>(STREAM_SHARED, (uint32_t)i, (uint32_t)k, a.step,
-                                                              a.seed0, a.seed1);
+                                                              a.key);
             sg += g; sge += g * e;
             if (a.dump) a.dump[(size_t)k * n2 + i] = g;
         }
@@ -165,7 +166,8 @@ template <typename real> struct HyperArgs {
     vec2<real> *hy_th, *hy_acc, *hy_ring;   // [H]; ring [n][H]
     const vec2<real> *hy_pr;     // (mean, 1/var) [H]
     vec2<real> *zeps;            // [K][H] (z, eps)
-    uint32_t seed0, seed1, step;
+    PhiloxKey key;
+    uint32_t step;
     const real *eps_hy;          // supplied noise [K][H] or nullptr
     int z_direct;
     // update
@@ -185,11 +187,11 @@ __global__ void __launch_bounds__(BLOCK) hyper_prep_kernel(const HyperArgs<real>
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= a.H) return;
     const vec2<real> th = a.hy_th[h];
-    const real sigma = softplus(th.y);
+    const real sigma = softplus_only<real>(th.y);
     for (int k = 0; k < a.K; ++k) {
         const real e = a.eps_hy ? a.eps_hy[(size_t)k * a.H + h]
                                 : stream_normal<real>(STREAM_HYPER, a.gid0 + (uint32_t)h, (uint32_t)k, a.step,
-                                                      a.seed0, a.seed1);
+                                                      a.key);
         const real z = a.z_direct ? e : fma(sigma, e, th.x);
         a.zeps[(size_t)k * a.H + h] = mk2<real>(z, e);
     }
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(BLOCK) hyper_update_kernel(const HyperArgs<rea
         for (int k = 0; k <= a.K; ++k) sel[k * BLOCK + tid] = 0.0;
     if (h < a.H) {
         vec2<real> th = a.hy_th[h];
-        const real sigma = softplus(th.y);
+        const real sigma = softplus_only<real>(th.y);
         const vec2<real> pr = a.hy_pr[h];
         real sg = real(0), sge = real(0);
         const int m0 = a.csr_off[h], m1 = a.csr_off[h + 1];
@@ -228,9 +230,9 @@ __global__ void __launch_bounds__(BLOCK) hyper_update_kernel(const HyperArgs<rea
         }
         if (want_elbo) sel[a.K * BLOCK + tid] = (double)bb_log(sigma);
         const real invK = real(1) / real(a.K);
-        finish_latent<real>(a.opt, invK, sg, sge, sigma, a.hy_th + h, a.hy_acc + h,
+        finish_latent<real>(a.opt, invK, sg, sge, th, a.hy_acc[h], a.hy_th + h, a.hy_acc + h,
                             a.hy_ring ? a.hy_ring + (size_t)a.opt.slot * a.H + h : nullptr,
-                            a.gout ? a.gout + h : nullptr, th.x, th.y);
+                            a.gout ? a.gout + h : nullptr);
     }
     if (want_elbo) {
         __syncthreads();
@@ -305,14 +307,13 @@ __global__ void gather_rows_kernel(const real *src, const int *map, long long n,
 
 // mean-field initialisation: mu_j = n(INIT, j), omega_j = n(INIT, D + j) with j the reference index
 template <typename real>
-__global__ void init_params_kernel(vec2<real> *dst, const int *map, long long n, long long D, uint32_t seed0,
-                                   uint32_t seed1) {
+__global__ void init_params_kernel(vec2<real> *dst, const int *map, long long n, long long D, const PhiloxKey key) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int m = map[i];
     if (m < 0) { dst[i] = mk2<real>(0, 0); return; }
-    const double mu = stream_normal<double>(STREAM_INIT, (uint32_t)m, 0u, 0u, seed0, seed1);
-    const double om = stream_normal<double>(STREAM_INIT, (uint32_t)(D + m), 0u, 0u, seed0, seed1);
+    const double mu = stream_normal<double>(STREAM_INIT, (uint32_t)m, 0u, 0u, key);
+    const double om = stream_normal<double>(STREAM_INIT, (uint32_t)(D + m), 0u, 0u, key);
     dst[i] = mk2<real>((real)mu, (real)om);
 }
 
@@ -324,8 +325,8 @@ template <typename T> __global__ void fill_kernel(T *p, long long n, T v) {
 // the lattice's draws, reference order: eps[k * D + map[i]] for the column latents of one class row
 template <typename real>
 __global__ void noise_columns_kernel(const SegList segs, int cpad, int row, int is_bc, const uint32_t *col_id,
-                                     const int *map_row, int K, long long D, uint32_t step, uint32_t seed0,
-                                     uint32_t seed1, double *eps) {
+                                     const int *map_row, int K, long long D, uint32_t step, const PhiloxKey key,
+                                     double *eps) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cpad) return;
     const int m = map_row[c];
@@ -337,7 +338,7 @@ __global__ void noise_columns_kernel(const SegList segs, int cpad, int row, int 
     const int slot = is_bc ? sg.nt + row : row;
     for (int k = 0; k < K; ++k) {
         real n[4];
-        normals4<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)(slot >> 2), (uint32_t)k, step, seed0, seed1, n);
+        normals4<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)(slot >> 2), (uint32_t)k, step, key, n);
         const int l = slot & 3;
         eps[(size_t)k * D + m] = (double)(l == 0 ? n[0] : l == 1 ? n[1] : l == 2 ? n[2] : n[3]);
     }
@@ -345,15 +346,14 @@ __global__ void noise_columns_kernel(const SegList segs, int cpad, int row, int 
 
 template <typename real>
 __global__ void noise_stream_kernel(uint32_t stream, uint32_t slot0, const int *map, int n, int K, long long D,
-                                    uint32_t step, uint32_t seed0, uint32_t seed1, int as_double, double *eps) {
+                                    uint32_t step, const PhiloxKey key, int as_double, double *eps) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int m = map[i];
     if (m < 0) return;
     for (int k = 0; k < K; ++k) {
-        const double e = as_double ? stream_normal<double>(stream, slot0 + (uint32_t)i, (uint32_t)k, step, seed0, seed1)
-                                   : (double)stream_normal<real>(stream, slot0 + (uint32_t)i, (uint32_t)k, step,
-                                                                 seed0, seed1);
+        const double e = as_double ? stream_normal<double>(stream, slot0 + (uint32_t)i, (uint32_t)k, step, key)
+                                   : (double)stream_normal<real>(stream, slot0 + (uint32_t)i, (uint32_t)k, step, key);
         eps[(size_t)k * D + m] = e;
     }
 }

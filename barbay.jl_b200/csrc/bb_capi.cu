@@ -129,8 +129,11 @@ int bb_use_graph(bb_handle *h, int32_t enable) {
     return guarded(h, [&](bb::EngineBase &e) { e.use_graph(enable); });
 }
 double bb_algorithmic_bytes_per_step(const bb_handle *h) { return h && h->eng ? h->eng->alg_bytes : -1.0; }
-int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_main) {
-    return guarded(h, [&](bb::EngineBase &e) { e.time_steps(n_steps, ms_total, ms_main); });
+int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_pass1, float *ms_pass2) {
+    return guarded(h, [&](bb::EngineBase &e) {
+        if (n_steps < 1 || !ms_total) throw std::runtime_error("bb_time_steps: bad arguments");
+        e.time_steps(n_steps, ms_total, ms_pass1, ms_pass2);
+    });
 }
 int bb_comm_unique_id(char id[128]) {
     try {

@@ -25,19 +25,35 @@ template <typename real> __device__ __forceinline__ vec2<real> mk2(real a, real 
 }
 
 // ---------------------------------------------------------------- Philox4x32-10
+// The ten round keys (k + r * W) are kernel-uniform: they are computed once on the host
+// and sit in the kernel's constant bank, so a round is 2 IMAD.WIDE + 2 LOP3.
+struct PhiloxKey {
+    uint32_t k0[10], k1[10];
+};
+inline PhiloxKey make_philox_key(uint64_t seed) {
+    PhiloxKey k;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { k.k0[r] = a; k.k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+    return k;
+}
+
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
-    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+                                              const PhiloxKey &key, uint32_t (&out)[4]) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += W0; k1 += W1;
+        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.k0[r], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.k1[r];
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+
+// MUFU-level approximations (no denormal / IEEE slow paths): operands here are never denormal
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // uniform in (0,1) from the top 23 bits: ((x >> 9) + 0.5) / 2^23
 __device__ __forceinline__ float u23(uint32_t x, float) {
@@ -49,7 +65,7 @@ __device__ __forceinline__ double u23(uint32_t x, double) {
 
 __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float &n0, float &n1) {
     const float u = u23(xa, 0.f), v = u23(xb, 0.f);
-    const float radius = sqrtf(-1.3862943611198906f * __log2f(u));     // sqrt(-2 ln u)
+    const float radius = fast_sqrt(-1.3862943611198906f * fast_lg2(u));   // sqrt(-2 ln u)
     float s, c;
     __sincosf(6.2831853071795865f * v, &s, &c);
     n0 = radius * c; n1 = radius * s;
@@ -64,9 +80,9 @@ __device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, double &n0,
 
 template <typename real>
 __device__ __forceinline__ void normals4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                         uint32_t k0, uint32_t k1, real (&n)[4]) {
+                                         const PhiloxKey &key, real (&n)[4]) {
     uint32_t x[4];
-    philox4x32_10(c0, c1, c2, c3, k0, k1, x);
+    philox4x32_10(c0, c1, c2, c3, key, x);
     box_muller(x[0], x[1], n[0], n[1]);
     box_muller(x[2], x[3], n[2], n[3]);
 }
@@ -74,19 +90,21 @@ __device__ __forceinline__ void normals4(uint32_t c0, uint32_t c1, uint32_t c2, 
 // normal attached to slot `i` of a non-column stream (shared / hyper / init)
 template <typename real>
 __device__ __forceinline__ real stream_normal(uint32_t stream, uint32_t i, uint32_t k, uint32_t step,
-                                              uint32_t k0, uint32_t k1) {
+                                              const PhiloxKey &key) {
     real n[4];
-    normals4<real>(i >> 2, stream << 24, k, step, k0, k1, n);
+    normals4<real>(i >> 2, stream << 24, k, step, key, n);
     const uint32_t lane = i & 3u;
     return lane == 0 ? n[0] : lane == 1 ? n[1] : lane == 2 ? n[2] : n[3];
 }
 
 // ---------------------------------------------------------------- scalar math
-__device__ __forceinline__ float bb_exp(float x) { return __expf(x); }
+__device__ __forceinline__ float bb_exp(float x) { return fast_ex2(x * 1.4426950408889634f); }
 __device__ __forceinline__ double bb_exp(double x) { return exp(x); }
 __device__ __forceinline__ float bb_log(float x) { return logf(x); }
 __device__ __forceinline__ double bb_log(double x) { return log(x); }
-__device__ __forceinline__ float bb_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ float bb_sqrt(float x) { return fast_sqrt(x); }
+__device__ __forceinline__ float bb_rcp(float x) { return fast_rcp(x); }
+__device__ __forceinline__ double bb_rcp(double x) { return 1.0 / x; }
 __device__ __forceinline__ double bb_sqrt(double x) { return sqrt(x); }
 
 // softplus(w) = log(1 + e^w), stable; StatsFuns.softplus

@@ -103,7 +103,7 @@ class EngineBase {
     virtual void set_state(const double *s) = 0;
     virtual void set_stream(void *s) = 0;
     virtual void sync() = 0;
-    virtual void time_steps(int n, float *ms_total, float *ms_main) = 0;
+    virtual void time_steps(int n, float *ms_total, float *ms_pass1, float *ms_pass2) = 0;
     virtual void comm_init(const char id[128]) = 0;
     virtual void use_graph(int enable) = 0;
     long long launches = 0;
@@ -135,7 +135,7 @@ template <typename real> class Engine : public EngineBase {
     void set_state(const double *s) override;
     void set_stream(void *s) override { stream_ = s ? (cudaStream_t)s : own_stream_; }
     void sync() override { BB_CUDA(cudaStreamSynchronize(stream_)); }
-    void time_steps(int n, float *ms_total, float *ms_main) override;
+    void time_steps(int n, float *ms_total, float *ms_pass1, float *ms_pass2) override;
     void comm_init(const char id[128]) override;
     void use_graph(int) override {}
 
@@ -147,7 +147,7 @@ template <typename real> class Engine : public EngineBase {
         int p1blocks = 0, p2blocks = 0;
         KernelSet<real> ks, ks_sup;
         int pv = 0, kchunk = 0;
-        size_t p1smem = 0, p2smem = 0;
+        size_t p1smem = 0, p2smem = 0, p2smem_elbo = 0;
         size_t part_off = 0, epart_off = 0;     // block offsets into part_ / epart_
     };
     struct RunMode {
@@ -198,6 +198,8 @@ template <typename real> class Engine : public EngineBase {
     // comm
     NcclApi::Comm comm_ = nullptr;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> tev_;   // per-step kernel brackets while timing
+    int tev_pos_ = -1;               // >= 0: record pass brackets into tev_
 };
 
 // ------------------------------------------------------------------ construction
@@ -273,6 +275,7 @@ template <typename real> Engine<real>::Engine(const bb_desc &d) {
 template <typename real> Engine<real>::~Engine() {
     if (comm_) NcclApi::get().CommDestroy(comm_);
     for (auto &e : ev_) if (e) cudaEventDestroy(e);
+    for (auto &e : tev_) cudaEventDestroy(e);
     if (own_stream_) cudaStreamDestroy(own_stream_);
 }
 
@@ -313,16 +316,32 @@ template <typename real> void Engine<real>::build_groups() {
             !lookup_kernels<real>(nt, L.E, L.hier, true, &g.ks_sup))
             throw std::runtime_error("no kernel instantiation for this shape");
         g.pv = nt + 2 * (nt - 1);
-        const size_t per_k = (size_t)g.pv * BLOCK * sizeof(real);
-        const int sweeps = (int)((L.K * per_k + smem_limit - 1) / smem_limit);
-        g.kchunk = (L.K + sweeps - 1) / sweeps;
-        g.p1smem = (size_t)g.kchunk * per_k;
+        // shared-memory accumulator budget of pass 1: sized for the mutant population (2 nt slots per
+        // sample when E == 1), capped so >= 4 CTAs fit per SM; blocks sweep K in chunks when it is short
+        const int pv_m = L.E == 1 ? 2 * nt : g.pv;
+        const size_t slot_b = (size_t)BLOCK * sizeof(real);
+        int slots = L.K * pv_m;
+        const int max_slots = (int)((44 * 1024) / slot_b);
+        if (slots > max_slots) {
+            const int sweeps = (slots + max_slots - 1) / max_slots;
+            slots = ((L.K + sweeps - 1) / sweeps) * pv_m;
+        }
+        slots = std::max(slots, g.pv);           // at least one sample of the widest population
+        g.kchunk = slots;
+        // + two cp.async staging buffers (see bb_kernels.cuh)
+        const size_t th_b = (size_t)(L.tmax + L.nj) * BLOCK * sizeof(r2);
+        g.p1smem = ((size_t)g.kchunk * slot_b + 15) / 16 * 16 + 2 * th_b;
         const size_t ctx_b = (((size_t)L.K * 3 * L.tmax * sizeof(real)) + 15) / 16 * 16;
-        g.p2smem = ctx_b + (size_t)(L.K + 1) * BLOCK * sizeof(double);
+        const int npr = (L.lam_pr_matrix || L.bc_pr_matrix) ? 1 : 0;
+        const size_t buf_b = (2 + npr) * th_b + (size_t)L.tmax * BLOCK * sizeof(int);
+        g.p2smem = ctx_b + 2 * buf_b;                                             // ELBO = false kernels
+        g.p2smem_elbo = g.p2smem + (size_t)(L.K + 1) * BLOCK * sizeof(double);
         for (auto *fn : {(const void *)g.ks.pass1, (const void *)g.ks_sup.pass1})
             BB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p1smem));
-        for (auto *fn : {(const void *)g.ks.pass2, (const void *)g.ks_sup.pass2})
-            BB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p2smem));
+        BB_CUDA(cudaFuncSetAttribute((const void *)g.ks.pass2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)g.p2smem));
+        for (auto *fn : {(const void *)g.ks.pass2_elbo, (const void *)g.ks_sup.pass2_elbo})
+            BB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p2smem_elbo));
         int occ1 = 1, occ2 = 1;
         BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, g.ks.pass1, BLOCK, g.p1smem));
         BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, g.ks.pass2, BLOCK, g.p2smem));
@@ -362,10 +381,10 @@ template <typename real> OptArgs Engine<real>::opt_args(bool update) const {
 
 // ------------------------------------------------------------------ parameters
 template <typename real> void Engine<real>::init_params(uint64_t seed) {
-    const uint32_t s0 = (uint32_t)seed, s1 = (uint32_t)(seed >> 32);
+    const PhiloxKey ikey = make_philox_key(seed);
     auto run = [&](r2 *dst, const int *map, size_t n) {
         if (!n) return;
-        init_params_kernel<real><<<cdiv(n, 256), 256, 0, stream_>>>(dst, map, (long long)n, L.D, s0, s1);
+        init_params_kernel<real><<<cdiv(n, 256), 256, 0, stream_>>>(dst, map, (long long)n, L.D, ikey);
         ++launches;
     };
     run(lam_th_.p, map_lam_.p, lam_th_.n);
@@ -380,7 +399,7 @@ template <typename real> void Engine<real>::init_params(uint64_t seed) {
         idm.upload(id);
         DBuf<double2> tmp;
         tmp.alloc(2 * L.nst);
-        init_params_kernel<double><<<cdiv(2 * L.nst, 128), 128, 0, stream_>>>(tmp.p, idm.p, 2 * L.nst, L.D, s0, s1);
+        init_params_kernel<double><<<cdiv(2 * L.nst, 128), 128, 0, stream_>>>(tmp.p, idm.p, 2 * L.nst, L.D, ikey);
         ++launches;
         BB_CUDA(cudaMemcpyAsync(sh_th_.p, tmp.p, sizeof(double2) * 2 * L.nst, cudaMemcpyDeviceToDevice, stream_));
         BB_CUDA(cudaStreamSynchronize(stream_));
@@ -512,7 +531,7 @@ template <typename real> void Engine<real>::upload_supplied(const double *x, int
 
 // ------------------------------------------------------------------ the step pipeline
 template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
-    const uint32_t s0 = (uint32_t)seed_, s1 = (uint32_t)(seed_ >> 32);
+    const PhiloxKey pkey = make_philox_key(seed_);
     const ColArrays<real> C = col_arrays();
     SupArgs<real> sup{};
     if (m.sup) {
@@ -523,7 +542,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
     if (L.hier) {
         ha.H = L.H; ha.K = L.K; ha.gid0 = L.hy_gid0;
         ha.hy_th = hy_th_.p; ha.hy_acc = hy_acc_.p; ha.hy_ring = hy_ring_.p; ha.hy_pr = hy_pr_.p;
-        ha.zeps = zeps_.p; ha.seed0 = s0; ha.seed1 = s1; ha.step = m.step;
+        ha.zeps = zeps_.p; ha.key = pkey; ha.step = m.step;
         ha.eps_hy = m.sup ? sup_hy_.p : nullptr; ha.z_direct = m.z_direct ? 1 : 0;
         ha.csr_off = csr_off_.p; ha.csr_mem = csr_mem_.p; ha.hcontrib = hcontrib_.p;
         ha.dump_hcontrib = m.dump ? dump_hc_.p : nullptr; ha.dump_stride = (long long)L.E * L.cpad;
@@ -537,16 +556,18 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         }
     }
     // ---- pass 1
+    if (tev_pos_ >= 0) BB_CUDA(cudaEventRecord(tev_[tev_pos_++], stream_));
     for (Group &g : groups_) {
         P1Args<real> a{};
-        a.segs = g.p1segs; a.cols = C; a.K = L.K; a.kchunk = g.kchunk; a.ne = L.E;
+        a.segs = g.p1segs; a.cols = C; a.K = L.K; a.acc_slots = g.kchunk; a.ne = L.E;
         for (int t = 0; t < MAX_NT_DYN; ++t) a.env_of_t[t] = L.env_of_t[t];
-        a.seed0 = s0; a.seed1 = s1; a.step = m.step;
+        a.key = pkey; a.step = m.step;
         a.hy_zeps = zeps_.p; a.H = L.H;
         a.part = part_.p + (size_t)g.part_off * L.K * (3 * L.tmax);
         a.pv = g.pv; a.sup = sup;
         (m.sup ? g.ks_sup.pass1 : g.ks.pass1)<<<g.p1blocks, BLOCK, g.p1smem, stream_>>>(a);
         ++launches;
+        if (tev_pos_ >= 0 && &g == &groups_.back()) BB_CUDA(cudaEventRecord(tev_[tev_pos_++], stream_));
         ReduceArgs ra{};
         ra.segs = g.p1segs; ra.K = L.K; ra.tmax = L.tmax; ra.pv = g.pv; ra.nt = g.nt;
         ra.w_single = L.E == 1 ? 1 : 0; ra.rep_mask = g.rep_mask;
@@ -566,7 +587,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         for (int r = 0; r < L.R; ++r) { sa.nt[r] = L.nt[r]; sa.sh0[r] = L.sh0[r]; }
         sa.n_neutral = (double)L.N;
         sa.sums = sums_.p; sa.sh_th = sh_th_.p; sa.sh_acc = sh_acc_.p; sa.sh_ring = sh_ring_.p; sa.sh_pr = sh_pr_.p;
-        sa.seed0 = s0; sa.seed1 = s1; sa.step = m.step;
+        sa.key = pkey; sa.step = m.step;
         sa.eps_sh = m.sup ? sup_sh_.p : nullptr; sa.z_direct = m.z_direct ? 1 : 0;
         sa.ctx = ctx_.p; sa.scratch = sh_scratch_.p;
         sa.gout = m.gout ? sh_gout_.p : nullptr;
@@ -578,21 +599,30 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         ++launches;
     }
     // ---- pass 2
+    if (tev_pos_ >= 0) BB_CUDA(cudaEventRecord(tev_[tev_pos_++], stream_));
     for (Group &g : groups_) {
         P2Args<real> a{};
         a.segs = g.p2segs; a.cols = C; a.K = L.K; a.ne = L.E;
         for (int t = 0; t < MAX_NT_DYN; ++t) a.env_of_t[t] = L.env_of_t[t];
-        a.seed0 = s0; a.seed1 = s1; a.step = m.step;
+        a.key = pkey; a.step = m.step;
         a.hy_zeps = zeps_.p; a.H = L.H;
         a.ctx = ctx_.p; a.tmax_ctx = L.tmax;
         a.opt = opt_args(m.update);
         a.gout_lam = m.gout ? gout_lam_.p : nullptr; a.gout_bc = m.gout ? gout_bc_.p : nullptr;
         a.hcontrib = hcontrib_.p;
-        a.epart = m.want_elbo ? epart_.p + (size_t)g.epart_off * (L.K + 1) : nullptr;
+        // the supplied-noise kernels always carry the ELBO terms (ELBO = true instantiation only)
+        const bool elbo = m.want_elbo || m.sup;
+        a.epart = elbo ? epart_.p + (size_t)g.epart_off * (L.K + 1) : nullptr;
         a.sup = sup;
-        (m.sup ? g.ks_sup.pass2 : g.ks.pass2)<<<g.p2blocks, BLOCK, g.p2smem, stream_>>>(a);
+        a.stage_pr = (L.lam_pr_matrix || L.bc_pr_matrix) ? 1 : 0;
+        {
+            const KernelSet<real> &ks = m.sup ? g.ks_sup : g.ks;
+            if (elbo) ks.pass2_elbo<<<g.p2blocks, BLOCK, g.p2smem_elbo, stream_>>>(a);
+            else ks.pass2<<<g.p2blocks, BLOCK, g.p2smem, stream_>>>(a);
+        }
         ++launches;
     }
+    if (tev_pos_ >= 0) BB_CUDA(cudaEventRecord(tev_[tev_pos_++], stream_));
     if (L.hier && L.H > 0) {
         hyper_update_kernel<real><<<hyblocks_, BLOCK, (size_t)(L.K + 1) * BLOCK * sizeof(double), stream_>>>(ha);
         ++launches;
@@ -669,7 +699,7 @@ template <typename real> void Engine<real>::elbo_grad(const double *eps, long lo
 }
 
 template <typename real> void Engine<real>::get_noise(long long step, double *eps) {
-    const uint32_t s0 = (uint32_t)seed_, s1 = (uint32_t)(seed_ >> 32);
+    const PhiloxKey pkey = make_philox_key(seed_);
     const size_t n = (size_t)L.K * L.D;
     hostvec_a_.ensure(n);
     BB_CUDA(cudaMemsetAsync(hostvec_a_.p, 0, sizeof(double) * n, stream_));
@@ -680,22 +710,22 @@ template <typename real> void Engine<real>::get_noise(long long step, double *ep
     }
     for (int t = 0; t < L.tmax; ++t) {
         noise_columns_kernel<real><<<cdiv(L.cpad, 128), 128, 0, stream_>>>(sl, L.cpad, t, 0, col_id_.p,
-            map_lam_.p + (size_t)t * L.cpad, L.K, L.D, (uint32_t)step, s0, s1, hostvec_a_.p);
+            map_lam_.p + (size_t)t * L.cpad, L.K, L.D, (uint32_t)step, pkey, hostvec_a_.p);
         ++launches;
     }
     for (int j = 0; j < L.nj; ++j) {
         noise_columns_kernel<real><<<cdiv(L.cpad, 128), 128, 0, stream_>>>(sl, L.cpad, j, 1, col_id_.p,
-            map_bc_.p + (size_t)j * L.cpad, L.K, L.D, (uint32_t)step, s0, s1, hostvec_a_.p);
+            map_bc_.p + (size_t)j * L.cpad, L.K, L.D, (uint32_t)step, pkey, hostvec_a_.p);
         ++launches;
     }
     if (L.hier && L.H > 0) {
         noise_stream_kernel<real><<<cdiv(L.H, 128), 128, 0, stream_>>>(STREAM_HYPER, L.hy_gid0, map_hy_.p, L.H, L.K,
-                                                                       L.D, (uint32_t)step, s0, s1, 0, hostvec_a_.p);
+                                                                       L.D, (uint32_t)step, pkey, 0, hostvec_a_.p);
         ++launches;
     }
     if (L.nst) {
         noise_stream_kernel<real><<<cdiv(2 * L.nst, 128), 128, 0, stream_>>>(STREAM_SHARED, 0u, map_sh_.p, 2 * L.nst,
-                                                                             L.K, L.D, (uint32_t)step, s0, s1, 1,
+                                                                             L.K, L.D, (uint32_t)step, pkey, 1,
                                                                              hostvec_a_.p);
         ++launches;
     }
@@ -743,14 +773,31 @@ template <typename real> void Engine<real>::step_with_noise(const double *eps) {
     BB_CUDA(cudaStreamSynchronize(stream_));
 }
 
-template <typename real> void Engine<real>::time_steps(int n, float *ms_total, float *ms_main) {
+template <typename real> void Engine<real>::time_steps(int n, float *ms_total, float *ms_pass1, float *ms_pass2) {
+    // CUDA-event timing on the launching stream: whole region, plus per-step brackets around the
+    // pass-1 and pass-2 column kernels (with ragged T the bracket spans the group launches).
     if (!opt_ready_) set_optimizer(opt_);
+    while ((int)tev_.size() < 4 * n) {
+        cudaEvent_t e;
+        BB_CUDA(cudaEventCreate(&e));
+        tev_.push_back(e);
+    }
+    tev_pos_ = 0;
     BB_CUDA(cudaEventRecord(ev_[0], stream_));
-    step(n, nullptr);
+    try { step(n, nullptr); } catch (...) { tev_pos_ = -1; throw; }
     BB_CUDA(cudaEventRecord(ev_[1], stream_));
     BB_CUDA(cudaEventSynchronize(ev_[1]));
+    tev_pos_ = -1;
     BB_CUDA(cudaEventElapsedTime(ms_total, ev_[0], ev_[1]));
-    if (ms_main) *ms_main = 0.f;
+    float p1 = 0.f, p2 = 0.f;
+    for (int i = 0; i < n; ++i) {
+        float a = 0.f, b = 0.f;
+        BB_CUDA(cudaEventElapsedTime(&a, tev_[4 * i + 0], tev_[4 * i + 1]));
+        BB_CUDA(cudaEventElapsedTime(&b, tev_[4 * i + 2], tev_[4 * i + 3]));
+        p1 += a; p2 += b;
+    }
+    if (ms_pass1) *ms_pass1 = p1;
+    if (ms_pass2) *ms_pass2 = p2;
 }
 
 // ------------------------------------------------------------------ state

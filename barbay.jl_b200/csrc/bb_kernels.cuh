@@ -15,6 +15,9 @@
 #include "bb_types.cuh"
 
 namespace bb {
+#ifndef BB_P2_MIN_BLOCKS
+#define BB_P2_MIN_BLOCKS 6
+#endif
 
 template <int NT> struct TD { static constexpr int MAX = NT > 0 ? NT : MAX_NT_DYN; };
 template <int NE> struct ED { static constexpr int MAX = NE > 0 ? NE : MAX_NE_DYN; };
@@ -37,7 +40,7 @@ __device__ __forceinline__ int find_segment(const SegList &sl, int blk) {
 // eps for every latent of one column and one MC sample
 template <typename real, int MAXC, bool SUP>
 __device__ __forceinline__ void column_noise(real (&eps)[MAXC], int nclass, int nt, uint32_t colid, uint32_t k,
-                                             uint32_t step, uint32_t k0, uint32_t k1, const SupArgs<real> &sup,
+                                             uint32_t step, const PhiloxKey &key, const SupArgs<real> &sup,
                                              int c, int cpad, int tmax, int nj) {
     if constexpr (SUP) {
 #pragma unroll
@@ -51,10 +54,49 @@ __device__ __forceinline__ void column_noise(real (&eps)[MAXC], int nclass, int 
         for (int q = 0; q < MAXC / 4; ++q) {
             if (q * 4 >= nclass) break;
             real n[4];
-            normals4<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k, step, k0, k1, n);
+            normals4<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k, step, key, n);
             eps[4 * q + 0] = n[0]; eps[4 * q + 1] = n[1]; eps[4 * q + 2] = n[2]; eps[4 * q + 3] = n[3];
         }
     }
+}
+
+// ===================================================================== staging
+// Thread-private double buffering through shared memory with cp.async (LDGSTS): while a
+// thread computes the K samples of one column it already has the next column's rows in
+// flight, so the ~1 us HBM latency is paid once per kernel, not once per tile.  Each thread
+// copies and reads only its own slot [row][tid]: no block barrier, no bank conflicts.
+template <int BYTES> __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// softplus(w) and its derivative sigmoid(w) from one ex2 (fp32: MUFU ex2 / lg2 / rcp; the
+// log1p is compensated -- log1p(x) = log(u) x / (u - 1), u = fl(1 + x) -- so small sigma keeps
+// full relative accuracy); fp64: libm.
+__device__ __forceinline__ void softplus_sigmoid(float w, float &sp, float &sgm) {
+    const float x = fast_ex2(-fabsf(w) * 1.4426950408889634f);      // e^{-|w|} in (0, 1]
+    const float u = 1.0f + x;
+    const float um1 = u - 1.0f;
+    const float l1p = um1 == 0.0f ? x : 0.6931471805599453f * fast_lg2(u) * x * fast_rcp(um1);
+    sp = fmaxf(w, 0.0f) + l1p;
+    const float ru = fast_rcp(u);
+    sgm = w >= 0.0f ? ru : x * ru;
+}
+__device__ __forceinline__ void softplus_sigmoid(double w, double &sp, double &sgm) {
+    sp = softplus(w);
+    sgm = sigmoid(w);
+}
+template <typename real> __device__ __forceinline__ real softplus_only(real w) {
+    real sp, sg;
+    softplus_sigmoid(w, sp, sg);
+    return sp;
 }
 
 // ===================================================================== pass 1
@@ -62,11 +104,13 @@ __device__ __forceinline__ void column_noise(real (&eps)[MAXC], int nclass, int 
 //   [0, nt)              Lambda_t partial            (both populations)
 //   [nt, 2nt-1)          neutral: sum d_t            mutant: sum w (d_t - s)
 //   [2nt-1, 3nt-2)       neutral: sum d_t^2          mutant: sum w        (E == 1: slot 2nt-1 only)
+// smem: [kchunk][pv][BLOCK] thread-private accumulators, then 2 staging buffers [nt + nj][BLOCK] of (mu, omega)
 template <typename real, int NT, int NE, bool HIER, bool SUP>
 __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
     using S = Shape<NT, NE, HIER>;
+    using r2 = vec2<real>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    real *sacc = reinterpret_cast<real *>(smem_raw);        // [kchunk][pv][BLOCK] thread-private columns
+    real *sacc = reinterpret_cast<real *>(smem_raw);
 
     const int tid = threadIdx.x;
     const int sidx = find_segment(a.segs, blockIdx.x);
@@ -79,24 +123,58 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
     const int cpad = C.cpad;
     const int nblk = seg.blk1 - seg.blk0;
     const int ntile = (seg.ncol + BLOCK - 1) / BLOCK;
+    // accumulator slots this block's population actually uses; the smem budget (a.acc_slots rows of
+    // BLOCK reals) is sized by the host for the mutant population, the few neutral blocks sweep K in
+    // smaller chunks instead of inflating every block's shared memory
+    const int pvs = seg.neutral ? 3 * nt - 2 : (NE == 1 ? 2 * nt : 3 * nt - 2);
+    const int kchunk = max(1, min(a.K, a.acc_slots / pvs));
+    const size_t acc_bytes = (((size_t)a.acc_slots * BLOCK * sizeof(real)) + 15) / 16 * 16;
+    r2 *stage = reinterpret_cast<r2 *>(smem_raw + acc_bytes);          // [2][nt + nj][BLOCK]
+    const int stage_stride = (C.tmax + C.nj) * BLOCK;
 
-    for (int kc0 = 0; kc0 < a.K; kc0 += a.kchunk) {
-        const int kc1 = min(a.K, kc0 + a.kchunk);
-        for (int i = tid; i < (kc1 - kc0) * pv * BLOCK; i += BLOCK) sacc[i] = real(0);
+    auto prefetch = [&](int tile, int buf) {
+        const int i = tile * BLOCK + tid;
+        if (tile < ntile && i < seg.ncol) {
+            const int c = seg.col0 + i;
+            r2 *dst = stage + (size_t)buf * stage_stride + tid;
+#pragma unroll
+            for (int t = 0; t < S::MAXT; ++t) {
+                if (t >= nt) break;
+                cp_async<sizeof(r2)>(dst + t * BLOCK, C.lam_th + (size_t)t * cpad + c);
+            }
+            if (!seg.neutral) {
+#pragma unroll
+                for (int j = 0; j < S::MAXJ; ++j) {
+                    if (j >= nj) break;
+                    cp_async<sizeof(r2)>(dst + (nt + j) * BLOCK, C.bc_th + (size_t)j * cpad + c);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    for (int kc0 = 0; kc0 < a.K; kc0 += kchunk) {
+        const int kc1 = min(a.K, kc0 + kchunk);
+        for (int i = tid; i < (kc1 - kc0) * pvs * BLOCK; i += BLOCK) sacc[i] = real(0);
         __syncthreads();
 
-        for (int tile = blockIdx.x - seg.blk0; tile < ntile; tile += nblk) {
+        int buf = 0;
+        prefetch(blockIdx.x - seg.blk0, 0);
+        for (int tile = blockIdx.x - seg.blk0; tile < ntile; tile += nblk, buf ^= 1) {
+            prefetch(tile + nblk, buf ^ 1);
+            cp_async_wait<1>();
             const int i = tile * BLOCK + tid;
             if (i >= seg.ncol) continue;
             const int c = seg.col0 + i;
             const uint32_t colid = C.col_id ? C.col_id[c] : seg.colid0 + (uint32_t)i;
+            const r2 *src = stage + (size_t)buf * stage_stride + tid;
 
             real mu[S::MAXT], sg[S::MAXT];
 #pragma unroll
             for (int t = 0; t < S::MAXT; ++t) {
                 if (t >= nt) break;
-                const vec2<real> th = C.lam_th[(size_t)t * cpad + c];
-                mu[t] = th.x; sg[t] = softplus(th.y);
+                const r2 th = src[t * BLOCK];
+                mu[t] = th.x; sg[t] = softplus_only<real>(th.y);
                 if constexpr (SUP) if (a.sup.z_direct) { mu[t] = real(0); sg[t] = real(1); }
             }
             real mub[S::MAXJ], sgb[S::MAXJ];
@@ -105,8 +183,8 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
 #pragma unroll
                 for (int j = 0; j < S::MAXJ; ++j) {
                     if (j >= nj) break;
-                    const vec2<real> th = C.bc_th[(size_t)j * cpad + c];
-                    mub[j] = th.x; sgb[j] = softplus(th.y);
+                    const r2 th = src[(nt + j) * BLOCK];
+                    mub[j] = th.x; sgb[j] = softplus_only<real>(th.y);
                     if constexpr (SUP) if (a.sup.z_direct) { mub[j] = real(0); sgb[j] = real(1); }
                 }
                 if constexpr (HIER) hbase = C.hgroup[c];
@@ -115,9 +193,9 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
 
             for (int k = kc0; k < kc1; ++k) {
                 real eps[S::MAXC];
-                column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.seed0, a.seed1,
+                column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key,
                                                  a.sup, c, cpad, C.tmax, C.nj);
-                real *acc = sacc + (size_t)(k - kc0) * pv * BLOCK + tid;
+                real *acc = sacc + (size_t)(k - kc0) * pvs * BLOCK + tid;
                 real z[S::MAXT];
 #pragma unroll
                 for (int t = 0; t < S::MAXT; ++t) {
@@ -160,16 +238,17 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
                 }
             }
         }
+        cp_async_wait<0>();
         __syncthreads();
         // block reduction of the private columns, in double, fixed order
         const int warp = tid >> 5, lane = tid & 31;
-        for (int row = warp; row < (kc1 - kc0) * pv; row += BLOCK / 32) {
+        for (int row = warp; row < (kc1 - kc0) * pvs; row += BLOCK / 32) {
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < BLOCK / 32; ++j) s += (double)sacc[(size_t)row * BLOCK + j * 32 + lane];
             s = warp_sum<double>(s);
             if (lane == 0) {
-                const int kl = row / pv, v = row % pv;
+                const int kl = row / pvs, v = row % pvs;
                 a.part[((size_t)blockIdx.x * a.K + kc0 + kl) * pv + v] = s;
             }
         }
@@ -194,24 +273,25 @@ __device__ __forceinline__ void opt_apply(const OptArgs &o, real g, real &theta,
         ring_slot = g2;
         denom = real(o.tau) + bb_sqrt(acc) + real(1e-8);
     }
-    theta -= real(o.eta) * g / denom;
+    theta -= real(o.eta) * g * bb_rcp(denom);
 }
 
 // finish one latent: gradients of the objective, update (or emit), in place
 template <typename real>
-__device__ __forceinline__ void finish_latent(const OptArgs &o, real invK, real sgrad, real sgrade, real sigma,
-                                              vec2<real> *th_ptr, vec2<real> *acc_ptr, vec2<real> *ring_ptr,
-                                              vec2<real> *gout_ptr, real mu, real om) {
+__device__ __forceinline__ void finish_latent(const OptArgs &o, real invK, real sgrad, real sgrade,
+                                              vec2<real> th, vec2<real> ac, vec2<real> *th_ptr,
+                                              vec2<real> *acc_ptr, vec2<real> *ring_ptr, vec2<real> *gout_ptr) {
     // d ELBO / d mu = mean_k g ; d ELBO / d omega = (mean_k g eps + 1/sigma) sigmoid(omega)
+    real sigma, sgm;
+    softplus_sigmoid(th.y, sigma, sgm);
     const real gm = sgrad * invK;
-    const real go = (sgrade * invK + real(1) / sigma) * sigmoid(om);
+    const real go = (sgrade * invK + bb_rcp(sigma)) * sgm;
     if (o.update) {
-        vec2<real> ac = *acc_ptr;
         vec2<real> rg = mk2<real>(0, 0);
         if (o.kind == 0) rg = *ring_ptr;
-        opt_apply<real>(o, -gm, mu, ac.x, rg.x);      // the engine minimises -ELBO
-        opt_apply<real>(o, -go, om, ac.y, rg.y);
-        *th_ptr = mk2<real>(mu, om);
+        opt_apply<real>(o, -gm, th.x, ac.x, rg.x);      // the engine minimises -ELBO
+        opt_apply<real>(o, -go, th.y, ac.y, rg.y);
+        *th_ptr = th;
         *acc_ptr = ac;
         if (o.kind == 0) *ring_ptr = rg;
     } else if (gout_ptr) {
@@ -220,14 +300,19 @@ __device__ __forceinline__ void finish_latent(const OptArgs &o, real invK, real 
 }
 
 // ===================================================================== pass 2
-template <typename real, int NT, int NE, bool HIER, bool SUP>
-__global__ void __launch_bounds__(BLOCK) pass2_kernel(const P2Args<real> a) {
+// smem: ctx [K][3][tmax] of this block's replicate | ELBO private columns [K+1][BLOCK] (double) |
+//       2 staging buffers { theta [nt+nj][BLOCK], acc [nt+nj][BLOCK], counts [nt][BLOCK],
+//                           priors [nt+nj][BLOCK] (matrix priors only) }
+template <typename real, int NT, int NE, bool HIER, bool SUP, bool ELBO>
+__global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2Args<real> a) {
     using S = Shape<NT, NE, HIER>;
+    using r2 = vec2<real>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // smem: ctx [K][3][tmax_ctx] for this block's replicate, then ELBO private columns [K+1][BLOCK] (double)
     real *sctx = reinterpret_cast<real *>(smem_raw);
     const int ctx_n = a.K * 3 * a.tmax_ctx;
-    double *sel = reinterpret_cast<double *>(smem_raw + ((ctx_n * sizeof(real) + 15) / 16) * 16);
+    const size_t ctx_bytes = ((ctx_n * sizeof(real) + 15) / 16) * 16;
+    double *sel = reinterpret_cast<double *>(smem_raw + ctx_bytes);
+    const size_t sel_bytes = ELBO ? (size_t)(a.K + 1) * BLOCK * sizeof(double) : 0;
 
     const int tid = threadIdx.x;
     const int sidx = find_segment(a.segs, blockIdx.x);
@@ -239,9 +324,51 @@ __global__ void __launch_bounds__(BLOCK) pass2_kernel(const P2Args<real> a) {
     const int cpad = C.cpad;
     const int nblk = seg.blk1 - seg.blk0;
     const int ntile = (seg.ncol + BLOCK - 1) / BLOCK;
-    const bool want_elbo = a.epart != nullptr;
+    constexpr bool want_elbo = ELBO;
     const real invK = real(1) / real(a.K);
+    const bool lam_mat = C.lam_pr != nullptr, bc_mat = C.bc_pr != nullptr;
 
+    // staging geometry (rows sized by the arrays' tmax / nj so every block agrees with the host)
+    const int rows = C.tmax + C.nj;
+    const size_t th_bytes = (size_t)rows * BLOCK * sizeof(r2);
+    const size_t cn_bytes = (size_t)C.tmax * BLOCK * sizeof(int);
+    const int npr = a.stage_pr ? 1 : 0;                     // matrix priors are staged too
+    const size_t buf_bytes = (2 + npr) * th_bytes + cn_bytes;   // theta, acc, [priors], counts
+    unsigned char *stage0 = smem_raw + ctx_bytes + sel_bytes;
+
+    auto prefetch = [&](int tile, int buf) {
+        const int i = tile * BLOCK + tid;
+        if (tile < ntile && i < seg.ncol) {
+            const int c = seg.col0 + i;
+            unsigned char *base = stage0 + (size_t)buf * buf_bytes;
+            r2 *sth = reinterpret_cast<r2 *>(base) + tid;
+            r2 *sac = reinterpret_cast<r2 *>(base + th_bytes) + tid;
+            r2 *spr = reinterpret_cast<r2 *>(base + 2 * th_bytes) + tid;
+            int *scn = reinterpret_cast<int *>(base + (2 + npr) * th_bytes) + tid;
+#pragma unroll
+            for (int t = 0; t < S::MAXT; ++t) {
+                if (t >= nt) break;
+                const size_t o = (size_t)t * cpad + c;
+                cp_async<sizeof(r2)>(sth + t * BLOCK, C.lam_th + o);
+                cp_async<sizeof(r2)>(sac + t * BLOCK, C.lam_acc + o);
+                cp_async<4>(scn + t * BLOCK, C.cnt + o);
+                if (lam_mat) cp_async<sizeof(r2)>(spr + t * BLOCK, C.lam_pr + o);
+            }
+            if (!seg.neutral) {
+#pragma unroll
+                for (int j = 0; j < S::MAXJ; ++j) {
+                    if (j >= nj) break;
+                    const size_t o = (size_t)j * cpad + c;
+                    cp_async<sizeof(r2)>(sth + (nt + j) * BLOCK, C.bc_th + o);
+                    cp_async<sizeof(r2)>(sac + (nt + j) * BLOCK, C.bc_acc + o);
+                    if (bc_mat) cp_async<sizeof(r2)>(spr + (nt + j) * BLOCK, C.bc_pr + o);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    prefetch(blockIdx.x - seg.blk0, 0);
     for (int i = tid; i < ctx_n; i += BLOCK) sctx[i] = a.ctx[(size_t)seg.rep * ctx_n + i];
     if (want_elbo)
         for (int k = 0; k <= a.K; ++k) sel[k * BLOCK + tid] = 0.0;
@@ -254,39 +381,42 @@ __global__ void __launch_bounds__(BLOCK) pass2_kernel(const P2Args<real> a) {
     if (NE == 1) n_of_e[0] = nt - 1;
     else for (int t = 1; t < nt; ++t) n_of_e[a.env_of_t[t]] += 1;
 
-    for (int tile = blockIdx.x - seg.blk0; tile < ntile; tile += nblk) {
+    int buf = 0;
+    for (int tile = blockIdx.x - seg.blk0; tile < ntile; tile += nblk, buf ^= 1) {
+        prefetch(tile + nblk, buf ^ 1);
+        cp_async_wait<1>();
         const int i = tile * BLOCK + tid;
         if (i >= seg.ncol) continue;
         const int c = seg.col0 + i;
         const uint32_t colid = C.col_id ? C.col_id[c] : seg.colid0 + (uint32_t)i;
+        unsigned char *base = stage0 + (size_t)buf * buf_bytes;
+        const r2 *sth = reinterpret_cast<const r2 *>(base) + tid;
+        const r2 *sac = reinterpret_cast<const r2 *>(base + th_bytes) + tid;
+        const r2 *spr = reinterpret_cast<const r2 *>(base + 2 * th_bytes) + tid;
+        const int *scn = reinterpret_cast<const int *>(base + (2 + npr) * th_bytes) + tid;
 
-        real mu[S::MAXT], om[S::MAXT], sg[S::MAXT], sgr[S::MAXT], sge[S::MAXT], cnt[S::MAXT];
-        real pm[S::MAXT], piv[S::MAXT];
+        real mu[S::MAXT], sg[S::MAXT], sgr[S::MAXT], sge[S::MAXT], cnt[S::MAXT];
         double lsig_sum = 0.0;
 #pragma unroll
         for (int t = 0; t < S::MAXT; ++t) {
             if (t >= nt) break;
-            const vec2<real> th = C.lam_th[(size_t)t * cpad + c];
-            mu[t] = th.x; om[t] = th.y; sg[t] = softplus(th.y);
+            const r2 th = sth[t * BLOCK];
+            mu[t] = th.x; sg[t] = softplus_only<real>(th.y);
             if constexpr (SUP) if (a.sup.z_direct) { mu[t] = real(0); sg[t] = real(1); }
-            cnt[t] = (real)C.cnt[(size_t)t * cpad + c];
-            const vec2<real> p = C.lam_pr ? C.lam_pr[(size_t)t * cpad + c] : C.lam_pr_s;
-            pm[t] = p.x; piv[t] = p.y;
+            cnt[t] = (real)scn[t * BLOCK];
             sgr[t] = real(0); sge[t] = real(0);
             if (want_elbo) lsig_sum += (double)bb_log(sg[t]);
         }
-        real mub[S::MAXJ], omb[S::MAXJ], sgb[S::MAXJ], sgrb[S::MAXJ], sgeb[S::MAXJ], pmb[S::MAXJ], pivb[S::MAXJ];
+        real mub[S::MAXJ], sgb[S::MAXJ], sgrb[S::MAXJ], sgeb[S::MAXJ];
         real hc[S::MAXE], hce[S::MAXE];
         int hbase = 0;
         if (!seg.neutral) {
 #pragma unroll
             for (int j = 0; j < S::MAXJ; ++j) {
                 if (j >= nj) break;
-                const vec2<real> th = C.bc_th[(size_t)j * cpad + c];
-                mub[j] = th.x; omb[j] = th.y; sgb[j] = softplus(th.y);
+                const r2 th = sth[(nt + j) * BLOCK];
+                mub[j] = th.x; sgb[j] = softplus_only<real>(th.y);
                 if constexpr (SUP) if (a.sup.z_direct) { mub[j] = real(0); sgb[j] = real(1); }
-                const vec2<real> p = C.bc_pr ? C.bc_pr[(size_t)j * cpad + c] : C.bc_pr_s[j % S::PER];
-                pmb[j] = p.x; pivb[j] = p.y;
                 sgrb[j] = real(0); sgeb[j] = real(0);
                 if (want_elbo) lsig_sum += (double)bb_log(sgb[j]);
             }
@@ -300,7 +430,7 @@ __global__ void __launch_bounds__(BLOCK) pass2_kernel(const P2Args<real> a) {
 
         for (int k = 0; k < a.K; ++k) {
             real eps[S::MAXC];
-            column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.seed0, a.seed1, a.sup,
+            column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, a.sup,
                                              c, cpad, C.tmax, C.nj);
             const real *cE = sctx + (size_t)(k * 3 + 0) * a.tmax_ctx;   // c_t - sbar_t
             const real *cG = sctx + (size_t)(k * 3 + 1) * a.tmax_ctx;   // (U_{t-1} - U_t) / Lambda_t
@@ -312,10 +442,12 @@ __global__ void __launch_bounds__(BLOCK) pass2_kernel(const P2Args<real> a) {
                 if (t >= nt) break;
                 z[t] = fma(sg[t], eps[t], mu[t]);
                 const real lam = bb_exp(z[t]);
-                const real dz = z[t] - pm[t];
+                r2 p = C.lam_pr_s;
+                if (lam_mat) p = spr[t * BLOCK];
+                const real dz = z[t] - p.x;
                 // Poisson (collapsed Poisson x Multinomial) + logLambda coupling + Normal prior
-                g[t] = (cnt[t] - lam) + lam * cG[t] - dz * piv[t];
-                if (want_elbo) lp += cnt[t] * z[t] - lam - real(0.5) * dz * dz * piv[t];
+                g[t] = (cnt[t] - lam) + lam * cG[t] - dz * p.y;
+                if (want_elbo) lp += cnt[t] * z[t] - lam - real(0.5) * dz * dz * p.y;
             }
             if (seg.neutral) {
                 real uprev = real(0);
@@ -340,7 +472,7 @@ __global__ void __launch_bounds__(BLOCK) pass2_kernel(const P2Args<real> a) {
                 for (int e = 0; e < S::MAXE; ++e) {
                     if (e >= ne) break;
                     if constexpr (HIER) {
-                        const vec2<real> hz = a.hy_zeps[(size_t)k * a.H + hbase + e];
+                        const r2 hz = a.hy_zeps[(size_t)k * a.H + hbase + e];
                         extau[e] = bb_exp(zb[3 * e + 1]);
                         zs[e] = fma(extau[e], zb[3 * e], hz.x);
                         epsth[e] = hz.y;
@@ -387,9 +519,11 @@ __global__ void __launch_bounds__(BLOCK) pass2_kernel(const P2Args<real> a) {
 #pragma unroll
                 for (int j = 0; j < S::MAXJ; ++j) {
                     if (j >= nj) break;
-                    const real dz = zb[j] - pmb[j];
-                    gb[j] -= dz * pivb[j];
-                    if (want_elbo) lp -= real(0.5) * dz * dz * pivb[j];
+                    r2 p = C.bc_pr_s[j % S::PER];
+                    if (bc_mat) p = spr[(nt + j) * BLOCK];
+                    const real dz = zb[j] - p.x;
+                    gb[j] -= dz * p.y;
+                    if (want_elbo) lp -= real(0.5) * dz * dz * p.y;
                     sgrb[j] += gb[j];
                     sgeb[j] = fma(gb[j], eps[nt + j], sgeb[j]);
                     if constexpr (SUP) if (a.sup.dump_bc) a.sup.dump_bc[((size_t)k * C.nj + j) * cpad + c] = gb[j];
@@ -406,23 +540,25 @@ __global__ void __launch_bounds__(BLOCK) pass2_kernel(const P2Args<real> a) {
         }
         if (want_elbo) sel[a.K * BLOCK + tid] += lsig_sum;
 
-        // fused optimiser update of every latent of the column
+        // fused optimiser update of every latent of the column (theta / accumulators re-read from the stage)
 #pragma unroll
         for (int t = 0; t < S::MAXT; ++t) {
             if (t >= nt) break;
             const size_t o = (size_t)t * cpad + c;
-            finish_latent<real>(a.opt, invK, sgr[t], sge[t], sg[t], C.lam_th + o, C.lam_acc + o,
+            finish_latent<real>(a.opt, invK, sgr[t], sge[t], sth[t * BLOCK], sac[t * BLOCK], C.lam_th + o,
+                                C.lam_acc + o,
                                 C.lam_ring ? C.lam_ring + (size_t)a.opt.slot * a.opt.ring_stride_lam + o : nullptr,
-                                a.gout_lam ? a.gout_lam + o : nullptr, mu[t], om[t]);
+                                a.gout_lam ? a.gout_lam + o : nullptr);
         }
         if (!seg.neutral) {
 #pragma unroll
             for (int j = 0; j < S::MAXJ; ++j) {
                 if (j >= nj) break;
                 const size_t o = (size_t)j * cpad + c;
-                finish_latent<real>(a.opt, invK, sgrb[j], sgeb[j], sgb[j], C.bc_th + o, C.bc_acc + o,
+                finish_latent<real>(a.opt, invK, sgrb[j], sgeb[j], sth[(nt + j) * BLOCK], sac[(nt + j) * BLOCK],
+                                    C.bc_th + o, C.bc_acc + o,
                                     C.bc_ring ? C.bc_ring + (size_t)a.opt.slot * a.opt.ring_stride_bc + o : nullptr,
-                                    a.gout_bc ? a.gout_bc + o : nullptr, mub[j], omb[j]);
+                                    a.gout_bc ? a.gout_bc + o : nullptr);
             }
             if constexpr (HIER) {
 #pragma unroll
@@ -433,6 +569,7 @@ __global__ void __launch_bounds__(BLOCK) pass2_kernel(const P2Args<real> a) {
             }
         }
     }
+    cp_async_wait<0>();
     if (want_elbo) {
         __syncthreads();
         const int warp = tid >> 5, lane = tid & 31;
@@ -449,13 +586,17 @@ __global__ void __launch_bounds__(BLOCK) pass2_kernel(const P2Args<real> a) {
 // function-pointer bundle of one (real, NT, NE, HIER, SUP) instantiation
 template <typename real> struct KernelSet {
     void (*pass1)(const P1Args<real>);
-    void (*pass2)(const P2Args<real>);
+    void (*pass2)(const P2Args<real>);        // no ELBO partial sums (the production step)
+    void (*pass2_elbo)(const P2Args<real>);   // also accumulates the log-density / entropy partials
 };
 
 template <typename real, int NT, int NE, bool HIER, bool SUP> KernelSet<real> make_kernel_set() {
     KernelSet<real> ks;
     ks.pass1 = pass1_kernel<real, NT, NE, HIER, SUP>;
-    ks.pass2 = pass2_kernel<real, NT, NE, HIER, SUP>;
+    ks.pass2_elbo = pass2_kernel<real, NT, NE, HIER, SUP, true>;
+    // the caller-supplied-noise kernels are the parity path: always with the ELBO terms
+    if constexpr (SUP) ks.pass2 = ks.pass2_elbo;
+    else ks.pass2 = pass2_kernel<real, NT, NE, HIER, SUP, false>;
     return ks;
 }
 

@@ -70,10 +70,11 @@ template <typename real> struct P1Args {
     SegList segs;
     ColArrays<real> cols;
     int K;
-    int kchunk;            // MC samples accumulated per sweep (smem budget)
+    int acc_slots;         // rows of BLOCK accumulators in shared memory (K-chunking budget)
     int ne;                // E
     int env_of_t[MAX_NT_DYN];   // 0-based environment of time point t
-    uint32_t seed0, seed1, step;
+    PhiloxKey key;
+    uint32_t step;
     const vec2<real> *hy_zeps;  // [K][H] (z, eps) of the hyper latents (hier)
     int H;
     double *part;          // [gridDim.x][K][pv] block partial sums (double)
@@ -87,7 +88,8 @@ template <typename real> struct P2Args {
     int K;
     int ne;
     int env_of_t[MAX_NT_DYN];
-    uint32_t seed0, seed1, step;
+    PhiloxKey key;
+    uint32_t step;
     const vec2<real> *hy_zeps;
     int H;
     const real *ctx;       // [R][K][3][tmax]: (c_t - sbar_t), G_Lambda_t, wbar_t
@@ -97,6 +99,7 @@ template <typename real> struct P2Args {
     vec2<real> *gout_bc;   // [nj][cpad]
     vec2<real> *hcontrib;  // [E][cpad] (sum_k g_s, sum_k g_s eps_theta) (hier)
     double *epart;         // [gridDim.x][K+1] ELBO partials (log pi variable part per k; sum log sigma), or nullptr
+    int stage_pr;          // 1: per-latent (matrix) priors are staged through shared memory
     SupArgs<real> sup;
 };
 

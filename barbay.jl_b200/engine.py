@@ -246,9 +246,10 @@ class Engine:
         return float(self._lib.bb_algorithmic_bytes_per_step(self._h))
 
     def time_steps(self, n_steps: int):
-        a, b = C.c_float(), C.c_float()
-        self._check(self._lib.bb_time_steps(self._h, int(n_steps), C.byref(a), C.byref(b)))
-        return a.value, b.value
+        """(ms_total, ms_pass1, ms_pass2) for n_steps, CUDA events on the launching stream."""
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        self._check(self._lib.bb_time_steps(self._h, int(n_steps), C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def comm_init(self, unique_id: bytes):
         buf = (C.c_char * 128).from_buffer_copy(unique_id)

@@ -132,7 +132,9 @@ int bb_sync(bb_handle *h);
 int64_t bb_launch_count(const bb_handle *h);            /* kernels launched by this handle so far */
 int bb_use_graph(bb_handle *h, int32_t enable);         /* capture the step sequence in a CUDA graph */
 double bb_algorithmic_bytes_per_step(const bb_handle *h);   /* SURVEY §8d figure for this shard */
-int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_main_kernels);
+/* n_steps of bb_step timed with CUDA events on the launching stream: whole region, and the summed
+ * durations of the pass-1 and pass-2 column kernels (the roofline numerators of bench.py). */
+int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_pass1, float *ms_pass2);
 
 /* ---- multi-GPU: one process per GPU; id is an ncclUniqueId (128 bytes) ---- */
 int bb_comm_unique_id(char id[128]);
