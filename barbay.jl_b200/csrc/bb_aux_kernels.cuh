@@ -60,7 +60,7 @@ template <typename real> struct SharedArgs {
     double2 *gout;                // [2 nst] (dELBO/dmu, dELBO/domega) when !opt.update
     double *dump;                 // [K][2 nst] per-sample d log pi/dz or nullptr
     double *elbo_sh;              // [K+1]: neutral-likelihood + shared-prior log-density per k; sum log sigma
-    OptArgs opt;
+    OptArgsT<double> opt;
     int leader;                   // 1: this rank reports the shared latents' ELBO terms (rank 0)
 };
 
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(128) shared_kernel(const SharedArgs<real> a) {
         if (a.opt.update) {
             double2 ac = a.sh_acc[i];
             double2 rg = make_double2(0.0, 0.0);
-            double2 *rp = a.opt.kind == 0 ? a.sh_ring + (size_t)a.opt.slot * n2 + i : nullptr;
+            double2 *rp = a.opt.kind == 0 ? a.sh_ring + i : nullptr;   // sh_ring: this step's slot
             if (rp) rg = *rp;
             opt_apply<double>(a.opt, -gm, th.x, ac.x, rg.x);
             opt_apply<double>(a.opt, -go, th.y, ac.y, rg.y);
@@ -179,7 +179,7 @@ template <typename real> struct HyperArgs {
     real *dump;                  // [K][H] per-sample d log pi / d theta or nullptr
     vec2<real> *gout;            // [H]
     double *epart;               // [gridDim.x][K+1] or nullptr
-    OptArgs opt;
+    OptArgsT<real> opt;
 };
 
 template <typename real>
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(BLOCK) hyper_update_kernel(const HyperArgs<rea
         if (want_elbo) sel[a.K * BLOCK + tid] = (double)bb_log(sigma);
         const real invK = real(1) / real(a.K);
         finish_latent<real>(a.opt, invK, sg, sge, th, a.hy_acc[h], a.hy_th + h, a.hy_acc + h,
-                            a.hy_ring ? a.hy_ring + (size_t)a.opt.slot * a.H + h : nullptr,
+                            a.hy_ring ? a.hy_ring + h : nullptr,
                             a.gout ? a.gout + h : nullptr);
     }
     if (want_elbo) {

@@ -166,7 +166,12 @@ template <typename real> class Engine : public EngineBase {
     void upload_supplied(const double *x, int K);
     void ensure_supplied(bool dump);
     ColArrays<real> col_arrays() const;
-    OptArgs opt_args(bool update) const;
+    template <typename T> OptArgsT<T> opt_args(bool update) const {
+        OptArgsT<T> o;
+        o.kind = opt_.kind; o.update = update ? 1 : 0;
+        o.eta = (T)opt_.eta; o.tau = (T)opt_.tau; o.post = (T)opt_.post;
+        return o;
+    }
     void zero_like_init_acc();
     double finish_elbo(double *logp_k);
     void gather_to_ref(const r2 *lam, const r2 *bc, const r2 *hy, const double2 *sh, double *x, double *y, bool sp);
@@ -365,18 +370,10 @@ template <typename real> ColArrays<real> Engine<real>::col_arrays() const {
     C.lam_pr_s = r2{(real)L.pr_lam_s[0], (real)L.pr_lam_s[1]};
     for (int k = 0; k < 3; ++k) C.bc_pr_s[k] = r2{(real)L.pr_bc_s[k][0], (real)L.pr_bc_s[k][1]};
     C.hgroup = hgroup_.p; C.col_id = col_id_.p;
-    C.lam_ring = lam_ring_.p; C.bc_ring = bc_ring_.p;
+    // the rings are [n][...]: hand the kernels this step's slot
+    C.lam_ring = lam_ring_.p ? lam_ring_.p + (size_t)ring_slot_ * L.tmax * L.cpad : nullptr;
+    C.bc_ring = bc_ring_.p ? bc_ring_.p + (size_t)ring_slot_ * L.nj * L.cpad : nullptr;
     return C;
-}
-
-template <typename real> OptArgs Engine<real>::opt_args(bool update) const {
-    OptArgs o;
-    o.kind = opt_.kind; o.update = update ? 1 : 0;
-    o.eta = opt_.eta; o.tau = opt_.tau; o.post = opt_.post;
-    o.slot = ring_slot_;
-    o.ring_stride_lam = (long long)L.tmax * L.cpad;
-    o.ring_stride_bc = (long long)L.nj * L.cpad;
-    return o;
 }
 
 // ------------------------------------------------------------------ parameters
@@ -541,7 +538,8 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
     HyperArgs<real> ha{};
     if (L.hier) {
         ha.H = L.H; ha.K = L.K; ha.gid0 = L.hy_gid0;
-        ha.hy_th = hy_th_.p; ha.hy_acc = hy_acc_.p; ha.hy_ring = hy_ring_.p; ha.hy_pr = hy_pr_.p;
+        ha.hy_th = hy_th_.p; ha.hy_acc = hy_acc_.p;
+        ha.hy_ring = hy_ring_.p ? hy_ring_.p + (size_t)ring_slot_ * L.H : nullptr; ha.hy_pr = hy_pr_.p;
         ha.zeps = zeps_.p; ha.key = pkey; ha.step = m.step;
         ha.eps_hy = m.sup ? sup_hy_.p : nullptr; ha.z_direct = m.z_direct ? 1 : 0;
         ha.csr_off = csr_off_.p; ha.csr_mem = csr_mem_.p; ha.hcontrib = hcontrib_.p;
@@ -549,7 +547,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         ha.dump = m.dump ? dump_hy_.p : nullptr;
         ha.gout = m.gout ? gout_hy_.p : nullptr;
         ha.epart = m.want_elbo ? hy_epart_.p : nullptr;
-        ha.opt = opt_args(m.update);
+        ha.opt = opt_args<real>(m.update);
         if (L.H > 0) {
             hyper_prep_kernel<real><<<hyblocks_, BLOCK, 0, stream_>>>(ha);
             ++launches;
@@ -586,14 +584,15 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         sa.R = L.R; sa.K = L.K; sa.tmax = L.tmax; sa.nst = L.nst;
         for (int r = 0; r < L.R; ++r) { sa.nt[r] = L.nt[r]; sa.sh0[r] = L.sh0[r]; }
         sa.n_neutral = (double)L.N;
-        sa.sums = sums_.p; sa.sh_th = sh_th_.p; sa.sh_acc = sh_acc_.p; sa.sh_ring = sh_ring_.p; sa.sh_pr = sh_pr_.p;
+        sa.sums = sums_.p; sa.sh_th = sh_th_.p; sa.sh_acc = sh_acc_.p;
+        sa.sh_ring = sh_ring_.p ? sh_ring_.p + (size_t)ring_slot_ * 2 * L.nst : nullptr; sa.sh_pr = sh_pr_.p;
         sa.key = pkey; sa.step = m.step;
         sa.eps_sh = m.sup ? sup_sh_.p : nullptr; sa.z_direct = m.z_direct ? 1 : 0;
         sa.ctx = ctx_.p; sa.scratch = sh_scratch_.p;
         sa.gout = m.gout ? sh_gout_.p : nullptr;
         sa.dump = m.dump ? dump_sh_.p : nullptr;
         sa.elbo_sh = m.want_elbo ? elbo_sh_.p : nullptr;
-        sa.opt = opt_args(m.update);
+        sa.opt = opt_args<double>(m.update);
         sa.leader = L.rank == 0 ? 1 : 0;
         shared_kernel<real><<<1, 128, 0, stream_>>>(sa);
         ++launches;
@@ -607,7 +606,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         a.key = pkey; a.step = m.step;
         a.hy_zeps = zeps_.p; a.H = L.H;
         a.ctx = ctx_.p; a.tmax_ctx = L.tmax;
-        a.opt = opt_args(m.update);
+        a.opt = opt_args<real>(m.update);
         a.gout_lam = m.gout ? gout_lam_.p : nullptr; a.gout_bc = m.gout ? gout_bc_.p : nullptr;
         a.hcontrib = hcontrib_.p;
         // the supplied-noise kernels always carry the ELBO terms (ELBO = true instantiation only)

@@ -12,6 +12,8 @@
 // z: storing would add 2*K*w bytes per latent to a step whose algorithmic traffic
 // is 8*w bytes per latent.
 #pragma once
+#include <type_traits>
+
 #include "bb_types.cuh"
 
 namespace bb {
@@ -262,40 +264,68 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
 //   TruncatedADAGrad s   = sum of the last n g^2 (running form: s - evicted + g^2);
 //                    delta = eta*g / (tau + sqrt(s) + 1e-8)
 template <typename real>
-__device__ __forceinline__ void opt_apply(const OptArgs &o, real g, real &theta, real &acc, real &ring_slot) {
+__device__ __forceinline__ void opt_apply(const OptArgsT<real> &o, real g, real &theta, real &acc, real &ring_slot) {
     const real g2 = g * g;
     real denom;
     if (o.kind == 1) {
-        acc = fma(real(o.post), acc, real(o.tau) * g2);
+        acc = fma(o.post, acc, o.tau * g2);
         denom = bb_sqrt(acc) + real(1e-8);
     } else {
         acc = fmax(acc - ring_slot + g2, real(0));
         ring_slot = g2;
-        denom = real(o.tau) + bb_sqrt(acc) + real(1e-8);
+        denom = o.tau + bb_sqrt(acc) + real(1e-8);
     }
-    theta -= real(o.eta) * g * bb_rcp(denom);
+    theta -= o.eta * g * bb_rcp(denom);
 }
 
-// finish one latent: gradients of the objective, update (or emit), in place
-template <typename real>
-__device__ __forceinline__ void finish_latent(const OptArgs &o, real invK, real sgrad, real sgrade,
-                                              vec2<real> th, vec2<real> ac, vec2<real> *th_ptr,
-                                              vec2<real> *acc_ptr, vec2<real> *ring_ptr, vec2<real> *gout_ptr) {
+// finish one latent: gradients of the objective, update (or emit), in place.
+// MODE 0: DecayedADAGrad update | 1: TruncatedADAGrad update | 2: emit (dELBO/dmu, dELBO/domega) | 3: nothing.
+// The mode is block-uniform, so each instantiation is a straight line of ~40 instructions.
+template <typename real, int MODE>
+__device__ __forceinline__ void finish_latent_mode(const OptArgsT<real> &o, real invK, real sgrad, real sgrade,
+                                                   vec2<real> th, vec2<real> ac, vec2<real> *th_ptr,
+                                                   vec2<real> *acc_ptr, vec2<real> *ring_ptr, vec2<real> *gout_ptr) {
+    if constexpr (MODE == 3) return;
     // d ELBO / d mu = mean_k g ; d ELBO / d omega = (mean_k g eps + 1/sigma) sigmoid(omega)
     real sigma, sgm;
     softplus_sigmoid(th.y, sigma, sgm);
     const real gm = sgrad * invK;
     const real go = (sgrade * invK + bb_rcp(sigma)) * sgm;
-    if (o.update) {
-        vec2<real> rg = mk2<real>(0, 0);
-        if (o.kind == 0) rg = *ring_ptr;
-        opt_apply<real>(o, -gm, th.x, ac.x, rg.x);      // the engine minimises -ELBO
-        opt_apply<real>(o, -go, th.y, ac.y, rg.y);
+    if constexpr (MODE == 2) {
+        *gout_ptr = mk2<real>(gm, go);
+    } else {
+        const real g0 = -gm, g1 = -go;                  // the engine minimises -ELBO
+        const real q0 = g0 * g0, q1 = g1 * g1;
+        real d0, d1;
+        if constexpr (MODE == 0) {
+            ac.x = fma(o.post, ac.x, o.tau * q0);
+            ac.y = fma(o.post, ac.y, o.tau * q1);
+            d0 = bb_sqrt(ac.x) + real(1e-8);
+            d1 = bb_sqrt(ac.y) + real(1e-8);
+        } else {
+            const vec2<real> rg = *ring_ptr;
+            ac.x = fmax(ac.x - rg.x + q0, real(0));
+            ac.y = fmax(ac.y - rg.y + q1, real(0));
+            *ring_ptr = mk2<real>(q0, q1);
+            d0 = o.tau + bb_sqrt(ac.x) + real(1e-8);
+            d1 = o.tau + bb_sqrt(ac.y) + real(1e-8);
+        }
+        th.x -= o.eta * g0 * bb_rcp(d0);
+        th.y -= o.eta * g1 * bb_rcp(d1);
         *th_ptr = th;
         *acc_ptr = ac;
-        if (o.kind == 0) *ring_ptr = rg;
+    }
+}
+
+template <typename real>
+__device__ __forceinline__ void finish_latent(const OptArgsT<real> &o, real invK, real sgrad, real sgrade,
+                                              vec2<real> th, vec2<real> ac, vec2<real> *th_ptr,
+                                              vec2<real> *acc_ptr, vec2<real> *ring_ptr, vec2<real> *gout_ptr) {
+    if (o.update) {
+        if (o.kind == 1) finish_latent_mode<real, 0>(o, invK, sgrad, sgrade, th, ac, th_ptr, acc_ptr, ring_ptr, gout_ptr);
+        else finish_latent_mode<real, 1>(o, invK, sgrad, sgrade, th, ac, th_ptr, acc_ptr, ring_ptr, gout_ptr);
     } else if (gout_ptr) {
-        *gout_ptr = mk2<real>(gm, go);
+        finish_latent_mode<real, 2>(o, invK, sgrad, sgrade, th, ac, th_ptr, acc_ptr, ring_ptr, gout_ptr);
     }
 }
 
@@ -540,26 +570,35 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
         }
         if (want_elbo) sel[a.K * BLOCK + tid] += lsig_sum;
 
-        // fused optimiser update of every latent of the column (theta / accumulators re-read from the stage)
+        // fused optimiser update of every latent of the column (theta / accumulators re-read from the
+        // stage); the mode is kernel-uniform, so branch once around straight-line per-latent code
+        auto finish_all = [&](auto mode_tag) {
+            constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll
-        for (int t = 0; t < S::MAXT; ++t) {
-            if (t >= nt) break;
-            const size_t o = (size_t)t * cpad + c;
-            finish_latent<real>(a.opt, invK, sgr[t], sge[t], sth[t * BLOCK], sac[t * BLOCK], C.lam_th + o,
-                                C.lam_acc + o,
-                                C.lam_ring ? C.lam_ring + (size_t)a.opt.slot * a.opt.ring_stride_lam + o : nullptr,
-                                a.gout_lam ? a.gout_lam + o : nullptr);
+            for (int t = 0; t < S::MAXT; ++t) {
+                if (t >= nt) break;
+                const size_t o = (size_t)t * cpad + c;
+                finish_latent_mode<real, MODE>(a.opt, invK, sgr[t], sge[t], sth[t * BLOCK], sac[t * BLOCK],
+                                               C.lam_th + o, C.lam_acc + o, C.lam_ring + o, a.gout_lam + o);
+            }
+            if (!seg.neutral) {
+#pragma unroll
+                for (int j = 0; j < S::MAXJ; ++j) {
+                    if (j >= nj) break;
+                    const size_t o = (size_t)j * cpad + c;
+                    finish_latent_mode<real, MODE>(a.opt, invK, sgrb[j], sgeb[j], sth[(nt + j) * BLOCK],
+                                                   sac[(nt + j) * BLOCK], C.bc_th + o, C.bc_acc + o, C.bc_ring + o,
+                                                   a.gout_bc + o);
+                }
+            }
+        };
+        if (a.opt.update) {
+            if (a.opt.kind == 1) finish_all(std::integral_constant<int, 0>{});
+            else finish_all(std::integral_constant<int, 1>{});
+        } else if (a.gout_lam) {
+            finish_all(std::integral_constant<int, 2>{});
         }
         if (!seg.neutral) {
-#pragma unroll
-            for (int j = 0; j < S::MAXJ; ++j) {
-                if (j >= nj) break;
-                const size_t o = (size_t)j * cpad + c;
-                finish_latent<real>(a.opt, invK, sgrb[j], sgeb[j], sth[(nt + j) * BLOCK], sac[(nt + j) * BLOCK],
-                                    C.bc_th + o, C.bc_acc + o,
-                                    C.bc_ring ? C.bc_ring + (size_t)a.opt.slot * a.opt.ring_stride_bc + o : nullptr,
-                                    a.gout_bc ? a.gout_bc + o : nullptr);
-            }
             if constexpr (HIER) {
 #pragma unroll
                 for (int e = 0; e < S::MAXE; ++e) {

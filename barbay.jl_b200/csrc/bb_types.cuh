@@ -44,16 +44,14 @@ template <typename real> struct ColArrays {
     vec2<real> bc_pr_s[3];            // by kind: direct {s, logsigma}; hier {theta-tilde, log-tau, log-sigma}
     const int *hgroup;                // [cpad] hyper-latent base index of the column (hier), else nullptr
     const uint32_t *col_id;           // [cpad] canonical column ids, or nullptr -> seg.colid0 + i
-    vec2<real> *lam_ring;             // TruncatedADAGrad ring [n][tmax][cpad] of (g_mu^2, g_omega^2)
-    vec2<real> *bc_ring;              // [n][nj][cpad]
+    vec2<real> *lam_ring;             // TruncatedADAGrad: the ring slot written this step, [tmax][cpad] of (g_mu^2, g_omega^2)
+    vec2<real> *bc_ring;              // [nj][cpad] (the host offsets the [n][...] rings by slot)
 };
 
-struct OptArgs {
+template <typename real> struct OptArgsT {
     int kind;        // bb_opt_kind
     int update;      // 1: apply the optimiser; 0: only emit gradients
-    double eta, tau, post;   // tau doubles as `pre` for DecayedADAGrad
-    int slot;        // ring slot written this step (Truncated)
-    long long ring_stride_lam, ring_stride_bc;   // elements between ring slots
+    real eta, tau, post;     // tau doubles as `pre` for DecayedADAGrad; typed by the kernel's arithmetic
 };
 
 // caller-supplied noise / per-sample dumps, device layout (SUPPLIED kernels only)
@@ -94,7 +92,7 @@ template <typename real> struct P2Args {
     int H;
     const real *ctx;       // [R][K][3][tmax]: (c_t - sbar_t), G_Lambda_t, wbar_t
     int tmax_ctx;
-    OptArgs opt;
+    OptArgsT<real> opt;
     vec2<real> *gout_lam;  // (dELBO/dmu, dELBO/domega) [tmax][cpad] when !opt.update, else nullptr
     vec2<real> *gout_bc;   // [nj][cpad]
     vec2<real> *hcontrib;  // [E][cpad] (sum_k g_s, sum_k g_s eps_theta) (hier)
