@@ -10,7 +10,8 @@ import os
 
 ABI_VERSION = 1
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbarbay_b200.so")
+# BB_LIB_PATH: tuning builds of the same library (development only)
+LIB_PATH = os.environ.get("BB_LIB_PATH") or os.path.join(_HERE, "libbarbay_b200.so")
 
 MODEL_IDS = {
     "fitness_normal": 0,

@@ -13,9 +13,10 @@ enum { Q_LAM = 0, Q_DN = 1, Q_D2N = 2, Q_A = 3, Q_W = 4, NQ = 5 };
 struct ReduceArgs {
     SegList segs;
     int K, tmax, pv, nt;     // pv / nt of this launch group
+    int nblk;                // CTAs of the pass-1 launch (row length of part)
     int w_single;            // E == 1: mutant W stored once (slot 2nt-1)
     unsigned rep_mask;       // replicates belonging to this launch group (bit r)
-    const double *part;      // [blocks][K][pv]
+    const double *part;      // [K][pv][nblk]
     double *sums;
 };
 
@@ -37,7 +38,8 @@ static __global__ void __launch_bounds__(128) reduce_kernel(const ReduceArgs a, 
         if (q == Q_LAM) v = t;
         else if (q == Q_DN || q == Q_D2N) { if (!sg.neutral) continue; v = (q == Q_DN ? nt : 2 * nt - 1) + t; }
         else { if (sg.neutral) continue; v = q == Q_A ? nt + t : (a.w_single ? 2 * nt - 1 : 2 * nt - 1 + t); }
-        for (int b = sg.blk0 + lane; b < sg.blk1; b += 32) s += a.part[((size_t)b * a.K + k) * a.pv + v];
+        const double *row = a.part + ((size_t)k * a.pv + v) * a.nblk;
+        for (int b = sg.blk0 + lane; b < sg.blk1; b += 32) s += row[b];
     }
     s = warp_sum<double>(s);
     if (lane == 0) a.sums[((size_t)(r * a.K + k) * NQ + q) * a.tmax + t] = s;
@@ -56,7 +58,7 @@ template <typename real> struct SharedArgs {
     const double *eps_sh;         // supplied noise [K][2 nst] or nullptr
     int z_direct;
     real *ctx;                    // [R][K][3][tmax]
-    double *scratch;              // [K][2 nst] per-sample gradients
+    double *scratch;              // per-sample gradients [K][2 nst], then eps, z [K][2 nst] each, u, lp [R][K][tmax] each
     double2 *gout;                // [2 nst] (dELBO/dmu, dELBO/domega) when !opt.update
     double *dump;                 // [K][2 nst] per-sample d log pi/dz or nullptr
     double *elbo_sh;              // [K+1]: neutral-likelihood + shared-prior log-density per k; sum log sigma
@@ -66,71 +68,78 @@ template <typename real> struct SharedArgs {
 
 __device__ __forceinline__ double softplus_d(double w) { return fmax(w, 0.0) + log1p(exp(-fabs(w))); }
 
+// One CTA; every phase is parallel over its natural index and separated by a block barrier.
+//   phase 0  (k, i)        noise and z of the shared latents                 -> eps_z scratch
+//   phase 1  (r, k, t<T-1) c_t, residual sums u_t, per-sample gradients, ctx -> scratch
+//   phase 2  (r, k, t<T)   G_Lambda_t = (u_{t-1} - u_t) / Lambda_t           -> ctx
+//   phase 3  (i)           mean over samples, optimiser update (or emit)
 template <typename real>
-__global__ void __launch_bounds__(128) shared_kernel(const SharedArgs<real> a) {
-    const int tid = threadIdx.x;
+__global__ void __launch_bounds__(256) shared_kernel(const SharedArgs<real> a) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int n2 = 2 * a.nst;
-    __shared__ double s_lp[MAX_K_SHARED];
-    for (int k = tid; k < a.K; k += blockDim.x) s_lp[k] = 0.0;
+    double *eps_t = a.scratch + (size_t)a.K * n2;            // [K][n2] eps
+    double *z_t = eps_t + (size_t)a.K * n2;                  // [K][n2] z
+    double *u_t = z_t + (size_t)a.K * n2;                    // [R][K][tmax] sum_all w res
+    double *lp_t = u_t + (size_t)a.R * a.K * a.tmax;         // [R][K][tmax] log-density pieces
+    double *lsig_t = lp_t + (size_t)a.R * a.K * a.tmax;      // [n2] log sigma before the update
+    // ---- phase 0
+    for (int j = tid; j < a.K * n2; j += nthr) {
+        const int k = j / n2, i = j % n2;
+        const double e = a.eps_sh ? a.eps_sh[j]
+                                  : stream_normal<double>(STREAM_SHARED, (uint32_t)i, (uint32_t)k, a.step, a.key);
+        const double2 th = a.sh_th[i];
+        const double sigma = softplus_d(th.y);
+        eps_t[j] = e;
+        z_t[j] = a.z_direct ? e : th.x + sigma * e;
+        if (k == 0) lsig_t[i] = log(sigma);
+    }
     __syncthreads();
-    // ---- phase A: one thread per (replicate, sample)
-    for (int rk = tid; rk < a.R * a.K; rk += blockDim.x) {
-        const int r = rk / a.K, k = rk % a.K;
-        const int nt = a.nt[r], sh0 = a.sh0[r];
+    // ---- phase 1
+    for (int j = tid; j < a.R * a.K * a.tmax; j += nthr) {
+        const int t = j % a.tmax, k = (j / a.tmax) % a.K, r = j / (a.tmax * a.K);
+        const int nt = a.nt[r];
+        u_t[j] = 0.0; lp_t[j] = 0.0;
+        if (t >= nt - 1) continue;
+        const int is = a.sh0[r] + t, il = a.nst + a.sh0[r] + t;
         const double *S = a.sums + (size_t)(r * a.K + k) * NQ * a.tmax;
         real *ctx = a.ctx + (size_t)(r * a.K + k) * 3 * a.tmax;
-        double uprev = 0.0, lp = 0.0;
-        for (int t = 0; t < nt; ++t) {
-            double u = 0.0;
-            if (t < nt - 1) {
-                const int is = sh0 + t, il = a.nst + sh0 + t;
-                double es, el;
-                if (a.eps_sh) { es = a.eps_sh[(size_t)k * n2 + is]; el = a.eps_sh[(size_t)k * n2 + il]; }
-                else {
-                    es = stream_normal<double>(STREAM_SHARED, (uint32_t)is, (uint32_t)k, a.step, a.key);
-                    el = stream_normal<double>(STREAM_SHARED, (uint32_t)il, (uint32_t)k, a.step, a.key);
-                }
-                const double2 ths = a.sh_th[is], thl = a.sh_th[il];
-                const double zs = a.z_direct ? es : ths.x + softplus_d(ths.y) * es;   // s-bar_t
-                const double zl = a.z_direct ? el : thl.x + softplus_d(thl.y) * el;   // log-sigma-bar_t
-                const double c = log(S[Q_LAM * a.tmax + t + 1]) - log(S[Q_LAM * a.tmax + t]);
-                const double wbar = exp(-2.0 * zl);
-                const double av = zs - c;
-                const double dn = S[Q_DN * a.tmax + t], d2n = S[Q_D2N * a.tmax + t];
-                const double am = S[Q_A * a.tmax + t], wm = S[Q_W * a.tmax + t];
-                const double qn = d2n + 2.0 * av * dn + a.n_neutral * av * av;   // sum_neutral res^2
-                u = wbar * (dn + a.n_neutral * av) + (am + av * wm);            // sum_all w res
-                const double2 ps = a.sh_pr[is], pl = a.sh_pr[il];
-                a.scratch[(size_t)k * n2 + is] = -u - (zs - ps.x) * ps.y;
-                a.scratch[(size_t)k * n2 + il] = wbar * qn - a.n_neutral - (zl - pl.x) * pl.y;
-                lp += -a.n_neutral * zl - 0.5 * wbar * qn
-                      - 0.5 * (zs - ps.x) * (zs - ps.x) * ps.y - 0.5 * (zl - pl.x) * (zl - pl.x) * pl.y;
-                ctx[0 * a.tmax + t] = (real)(c - zs);
-                ctx[2 * a.tmax + t] = (real)wbar;
-            }
-            ctx[1 * a.tmax + t] = (real)((uprev - u) / S[Q_LAM * a.tmax + t]);
-            uprev = u;
-        }
-        atomicAdd(&s_lp[k], lp);      // R <= MAX_SEG terms per k; order-insensitive to ~1e-16, reporting only
+        const double zs = z_t[(size_t)k * n2 + is], zl = z_t[(size_t)k * n2 + il];   // s-bar_t, log-sigma-bar_t
+        const double c = log(S[Q_LAM * a.tmax + t + 1]) - log(S[Q_LAM * a.tmax + t]);
+        const double wbar = exp(-2.0 * zl);
+        const double av = zs - c;
+        const double dn = S[Q_DN * a.tmax + t], d2n = S[Q_D2N * a.tmax + t];
+        const double am = S[Q_A * a.tmax + t], wm = S[Q_W * a.tmax + t];
+        const double qn = d2n + 2.0 * av * dn + a.n_neutral * av * av;   // sum_neutral res^2
+        const double u = wbar * (dn + a.n_neutral * av) + (am + av * wm);   // sum_all w res
+        const double2 ps = a.sh_pr[is], pl = a.sh_pr[il];
+        a.scratch[(size_t)k * n2 + is] = -u - (zs - ps.x) * ps.y;
+        a.scratch[(size_t)k * n2 + il] = wbar * qn - a.n_neutral - (zl - pl.x) * pl.y;
+        u_t[j] = u;
+        lp_t[j] = -a.n_neutral * zl - 0.5 * wbar * qn - 0.5 * (zs - ps.x) * (zs - ps.x) * ps.y -
+                  0.5 * (zl - pl.x) * (zl - pl.x) * pl.y;
+        ctx[0 * a.tmax + t] = (real)(c - zs);
+        ctx[2 * a.tmax + t] = (real)wbar;
     }
-    __threadfence_block();
     __syncthreads();
-    // ---- phase B: one thread per shared latent
+    // ---- phase 2
+    for (int j = tid; j < a.R * a.K * a.tmax; j += nthr) {
+        const int t = j % a.tmax, k = (j / a.tmax) % a.K, r = j / (a.tmax * a.K);
+        if (t >= a.nt[r]) continue;
+        const double *S = a.sums + (size_t)(r * a.K + k) * NQ * a.tmax;
+        const double uprev = t > 0 ? u_t[j - 1] : 0.0;
+        a.ctx[(size_t)(r * a.K + k) * 3 * a.tmax + 1 * a.tmax + t] = (real)((uprev - u_t[j]) / S[Q_LAM * a.tmax + t]);
+    }
+    // ---- phase 3
     const double invK = 1.0 / a.K;
-    double lsig = 0.0;
-    for (int i = tid; i < n2; i += blockDim.x) {
+    for (int i = tid; i < n2; i += nthr) {
         double2 th = a.sh_th[i];
         const double sigma = softplus_d(th.y);
         double sg = 0.0, sge = 0.0;
         for (int k = 0; k < a.K; ++k) {
             const double g = a.scratch[(size_t)k * n2 + i];
-            const double e = a.eps_sh ? a.eps_sh[(size_t)k * n2 + i]
-                                      : stream_normal<double>(STREAM_SHARED, (uint32_t)i, (uint32_t)k, a.step,
-                                                              a.key);
-            sg += g; sge += g * e;
+            sg += g; sge += g * eps_t[(size_t)k * n2 + i];
             if (a.dump) a.dump[(size_t)k * n2 + i] = g;
         }
-        lsig += log(sigma);
         const double gm = sg * invK;
         const double go = (sge * invK + 1.0 / sigma) / (1.0 + exp(-th.y));
         if (a.opt.update) {
@@ -147,14 +156,16 @@ __global__ void __launch_bounds__(128) shared_kernel(const SharedArgs<real> a) {
         }
     }
     if (a.elbo_sh) {
-        __shared__ double s_ls[128];
-        s_ls[tid] = lsig;
-        __syncthreads();
-        if (tid == 0) {
+        // fixed-order sums: deterministic ELBO terms of the shared latents (reported by rank 0 only)
+        for (int k = tid; k <= a.K; k += nthr) {
             double s = 0.0;
-            for (int j = 0; j < blockDim.x; ++j) s += s_ls[j];
-            a.elbo_sh[a.K] = a.leader ? s : 0.0;
-            for (int k = 0; k < a.K; ++k) a.elbo_sh[k] = a.leader ? s_lp[k] : 0.0;
+            if (k < a.K) {
+                for (int r = 0; r < a.R; ++r)
+                    for (int t = 0; t < a.tmax; ++t) s += lp_t[(size_t)(r * a.K + k) * a.tmax + t];
+            } else {
+                for (int i = 0; i < n2; ++i) s += lsig_t[i];
+            }
+            a.elbo_sh[k] = a.leader ? s : 0.0;
         }
     }
 }

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -255,7 +256,7 @@ template <typename real> Engine<real>::Engine(const bb_desc &d) {
     }
     sums_.alloc((size_t)L.R * L.K * NQ * L.tmax);
     ctx_.alloc((size_t)L.R * L.K * 3 * L.tmax);
-    sh_scratch_.alloc((size_t)L.K * 2 * L.nst);
+    sh_scratch_.alloc((size_t)3 * L.K * 2 * L.nst + (size_t)2 * L.R * L.K * L.tmax + 2 * L.nst);
     elbo_sh_.alloc(L.K + 1);
     elbo_out_.alloc(L.K + 1);
     build_groups();
@@ -326,7 +327,10 @@ template <typename real> void Engine<real>::build_groups() {
         const int pv_m = L.E == 1 ? 2 * nt : g.pv;
         const size_t slot_b = (size_t)BLOCK * sizeof(real);
         int slots = L.K * pv_m;
-        const int max_slots = (int)((44 * 1024) / slot_b);
+        // BB_P1_ACC_KB (tuning knob): shared-memory budget of the pass-1 accumulators
+        const char *acc_kb_env = getenv("BB_P1_ACC_KB");
+        const int acc_kb = acc_kb_env ? std::max(4, atoi(acc_kb_env)) : 44;
+        const int max_slots = (int)((acc_kb * 1024) / slot_b);
         if (slots > max_slots) {
             const int sweeps = (slots + max_slots - 1) / max_slots;
             slots = ((L.K + sweeps - 1) / sweeps) * pv_m;
@@ -568,7 +572,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         if (tev_pos_ >= 0 && &g == &groups_.back()) BB_CUDA(cudaEventRecord(tev_[tev_pos_++], stream_));
         ReduceArgs ra{};
         ra.segs = g.p1segs; ra.K = L.K; ra.tmax = L.tmax; ra.pv = g.pv; ra.nt = g.nt;
-        ra.w_single = L.E == 1 ? 1 : 0; ra.rep_mask = g.rep_mask;
+        ra.w_single = L.E == 1 ? 1 : 0; ra.rep_mask = g.rep_mask; ra.nblk = g.p1blocks;
         ra.part = a.part; ra.sums = sums_.p;
         const int nwarps = L.R * L.K * NQ * L.tmax;
         reduce_kernel<<<cdiv((long long)nwarps * 32, 128), 128, 0, stream_>>>(ra, L.R);
@@ -594,7 +598,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         sa.elbo_sh = m.want_elbo ? elbo_sh_.p : nullptr;
         sa.opt = opt_args<double>(m.update);
         sa.leader = L.rank == 0 ? 1 : 0;
-        shared_kernel<real><<<1, 128, 0, stream_>>>(sa);
+        shared_kernel<real><<<1, 256, 0, stream_>>>(sa);
         ++launches;
     }
     // ---- pass 2

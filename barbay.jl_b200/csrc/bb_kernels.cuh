@@ -17,9 +17,18 @@
 #include "bb_types.cuh"
 
 namespace bb {
+#ifndef BB_P1_UNROLL
+#define BB_P1_UNROLL 2
+#endif
 #ifndef BB_P2_MIN_BLOCKS
 #define BB_P2_MIN_BLOCKS 6
 #endif
+#ifndef BB_P2_UNROLL
+#define BB_P2_UNROLL 1
+#endif
+
+constexpr int kP1Unroll = BB_P1_UNROLL;   // MC samples of pass 1 interleaved per thread (ILP)
+constexpr int kP2Unroll = BB_P2_UNROLL;
 
 template <int NT> struct TD { static constexpr int MAX = NT > 0 ? NT : MAX_NT_DYN; };
 template <int NE> struct ED { static constexpr int MAX = NE > 0 ? NE : MAX_NE_DYN; };
@@ -193,6 +202,7 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
             }
             const int nclass = seg.neutral ? nt : nt + nj;
 
+#pragma unroll kP1Unroll
             for (int k = kc0; k < kc1; ++k) {
                 real eps[S::MAXC];
                 column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key,
@@ -251,7 +261,8 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
             s = warp_sum<double>(s);
             if (lane == 0) {
                 const int kl = row / pvs, v = row % pvs;
-                a.part[((size_t)blockIdx.x * a.K + kc0 + kl) * pv + v] = s;
+                // [k][v][block]: the reducer reads consecutive blocks (coalesced)
+                a.part[((size_t)(kc0 + kl) * pv + v) * gridDim.x + blockIdx.x] = s;
             }
         }
         __syncthreads();
@@ -458,6 +469,7 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
         }
         const int nclass = seg.neutral ? nt : nt + nj;
 
+#pragma unroll kP2Unroll
         for (int k = 0; k < a.K; ++k) {
             real eps[S::MAXC];
             column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, a.sup,
