@@ -1,0 +1,131 @@
+"""GPU parity beyond the four fixtures: matrix priors, the multienv x replicate model (M5), the
+runtime-T / runtime-E fallback kernels, a 10^4-barcode synthetic, and size-independent properties
+at the full BASELINE size."""
+import numpy as np
+import pytest
+
+from helpers import load_fixture, oracle_problem, plausible_latents, plausible_theta, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_logjoint(bb, da, model, kwargs, priors, dtype="f64", K=2, seed=0, tol=1e-9):
+    from oracle import model_ref
+    eng = bb.Engine(da, model, kwargs, n_samples=K, dtype=dtype, seed=1)
+    rng = np.random.default_rng(seed)
+    z = plausible_latents(eng.layout, da, rng, K)
+    logp, grad = eng.logjoint_grad(z)
+    prob = oracle_problem(da, model, priors=priors)
+    for k in range(K):
+        lp_ref, g_ref = model_ref.logjoint_and_grad(model, z[k], prob)
+        assert abs(logp[k] - lp_ref) <= tol * abs(lp_ref), (logp[k], lp_ref)
+        assert rel_err(grad[k], g_ref) <= tol, rel_err(grad[k], g_ref)
+    eng.close()
+
+
+@pytest.mark.parametrize("model", ["fitness_normal", "replicate_fitness_normal", "multienv_fitness_normal",
+                                   "genotype_fitness_normal"])
+def test_matrix_priors(bb, model):
+    """Per-element n x 2 priors (model_fitness_normal.jl:137-203), the documented workflow with
+    stats.naive_prior (docs/src/examples.md:121-140)."""
+    df, cols = load_fixture(model)
+    da = bb.utils.data_to_arrays(df, **cols)
+    lay = bb.model.var_groups(bb.model.resolve(model), da.n_time, da.n_rep, da.n_neutral, da.n_bc, da.n_env, da.n_geno)
+    rng = np.random.default_rng(4)
+    size = {g.name: g.length for g in lay.groups}
+    M = bb.model
+
+    def mat(n, mean, sd):
+        return np.column_stack([mean + 0.3 * rng.standard_normal(n), sd * (0.5 + rng.random(n))])
+
+    R = np.asarray(da.bc_count)
+    flat = R.T.reshape(-1) if R.ndim == 2 else R.transpose(2, 1, 0).reshape(-1)
+    priors = {"s_pop_prior": mat(size[M.V_S_POP], 0.0, 0.5), "logσ_pop_prior": mat(size[M.V_LOGSIG_POP], -1.0, 0.5),
+              "logλ_prior": np.column_stack([np.log(flat + 1.0), np.full(flat.size, 3.0)]),
+              "logσ_bc_prior": mat(size[M.V_LOGSIG_BC], -1.0, 0.7)}
+    bc_name = M.V_THETA if bb.model.resolve(model).hier else M.V_S_BC
+    priors["s_bc_prior"] = mat(size[bc_name], 0.0, 1.0)
+    _check_logjoint(bb, da, model, dict(priors), priors)
+
+
+def test_multienv_replicate_model(bb):
+    """M5: src/model_multienv_fitness_normal_hierarchical_replicates.jl:158-363."""
+    df, _ = load_fixture("replicate_fitness_normal")
+    df = df.assign(env=df.time.map({1: "A", 2: "A", 3: "B", 4: "C", 5: "B"}))
+    da = bb.utils.data_to_arrays(df, rep_col="rep", env_col="env")
+    _check_logjoint(bb, da, "multienv_replicate_fitness_normal", {"envs": da.envs}, None)
+    _check_logjoint(bb, da, "multienv_replicate_fitness_normal", {"envs": da.envs}, None, dtype="f32", tol=2e-3)
+
+
+@pytest.mark.parametrize("n_time", [3, 6, 11])
+def test_runtime_time_points_fallback(bb, n_time):
+    """T without a compiled specialisation runs on the runtime-size kernels."""
+    da, _ = bb.synth.simulate("fitness_normal", 6, 40, n_time, seed=3)
+    _check_logjoint(bb, da, "fitness_normal", {}, None)
+
+
+def test_many_environments_fallback(bb):
+    da, _ = bb.synth.simulate("multienv_fitness_normal", 5, 30, 9, envs=[1, 2, 3, 4, 5, 6, 1, 2, 3], seed=5)
+    _check_logjoint(bb, da, "multienv_fitness_normal", {"envs": da.envs}, None)
+
+
+def test_synthetic_ten_thousand_barcodes(bb):
+    """SURVEY §8d gate (2): log-joint / gradient parity on a 10^4-barcode synthetic, fp64 and fp32."""
+    da, _ = bb.synth.simulate("fitness_normal", 100, 9_900, 5, seed=9)
+    _check_logjoint(bb, da, "fitness_normal", {}, None, K=1)
+    _check_logjoint(bb, da, "fitness_normal", {}, None, K=1, dtype="f32", tol=2e-3)
+
+
+def test_genotype_groups_of_uneven_size(bb):
+    da, _ = bb.synth.simulate("genotype_fitness_normal", 8, 200, 5, n_geno=7, seed=2)
+    _check_logjoint(bb, da, "genotype_fitness_normal", {"genotypes": da.genotypes}, None)
+
+
+def test_elbo_gradient_many_samples_chunked(bb):
+    """K large enough that pass 1 sweeps the samples in chunks (shared-memory budget)."""
+    from oracle import advi_ref
+    model, K = "fitness_normal", 24
+    df, cols = load_fixture(model)
+    da = bb.utils.data_to_arrays(df, **cols)
+    eng = bb.Engine(da, model, n_samples=K, dtype="f64", seed=2)
+    rng = np.random.default_rng(1)
+    mu, om = plausible_theta(eng.layout, da, rng)
+    eps = rng.standard_normal((K, eng.D))
+    eng.set_params(mu, om)
+    elbo, g_mu, g_om = eng.elbo_grad(eps)
+    e_ref, gm, go, _ = advi_ref.elbo_value_and_grad(model, oracle_problem(da, model), mu, om, eps)
+    assert abs(elbo - e_ref) <= 1e-9 * abs(e_ref) and rel_err(g_mu, gm) < 1e-9 and rel_err(g_om, go) < 1e-9
+    eng.close()
+
+
+def test_full_size_properties(bb):
+    """BASELINE configs[1] at full size (10^6 barcodes): properties that need no oracle run --
+    determinism (same seed => bitwise same theta), fp32 vs fp64 agreement on the same noise lattice,
+    ELBO increases, state round trip."""
+    model, da, _ = bb.synth.config(2)
+    out = {}
+    for dtype in ("f32", "f64"):
+        eng = bb.Engine(da, model, n_samples=2, dtype=dtype, seed=3)
+        eng.init_params(1)
+        eng.set_optimizer("decayed")
+        tr = eng.step(5, elbo_trace=True)
+        out[dtype] = (tr, *eng.get_posterior())
+        if dtype == "f32":
+            eng2 = bb.Engine(da, model, n_samples=2, dtype=dtype, seed=3)
+            eng2.init_params(1)
+            eng2.set_optimizer("decayed")
+            eng2.step(5)
+            m2, s2 = eng2.get_posterior()
+            assert np.array_equal(m2, out[dtype][1]) and np.array_equal(s2, out[dtype][2])   # bitwise
+            state = eng2.get_state()
+            eng2.step(2)
+            eng2.set_state(state)
+            m3, _ = eng2.get_posterior()
+            assert np.array_equal(m3, m2) and eng2.step_count == 5
+            eng2.close()
+        eng.close()
+    tr32, m32, s32 = out["f32"]
+    tr64, m64, s64 = out["f64"]
+    assert tr64[-1] > tr64[0]
+    assert np.all(np.abs(tr32 - tr64) <= 1e-4 * np.abs(tr64))
+    assert np.max(np.abs(m32 - m64)) < 5e-3 and np.max(np.abs(s32 - s64) / s64) < 5e-3
