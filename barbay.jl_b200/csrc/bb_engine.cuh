@@ -84,6 +84,7 @@ template <typename T> struct DBuf {
 };
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+constexpr size_t kMaxSmem = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
 
 class EngineBase {
   public:
@@ -149,6 +150,7 @@ template <typename real> class Engine : public EngineBase {
         KernelSet<real> ks, ks_sup;
         int pv = 0, kchunk = 0;
         size_t p1smem = 0, p2smem = 0, p2smem_elbo = 0;
+        int p1nbuf = 2, p2nbuf = 2, p2stage_acc = 1;
         size_t part_off = 0, epart_off = 0;     // block offsets into part_ / epart_
     };
     struct RunMode {
@@ -162,6 +164,7 @@ template <typename real> class Engine : public EngineBase {
     };
 
     void build_groups();
+    void size_pass2();
     void assign_blocks(SegList &sl, int nt, int budget, int *nblocks);
     void run_pipeline(const RunMode &m);
     void upload_supplied(const double *x, int K);
@@ -261,7 +264,6 @@ template <typename real> Engine<real>::Engine(const bb_desc &d) {
     elbo_out_.alloc(L.K + 1);
     build_groups();
     part_.alloc((size_t)p1blocks_total_ * L.K * (3 * L.tmax));
-    epart_.alloc((size_t)p2blocks_total_ * (L.K + 1));
 
     // algorithmic bytes per step of this shard: theta + accumulators read and written
     // once, int32 counts read once; matrix priors read once.
@@ -312,8 +314,7 @@ template <typename real> void Engine<real>::build_groups() {
     std::vector<int> distinct;
     for (int r = 0; r < L.R; ++r)
         if (std::find(distinct.begin(), distinct.end(), L.nt[r]) == distinct.end()) distinct.push_back(L.nt[r]);
-    const size_t smem_limit = 112 * 1024;
-    size_t part_off = 0, epart_off = 0;
+    size_t part_off = 0;
     for (int nt : distinct) {
         Group g;
         g.nt = nt;
@@ -339,30 +340,57 @@ template <typename real> void Engine<real>::build_groups() {
         g.kchunk = slots;
         // + two cp.async staging buffers (see bb_kernels.cuh)
         const size_t th_b = (size_t)(L.tmax + L.nj) * BLOCK * sizeof(r2);
-        g.p1smem = ((size_t)g.kchunk * slot_b + 15) / 16 * 16 + 2 * th_b;
-        const size_t ctx_b = (((size_t)L.K * 3 * L.tmax * sizeof(real)) + 15) / 16 * 16;
-        const int npr = (L.lam_pr_matrix || L.bc_pr_matrix) ? 1 : 0;
-        const size_t buf_b = (2 + npr) * th_b + (size_t)L.tmax * BLOCK * sizeof(int);
-        g.p2smem = ctx_b + 2 * buf_b;                                             // ELBO = false kernels
-        g.p2smem_elbo = g.p2smem + (size_t)(L.K + 1) * BLOCK * sizeof(double);
-        for (auto *fn : {(const void *)g.ks.pass1, (const void *)g.ks_sup.pass1})
-            BB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p1smem));
+        const size_t p1acc = ((size_t)g.kchunk * slot_b + 15) / 16 * 16;
+        g.p1nbuf = p1acc + 2 * th_b <= kMaxSmem ? 2 : 1;
+        g.p1smem = p1acc + g.p1nbuf * th_b;
+        if (g.p1smem > kMaxSmem) throw std::runtime_error("T x E too large for the column kernels' shared memory");
+        BB_CUDA(cudaFuncSetAttribute((const void *)g.ks.pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p1smem));
+        BB_CUDA(cudaFuncSetAttribute((const void *)g.ks_sup.pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p1smem));
+        int occ1 = 1;
+        BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, g.ks.pass1, BLOCK, g.p1smem));
+        assign_blocks(g.p1segs, nt, nsm_ * std::max(occ1, 1), &g.p1blocks);
+        g.part_off = part_off;
+        part_off += g.p1blocks;
+        groups_.push_back(g);
+    }
+    p1blocks_total_ = (int)part_off;
+    size_pass2();
+}
+
+// pass-2 shared memory, occupancy and grid: depends on the optimiser (ring staging), so it is redone
+// by set_optimizer
+template <typename real> void Engine<real>::size_pass2() {
+    const size_t th_b = (size_t)(L.tmax + L.nj) * BLOCK * sizeof(r2);
+    const size_t ctx_b = (((size_t)L.K * 3 * L.tmax * sizeof(real)) + 15) / 16 * 16;
+    const int npr = (L.lam_pr_matrix || L.bc_pr_matrix) ? 1 : 0;
+    const int nrg = opt_.kind == BB_OPT_TRUNCATED_ADAGRAD ? 1 : 0;
+    size_t epart_off = 0;
+    for (Group &g : groups_) {
+        // staging level by shared-memory budget: (2 buffers, everything) -> (1 buffer, everything) ->
+        // (1 buffer, theta + counts only; accumulators / priors / ring read from global)
+        const size_t cn_b = (size_t)L.tmax * BLOCK * sizeof(int);
+        const size_t sel_b = (size_t)(L.K + 1) * BLOCK * sizeof(double);
+        const size_t full_b = (2 + npr + nrg) * th_b + cn_b;
+        g.p2nbuf = 2; g.p2stage_acc = 1;
+        size_t stage_b = 2 * full_b;
+        if (ctx_b + sel_b + stage_b > kMaxSmem) { g.p2nbuf = 1; stage_b = full_b; }
+        if (ctx_b + sel_b + stage_b > kMaxSmem) { g.p2stage_acc = 0; stage_b = th_b + cn_b; }
+        if (ctx_b + sel_b + stage_b > kMaxSmem)
+            throw std::runtime_error("T x E too large for the column kernels' shared memory");
+        g.p2smem = ctx_b + stage_b;                                               // ELBO = false kernels
+        g.p2smem_elbo = g.p2smem + sel_b;
         BB_CUDA(cudaFuncSetAttribute((const void *)g.ks.pass2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)g.p2smem));
         for (auto *fn : {(const void *)g.ks.pass2_elbo, (const void *)g.ks_sup.pass2_elbo})
             BB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p2smem_elbo));
-        int occ1 = 1, occ2 = 1;
-        BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, g.ks.pass1, BLOCK, g.p1smem));
+        int occ2 = 1;
         BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, g.ks.pass2, BLOCK, g.p2smem));
-        occ1 = std::max(occ1, 1); occ2 = std::max(occ2, 1);
-        assign_blocks(g.p1segs, nt, nsm_ * occ1, &g.p1blocks);
-        assign_blocks(g.p2segs, nt, nsm_ * occ2, &g.p2blocks);
-        g.part_off = part_off; g.epart_off = epart_off;
-        part_off += g.p1blocks; epart_off += g.p2blocks;
-        groups_.push_back(g);
+        assign_blocks(g.p2segs, g.nt, nsm_ * std::max(occ2, 1), &g.p2blocks);
+        g.epart_off = epart_off;
+        epart_off += g.p2blocks;
     }
-    p1blocks_total_ = (int)part_off;
     p2blocks_total_ = (int)epart_off;
+    epart_.alloc((size_t)p2blocks_total_ * (L.K + 1));
 }
 
 template <typename real> ColArrays<real> Engine<real>::col_arrays() const {
@@ -467,6 +495,7 @@ template <typename real> void Engine<real>::set_optimizer(const bb_opt &o) {
     opt_ = o;
     step_count = 0;
     ring_slot_ = 0;
+    size_pass2();
     const size_t nlam = lam_th_.n, nbc = bc_th_.n, nhy = hy_th_.n, nsh = sh_th_.n;
     if (o.kind == BB_OPT_TRUNCATED_ADAGRAD) {
         lam_ring_.alloc(nlam * o.n); bc_ring_.alloc(nbc * o.n);
@@ -566,7 +595,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         a.key = pkey; a.step = m.step;
         a.hy_zeps = zeps_.p; a.H = L.H;
         a.part = part_.p + (size_t)g.part_off * L.K * (3 * L.tmax);
-        a.pv = g.pv; a.sup = sup;
+        a.pv = g.pv; a.sup = sup; a.nbuf = g.p1nbuf;
         (m.sup ? g.ks_sup.pass1 : g.ks.pass1)<<<g.p1blocks, BLOCK, g.p1smem, stream_>>>(a);
         ++launches;
         if (tev_pos_ >= 0 && &g == &groups_.back()) BB_CUDA(cudaEventRecord(tev_[tev_pos_++], stream_));
@@ -618,6 +647,9 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         a.epart = elbo ? epart_.p + (size_t)g.epart_off * (L.K + 1) : nullptr;
         a.sup = sup;
         a.stage_pr = (L.lam_pr_matrix || L.bc_pr_matrix) ? 1 : 0;
+        // smem is sized for the ring by size_pass2(); stage it only when the ring exists and is updated
+        a.stage_ring = (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p && m.update) ? 1 : 0;
+        a.stage_acc = g.p2stage_acc; a.nbuf = g.p2nbuf;
         {
             const KernelSet<real> &ks = m.sup ? g.ks_sup : g.ks;
             if (elbo) ks.pass2_elbo<<<g.p2blocks, BLOCK, g.p2smem_elbo, stream_>>>(a);

@@ -170,10 +170,11 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
         __syncthreads();
 
         int buf = 0;
+        const int nbuf = a.nbuf;
         prefetch(blockIdx.x - seg.blk0, 0);
-        for (int tile = blockIdx.x - seg.blk0; tile < ntile; tile += nblk, buf ^= 1) {
-            prefetch(tile + nblk, buf ^ 1);
-            cp_async_wait<1>();
+        for (int tile = blockIdx.x - seg.blk0; tile < ntile; tile += nblk, buf ^= (nbuf - 1)) {
+            if (nbuf == 2) { prefetch(tile + nblk, buf ^ 1); cp_async_wait<1>(); }
+            else { if (tile != (int)blockIdx.x - seg.blk0) prefetch(tile, 0); cp_async_wait<0>(); }
             const int i = tile * BLOCK + tid;
             if (i >= seg.ncol) continue;
             const int c = seg.col0 + i;
@@ -294,8 +295,9 @@ __device__ __forceinline__ void opt_apply(const OptArgsT<real> &o, real g, real 
 // The mode is block-uniform, so each instantiation is a straight line of ~40 instructions.
 template <typename real, int MODE>
 __device__ __forceinline__ void finish_latent_mode(const OptArgsT<real> &o, real invK, real sgrad, real sgrade,
-                                                   vec2<real> th, vec2<real> ac, vec2<real> *th_ptr,
+                                                   vec2<real> th, vec2<real> ac, vec2<real> rg, vec2<real> *th_ptr,
                                                    vec2<real> *acc_ptr, vec2<real> *ring_ptr, vec2<real> *gout_ptr) {
+    // rg: the ring slot evicted this step (MODE 1 only)
     if constexpr (MODE == 3) return;
     // d ELBO / d mu = mean_k g ; d ELBO / d omega = (mean_k g eps + 1/sigma) sigmoid(omega)
     real sigma, sgm;
@@ -314,7 +316,6 @@ __device__ __forceinline__ void finish_latent_mode(const OptArgsT<real> &o, real
             d0 = bb_sqrt(ac.x) + real(1e-8);
             d1 = bb_sqrt(ac.y) + real(1e-8);
         } else {
-            const vec2<real> rg = *ring_ptr;
             ac.x = fmax(ac.x - rg.x + q0, real(0));
             ac.y = fmax(ac.y - rg.y + q1, real(0));
             *ring_ptr = mk2<real>(q0, q1);
@@ -333,10 +334,11 @@ __device__ __forceinline__ void finish_latent(const OptArgsT<real> &o, real invK
                                               vec2<real> th, vec2<real> ac, vec2<real> *th_ptr,
                                               vec2<real> *acc_ptr, vec2<real> *ring_ptr, vec2<real> *gout_ptr) {
     if (o.update) {
-        if (o.kind == 1) finish_latent_mode<real, 0>(o, invK, sgrad, sgrade, th, ac, th_ptr, acc_ptr, ring_ptr, gout_ptr);
-        else finish_latent_mode<real, 1>(o, invK, sgrad, sgrade, th, ac, th_ptr, acc_ptr, ring_ptr, gout_ptr);
+        const vec2<real> z2 = mk2<real>(0, 0);
+        if (o.kind == 1) finish_latent_mode<real, 0>(o, invK, sgrad, sgrade, th, ac, z2, th_ptr, acc_ptr, ring_ptr, gout_ptr);
+        else finish_latent_mode<real, 1>(o, invK, sgrad, sgrade, th, ac, *ring_ptr, th_ptr, acc_ptr, ring_ptr, gout_ptr);
     } else if (gout_ptr) {
-        finish_latent_mode<real, 2>(o, invK, sgrad, sgrade, th, ac, th_ptr, acc_ptr, ring_ptr, gout_ptr);
+        finish_latent_mode<real, 2>(o, invK, sgrad, sgrade, th, ac, mk2<real>(0, 0), th_ptr, acc_ptr, ring_ptr, gout_ptr);
     }
 }
 
@@ -373,8 +375,13 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
     const int rows = C.tmax + C.nj;
     const size_t th_bytes = (size_t)rows * BLOCK * sizeof(r2);
     const size_t cn_bytes = (size_t)C.tmax * BLOCK * sizeof(int);
-    const int npr = a.stage_pr ? 1 : 0;                     // matrix priors are staged too
-    const size_t buf_bytes = (2 + npr) * th_bytes + cn_bytes;   // theta, acc, [priors], counts
+    // what is staged (host decides by the shared-memory budget): theta + counts always; accumulators,
+    // matrix priors and the evicted TruncatedADAGrad ring slot when they fit; one or two buffers
+    const int nac = a.stage_acc ? 1 : 0;
+    const int npr = (a.stage_acc && a.stage_pr) ? 1 : 0;
+    const int nrg = (a.stage_acc && a.stage_ring) ? 1 : 0;
+    const size_t buf_bytes = (1 + nac + npr + nrg) * th_bytes + cn_bytes;   // theta, [acc], [priors], [ring], counts
+    const int nbuf = a.nbuf;
     unsigned char *stage0 = smem_raw + ctx_bytes + sel_bytes;
 
     auto prefetch = [&](int tile, int buf) {
@@ -384,16 +391,18 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
             unsigned char *base = stage0 + (size_t)buf * buf_bytes;
             r2 *sth = reinterpret_cast<r2 *>(base) + tid;
             r2 *sac = reinterpret_cast<r2 *>(base + th_bytes) + tid;
-            r2 *spr = reinterpret_cast<r2 *>(base + 2 * th_bytes) + tid;
-            int *scn = reinterpret_cast<int *>(base + (2 + npr) * th_bytes) + tid;
+            r2 *spr = reinterpret_cast<r2 *>(base + (1 + nac) * th_bytes) + tid;
+            r2 *srg = reinterpret_cast<r2 *>(base + (1 + nac + npr) * th_bytes) + tid;
+            int *scn = reinterpret_cast<int *>(base + (1 + nac + npr + nrg) * th_bytes) + tid;
 #pragma unroll
             for (int t = 0; t < S::MAXT; ++t) {
                 if (t >= nt) break;
                 const size_t o = (size_t)t * cpad + c;
                 cp_async<sizeof(r2)>(sth + t * BLOCK, C.lam_th + o);
-                cp_async<sizeof(r2)>(sac + t * BLOCK, C.lam_acc + o);
+                if (nac) cp_async<sizeof(r2)>(sac + t * BLOCK, C.lam_acc + o);
                 cp_async<4>(scn + t * BLOCK, C.cnt + o);
-                if (lam_mat) cp_async<sizeof(r2)>(spr + t * BLOCK, C.lam_pr + o);
+                if (lam_mat && npr) cp_async<sizeof(r2)>(spr + t * BLOCK, C.lam_pr + o);
+                if (nrg) cp_async<sizeof(r2)>(srg + t * BLOCK, C.lam_ring + o);
             }
             if (!seg.neutral) {
 #pragma unroll
@@ -401,8 +410,9 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
                     if (j >= nj) break;
                     const size_t o = (size_t)j * cpad + c;
                     cp_async<sizeof(r2)>(sth + (nt + j) * BLOCK, C.bc_th + o);
-                    cp_async<sizeof(r2)>(sac + (nt + j) * BLOCK, C.bc_acc + o);
-                    if (bc_mat) cp_async<sizeof(r2)>(spr + (nt + j) * BLOCK, C.bc_pr + o);
+                    if (nac) cp_async<sizeof(r2)>(sac + (nt + j) * BLOCK, C.bc_acc + o);
+                    if (bc_mat && npr) cp_async<sizeof(r2)>(spr + (nt + j) * BLOCK, C.bc_pr + o);
+                    if (nrg) cp_async<sizeof(r2)>(srg + (nt + j) * BLOCK, C.bc_ring + o);
                 }
             }
         }
@@ -423,9 +433,9 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
     else for (int t = 1; t < nt; ++t) n_of_e[a.env_of_t[t]] += 1;
 
     int buf = 0;
-    for (int tile = blockIdx.x - seg.blk0; tile < ntile; tile += nblk, buf ^= 1) {
-        prefetch(tile + nblk, buf ^ 1);
-        cp_async_wait<1>();
+    for (int tile = blockIdx.x - seg.blk0; tile < ntile; tile += nblk, buf ^= (nbuf - 1)) {
+        if (nbuf == 2) { prefetch(tile + nblk, buf ^ 1); cp_async_wait<1>(); }
+        else { if (tile != (int)blockIdx.x - seg.blk0) prefetch(tile, 0); cp_async_wait<0>(); }
         const int i = tile * BLOCK + tid;
         if (i >= seg.ncol) continue;
         const int c = seg.col0 + i;
@@ -433,8 +443,9 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
         unsigned char *base = stage0 + (size_t)buf * buf_bytes;
         const r2 *sth = reinterpret_cast<const r2 *>(base) + tid;
         const r2 *sac = reinterpret_cast<const r2 *>(base + th_bytes) + tid;
-        const r2 *spr = reinterpret_cast<const r2 *>(base + 2 * th_bytes) + tid;
-        const int *scn = reinterpret_cast<const int *>(base + (2 + npr) * th_bytes) + tid;
+        const r2 *spr = reinterpret_cast<const r2 *>(base + (1 + nac) * th_bytes) + tid;
+        const r2 *srg = reinterpret_cast<const r2 *>(base + (1 + nac + npr) * th_bytes) + tid;
+        const int *scn = reinterpret_cast<const int *>(base + (1 + nac + npr + nrg) * th_bytes) + tid;
 
         real mu[S::MAXT], sg[S::MAXT], sgr[S::MAXT], sge[S::MAXT], cnt[S::MAXT];
         double lsig_sum = 0.0;
@@ -485,7 +496,7 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
                 z[t] = fma(sg[t], eps[t], mu[t]);
                 const real lam = bb_exp(z[t]);
                 r2 p = C.lam_pr_s;
-                if (lam_mat) p = spr[t * BLOCK];
+                if (lam_mat) p = npr ? spr[t * BLOCK] : C.lam_pr[(size_t)t * cpad + c];
                 const real dz = z[t] - p.x;
                 // Poisson (collapsed Poisson x Multinomial) + logLambda coupling + Normal prior
                 g[t] = (cnt[t] - lam) + lam * cG[t] - dz * p.y;
@@ -562,7 +573,7 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
                 for (int j = 0; j < S::MAXJ; ++j) {
                     if (j >= nj) break;
                     r2 p = C.bc_pr_s[j % S::PER];
-                    if (bc_mat) p = spr[(nt + j) * BLOCK];
+                    if (bc_mat) p = npr ? spr[(nt + j) * BLOCK] : C.bc_pr[(size_t)j * cpad + c];
                     const real dz = zb[j] - p.x;
                     gb[j] -= dz * p.y;
                     if (want_elbo) lp -= real(0.5) * dz * dz * p.y;
@@ -590,17 +601,20 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
             for (int t = 0; t < S::MAXT; ++t) {
                 if (t >= nt) break;
                 const size_t o = (size_t)t * cpad + c;
-                finish_latent_mode<real, MODE>(a.opt, invK, sgr[t], sge[t], sth[t * BLOCK], sac[t * BLOCK],
-                                               C.lam_th + o, C.lam_acc + o, C.lam_ring + o, a.gout_lam + o);
+                const r2 ac = MODE >= 2 ? mk2<real>(0, 0) : (nac ? sac[t * BLOCK] : C.lam_acc[o]);
+                const r2 rg = MODE != 1 ? mk2<real>(0, 0) : (nrg ? srg[t * BLOCK] : C.lam_ring[o]);
+                finish_latent_mode<real, MODE>(a.opt, invK, sgr[t], sge[t], sth[t * BLOCK], ac, rg, C.lam_th + o,
+                                               C.lam_acc + o, C.lam_ring + o, a.gout_lam + o);
             }
             if (!seg.neutral) {
 #pragma unroll
                 for (int j = 0; j < S::MAXJ; ++j) {
                     if (j >= nj) break;
                     const size_t o = (size_t)j * cpad + c;
-                    finish_latent_mode<real, MODE>(a.opt, invK, sgrb[j], sgeb[j], sth[(nt + j) * BLOCK],
-                                                   sac[(nt + j) * BLOCK], C.bc_th + o, C.bc_acc + o, C.bc_ring + o,
-                                                   a.gout_bc + o);
+                    const r2 ac = MODE >= 2 ? mk2<real>(0, 0) : (nac ? sac[(nt + j) * BLOCK] : C.bc_acc[o]);
+                    const r2 rg = MODE != 1 ? mk2<real>(0, 0) : (nrg ? srg[(nt + j) * BLOCK] : C.bc_ring[o]);
+                    finish_latent_mode<real, MODE>(a.opt, invK, sgrb[j], sgeb[j], sth[(nt + j) * BLOCK], ac, rg,
+                                                   C.bc_th + o, C.bc_acc + o, C.bc_ring + o, a.gout_bc + o);
                 }
             }
         };

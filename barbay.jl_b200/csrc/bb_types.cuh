@@ -77,6 +77,7 @@ template <typename real> struct P1Args {
     int H;
     double *part;          // [gridDim.x][K][pv] block partial sums (double)
     int pv;                // slots per sample: nt + 2 (nt - 1)
+    int nbuf;              // staging buffers (2, or 1 when shared memory is short)
     SupArgs<real> sup;
 };
 
@@ -98,6 +99,9 @@ template <typename real> struct P2Args {
     vec2<real> *hcontrib;  // [E][cpad] (sum_k g_s, sum_k g_s eps_theta) (hier)
     double *epart;         // [gridDim.x][K+1] ELBO partials (log pi variable part per k; sum log sigma), or nullptr
     int stage_pr;          // 1: per-latent (matrix) priors are staged through shared memory
+    int stage_ring;        // 1: TruncatedADAGrad update -> the evicted ring slot is staged too
+    int stage_acc;         // 1: accumulators (and priors / ring) go through the stage; 0: read from global
+    int nbuf;              // staging buffers: 2 = prefetch the next tile, 1 = no overlap (large T x E)
     SupArgs<real> sup;
 };
 

@@ -108,7 +108,10 @@ def test_full_size_properties(bb):
         eng = bb.Engine(da, model, n_samples=2, dtype=dtype, seed=3)
         eng.init_params(1)
         eng.set_optimizer("decayed")
+        e_before = eng.elbo_grad(step=1000)[0]            # fixed lattice step: same noise before / after
         tr = eng.step(5, elbo_trace=True)
+        e_after = eng.elbo_grad(step=1000)[0]
+        assert np.isfinite(tr).all() and e_after > e_before
         out[dtype] = (tr, *eng.get_posterior())
         if dtype == "f32":
             eng2 = bb.Engine(da, model, n_samples=2, dtype=dtype, seed=3)
@@ -126,6 +129,9 @@ def test_full_size_properties(bb):
         eng.close()
     tr32, m32, s32 = out["f32"]
     tr64, m64, s64 = out["f64"]
-    assert tr64[-1] > tr64[0]
     assert np.all(np.abs(tr32 - tr64) <= 1e-4 * np.abs(tr64))
-    assert np.max(np.abs(m32 - m64)) < 5e-3 and np.max(np.abs(s32 - s64) / s64) < 5e-3
+    # AdaGrad's first steps are sign-like (delta ~ eta * sign(g)): a latent whose gradient is within fp32
+    # rounding of zero can step the other way, so agreement is required of all but a sliver of latents
+    dm, ds = np.abs(m32 - m64), np.abs(s32 - s64) / s64
+    assert np.median(dm) < 1e-5 and np.mean(dm > 1e-3) < 1e-3
+    assert np.median(ds) < 1e-5 and np.mean(ds > 1e-3) < 1e-3
