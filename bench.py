@@ -141,28 +141,46 @@ def cpu_port_rate(da, budget_s: float, K: int, max_barcodes: int | None = None):
 
 
 def run_reference(args):
+    """Reference arm (tier rules): the reference algorithm's CPU path on the box's host cores.  Julia is
+    absent, so it is the oracle's compiled C/OpenMP port (kind "port") with all host threads.  W warm-up
+    and exactly K timed ADVI steps run on a bounded sample of the workload (all neutrals + the first nb
+    mutant barcodes) sized so the whole run stays within ~2 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sys.path.insert(0, ROOT)
-    model, da = make_workload(1, "strong")
-    T, B = np.asarray(da.bc_count).shape
-    units_step = B * T * K_MC
     from oracle import cport
     cport.build()
-    # size the per-step sample so steps + warmup finish within a few minutes
-    budget_total = 120.0
-    per = budget_total / max(1, args.steps + args.warmup)
-    rate, cores, sample = cpu_port_rate(da, min(per, 20.0), K_MC)
-    # the rate is per barcode*timepoint*sample, identical unit; ms/step is what one full-size step would take
-    ms_step = units_step / rate * 1e3
+    model, da = make_workload(1, "strong")
+    R = np.asarray(da.bc_count)
+    T, B = R.shape
+    N, M = da.n_neutral, da.n_bc
+    K = args.mc_samples
+    # probe the rate on a small sample, then size the per-step sample
+    probe_rate, _, cores = cpu_port_rate(da, 1.0, K, max_barcodes=50_000)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    nb = int(min(M, max(2_000, probe_rate * budget / (K * T) - N)))
+    sub = np.ascontiguousarray(R[:, :N + nb])
+    pp = cport.PortProblem(sub, N, nb)
+    rng = np.random.default_rng(0)
+    theta = np.concatenate([rng.standard_normal(pp.D), rng.standard_normal(pp.D)])
+    theta[2 * (T - 1) + 2 * nb:pp.D] += np.log(sub.T.reshape(-1) + 1.0)
+    acc = np.full(2 * pp.D, 1e-8)
+    pp.advi_steps(theta, acc, max(args.warmup, 1), K)
+    t0 = time.perf_counter()
+    pp.advi_steps(theta, acc, args.steps, K, first_step=args.warmup)
+    dt = time.perf_counter() - t0
+    units_step = K * T * (N + nb)
+    rate = args.steps * units_step / dt
+    sample = (f"{args.steps} ADVI steps on {N} neutral + {nb} of {M} mutant barcodes x {T} time points, K={K}, "
+              f"fp64, {dt:.1f} s, OpenMP {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: fitness_normal, 1e6 barcodes x 5 time points, 8 MC samples",
-                   "optimizer": "DecayedADAGrad", "note": "reference algorithm's CPU path (Julia absent: oracle C port, "
-                   "analytic gradient, OpenMP); Turing+ReverseDiff is single-threaded and slower"},
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[1]: fitness_normal, {B} barcodes x {T} time points, {K} MC samples",
+                   "optimizer": "DecayedADAGrad",
+                   "note": "reference algorithm's CPU path (Julia absent: oracle C port, analytic gradient, OpenMP); "
+                           "Turing+ReverseDiff is single-threaded and taped, i.e. slower than this"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -259,7 +277,10 @@ def main():
     step_achieved = alg_bytes / (ms / args.steps * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": "pass2_kernel (gradient + fused optimiser update)",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of pass2_kernel from the committed ncu --set full capture
+        # (profiles/r1_ncu_pass_kernels.csv; cfg2 fp32 K=8 DecayedADAGrad, 1 GPU) -- null for other configurations
+        "traffic": 186.5e6 if (world == 1 and args.dtype == "f32" and args.opt == "decayed") else None,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
         "kernel_us": t_p2 * 1e6, "pass1_us": t_p1 * 1e6, "step_us": ms / args.steps * 1e3,
         "kernel_share_of_step": t_p2 / (ms_tot / n_prof * 1e-3),
