@@ -151,6 +151,8 @@ template <typename real> class Engine : public EngineBase {
         int pv = 0, kchunk = 0;
         size_t p1smem = 0, p2smem = 0, p2smem_elbo = 0;
         int p1nbuf = 2, p2nbuf = 2, p2stage_acc = 1;
+        size_t fsmem = 0;          // fused step kernel: pass-2 staging + pass-1 accumulators
+        int facc_slots = 0;        // 0: the fused kernel is not available for this group
         size_t part_off = 0, epart_off = 0;     // block offsets into part_ / epart_
     };
     struct RunMode {
@@ -161,6 +163,8 @@ template <typename real> class Engine : public EngineBase {
         bool dump = false;         // per-sample gradients
         bool gout = false;         // (dELBO/dmu, dELBO/domega)
         uint32_t step = 0;
+        bool fuse = false;         // pass 2 also accumulates the next step's pass-1 partials
+        bool have_part = false;    // this step's partials were produced by the previous fused kernel
     };
 
     void build_groups();
@@ -187,6 +191,8 @@ template <typename real> class Engine : public EngineBase {
     bb_opt opt_{BB_OPT_TRUNCATED_ADAGRAD, 0.1, 1.0, 0.9, 100};
     bool opt_ready_ = false;
     int ring_slot_ = 0;
+    bool fused_ok_ = false;        // every launch group has a fused step kernel that fits
+    long long part_step_ = -1;     // step whose pass-1 partials already sit in part_ (fused layout), or -1
     std::vector<Group> groups_;
     int p1blocks_total_ = 0, p2blocks_total_ = 0, hyblocks_ = 0;
 
@@ -263,7 +269,6 @@ template <typename real> Engine<real>::Engine(const bb_desc &d) {
     elbo_sh_.alloc(L.K + 1);
     elbo_out_.alloc(L.K + 1);
     build_groups();
-    part_.alloc((size_t)p1blocks_total_ * L.K * (3 * L.tmax));
 
     // algorithmic bytes per step of this shard: theta + accumulators read and written
     // once, int32 counts read once; matrix priors read once.
@@ -379,18 +384,41 @@ template <typename real> void Engine<real>::size_pass2() {
             throw std::runtime_error("T x E too large for the column kernels' shared memory");
         g.p2smem = ctx_b + stage_b;                                               // ELBO = false kernels
         g.p2smem_elbo = g.p2smem + sel_b;
+        // fused step kernel (non-hierarchical, all K samples in one sweep of the mutant accumulators)
+        g.facc_slots = 0;
+        if (g.ks.pass2_fused && !getenv("BB_NO_FUSE")) {
+            const int pv_m = L.E == 1 ? 2 * g.nt : g.pv;
+            const int slots = std::max(L.K * pv_m, g.pv);
+            const size_t fs = g.p2smem + (size_t)slots * BLOCK * sizeof(real);
+            if (fs <= kMaxSmem && (size_t)slots * BLOCK * sizeof(real) <= 64 * 1024) {
+                BB_CUDA(cudaFuncSetAttribute((const void *)g.ks.pass2_fused,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+                int occf = 0;
+                BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occf, g.ks.pass2_fused, BLOCK, fs));
+                // measured (B200, cfg2): the fused kernel wins at >= 3 resident CTAs per SM; with 2 (large K plus
+                // the TruncatedADAGrad ring stage) the two-kernel step is faster
+                if (occf >= 3) { g.facc_slots = slots; g.fsmem = fs; }
+            }
+        }
         BB_CUDA(cudaFuncSetAttribute((const void *)g.ks.pass2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)g.p2smem));
         for (auto *fn : {(const void *)g.ks.pass2_elbo, (const void *)g.ks_sup.pass2_elbo})
             BB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p2smem_elbo));
         int occ2 = 1;
-        BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, g.ks.pass2, BLOCK, g.p2smem));
+        if (g.facc_slots)
+            BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, g.ks.pass2_fused, BLOCK, g.fsmem));
+        else
+            BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, g.ks.pass2, BLOCK, g.p2smem));
         assign_blocks(g.p2segs, g.nt, nsm_ * std::max(occ2, 1), &g.p2blocks);
         g.epart_off = epart_off;
         epart_off += g.p2blocks;
     }
     p2blocks_total_ = (int)epart_off;
     epart_.alloc((size_t)p2blocks_total_ * (L.K + 1));
+    part_.alloc((size_t)std::max(p1blocks_total_, p2blocks_total_) * L.K * (3 * L.tmax));
+    fused_ok_ = !L.hier;
+    for (Group &g : groups_) fused_ok_ = fused_ok_ && g.facc_slots > 0;
+    part_step_ = -1;
 }
 
 template <typename real> ColArrays<real> Engine<real>::col_arrays() const {
@@ -410,6 +438,7 @@ template <typename real> ColArrays<real> Engine<real>::col_arrays() const {
 
 // ------------------------------------------------------------------ parameters
 template <typename real> void Engine<real>::init_params(uint64_t seed) {
+    part_step_ = -1;
     const PhiloxKey ikey = make_philox_key(seed);
     auto run = [&](r2 *dst, const int *map, size_t n) {
         if (!n) return;
@@ -437,6 +466,7 @@ template <typename real> void Engine<real>::init_params(uint64_t seed) {
 }
 
 template <typename real> void Engine<real>::set_params(const double *mu, const double *omega) {
+    part_step_ = -1;
     hostvec_a_.ensure(L.D); hostvec_b_.ensure(L.D);
     BB_CUDA(cudaMemcpyAsync(hostvec_a_.p, mu, sizeof(double) * L.D, cudaMemcpyHostToDevice, stream_));
     BB_CUDA(cudaMemcpyAsync(hostvec_b_.p, omega, sizeof(double) * L.D, cudaMemcpyHostToDevice, stream_));
@@ -561,6 +591,7 @@ template <typename real> void Engine<real>::upload_supplied(const double *x, int
 
 // ------------------------------------------------------------------ the step pipeline
 template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
+    if (!m.fuse) part_step_ = -1;     // anything but a fused step invalidates the pipelined partial sums
     const PhiloxKey pkey = make_philox_key(seed_);
     const ColArrays<real> C = col_arrays();
     SupArgs<real> sup{};
@@ -589,20 +620,24 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
     // ---- pass 1
     if (tev_pos_ >= 0) BB_CUDA(cudaEventRecord(tev_[tev_pos_++], stream_));
     for (Group &g : groups_) {
-        P1Args<real> a{};
-        a.segs = g.p1segs; a.cols = C; a.K = L.K; a.acc_slots = g.kchunk; a.ne = L.E;
-        for (int t = 0; t < MAX_NT_DYN; ++t) a.env_of_t[t] = L.env_of_t[t];
-        a.key = pkey; a.step = m.step;
-        a.hy_zeps = zeps_.p; a.H = L.H;
-        a.part = part_.p + (size_t)g.part_off * L.K * (3 * L.tmax);
-        a.pv = g.pv; a.sup = sup; a.nbuf = g.p1nbuf;
-        (m.sup ? g.ks_sup.pass1 : g.ks.pass1)<<<g.p1blocks, BLOCK, g.p1smem, stream_>>>(a);
-        ++launches;
+        // partial sums of this step: from the previous fused kernel (its grid / segment split), or pass 1 now
+        double *gpart = part_.p + (size_t)(m.have_part ? g.epart_off : g.part_off) * L.K * (3 * L.tmax);
+        if (!m.have_part) {
+            P1Args<real> a{};
+            a.segs = g.p1segs; a.cols = C; a.K = L.K; a.acc_slots = g.kchunk; a.ne = L.E;
+            for (int t = 0; t < MAX_NT_DYN; ++t) a.env_of_t[t] = L.env_of_t[t];
+            a.key = pkey; a.step = m.step;
+            a.hy_zeps = zeps_.p; a.H = L.H;
+            a.part = gpart;
+            a.pv = g.pv; a.sup = sup; a.nbuf = g.p1nbuf;
+            (m.sup ? g.ks_sup.pass1 : g.ks.pass1)<<<g.p1blocks, BLOCK, g.p1smem, stream_>>>(a);
+            ++launches;
+        }
         if (tev_pos_ >= 0 && &g == &groups_.back()) BB_CUDA(cudaEventRecord(tev_[tev_pos_++], stream_));
         ReduceArgs ra{};
-        ra.segs = g.p1segs; ra.K = L.K; ra.tmax = L.tmax; ra.pv = g.pv; ra.nt = g.nt;
-        ra.w_single = L.E == 1 ? 1 : 0; ra.rep_mask = g.rep_mask; ra.nblk = g.p1blocks;
-        ra.part = a.part; ra.sums = sums_.p;
+        ra.segs = m.have_part ? g.p2segs : g.p1segs; ra.K = L.K; ra.tmax = L.tmax; ra.pv = g.pv; ra.nt = g.nt;
+        ra.w_single = L.E == 1 ? 1 : 0; ra.rep_mask = g.rep_mask; ra.nblk = m.have_part ? g.p2blocks : g.p1blocks;
+        ra.part = gpart; ra.sums = sums_.p;
         const int nwarps = L.R * L.K * NQ * L.tmax;
         reduce_kernel<<<cdiv((long long)nwarps * 32, 128), 128, 0, stream_>>>(ra, L.R);
         ++launches;
@@ -650,7 +685,12 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         // smem is sized for the ring by size_pass2(); stage it only when the ring exists and is updated
         a.stage_ring = (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p && m.update) ? 1 : 0;
         a.stage_acc = g.p2stage_acc; a.nbuf = g.p2nbuf;
-        {
+        if (m.fuse) {
+            // the reducer has consumed this step's partials (stream order): the fused kernel overwrites them
+            a.part = part_.p + (size_t)g.epart_off * L.K * (3 * L.tmax);
+            a.pv = g.pv; a.acc_slots = g.facc_slots;
+            g.ks.pass2_fused<<<g.p2blocks, BLOCK, g.fsmem, stream_>>>(a);
+        } else {
             const KernelSet<real> &ks = m.sup ? g.ks_sup : g.ks;
             if (elbo) ks.pass2_elbo<<<g.p2blocks, BLOCK, g.p2smem_elbo, stream_>>>(a);
             else ks.pass2<<<g.p2blocks, BLOCK, g.p2smem, stream_>>>(a);
@@ -774,7 +814,11 @@ template <typename real> void Engine<real>::step(int n, double *trace) {
     if (trace) trace_.ensure((size_t)n * (L.K + 1));
     for (int i = 0; i < n; ++i) {
         RunMode m; m.update = true; m.want_elbo = trace != nullptr; m.step = (uint32_t)step_count;
+        // software-pipelined step: pass 2 of this step also produces the partial sums of the next one
+        m.fuse = fused_ok_ && trace == nullptr;
+        m.have_part = fused_ok_ && part_step_ == step_count;
         run_pipeline(m);
+        part_step_ = m.fuse ? step_count + 1 : -1;
         if (trace)
             BB_CUDA(cudaMemcpyAsync(trace_.p + (size_t)i * (L.K + 1), elbo_out_.p, sizeof(double) * (L.K + 1),
                                     cudaMemcpyDeviceToDevice, stream_));

@@ -270,6 +270,55 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
     }
 }
 
+// Pass-1 accumulation of all K samples of one non-hierarchical column into the thread-private slots
+// `acc0[(k * pvs + slot) * BLOCK]` (same slot layout as pass1_kernel).  Used by the fused step kernel.
+template <typename real, int NT, int NE>
+__device__ __forceinline__ void pass1_column_direct(const real *mu, const real *sg, const real *mub, const real *sgb,
+                                                    bool neutral, int nt, int ne, int k0, int k1, uint32_t colid,
+                                                    uint32_t step, const PhiloxKey &key, const int *env_of_t,
+                                                    real *acc0, int pvs) {
+    using S = Shape<NT, NE, false>;
+    const int nclass = neutral ? nt : nt + 2 * ne;
+    const SupArgs<real> nosup{};
+    for (int k = k0; k < k1; ++k) {
+        real eps[S::MAXC];
+        column_noise<real, S::MAXC, false>(eps, nclass, nt, colid, (uint32_t)k, step, key, nosup, 0, 0, 0, 0);
+        real *acc = acc0 + (size_t)(k - k0) * pvs * BLOCK;
+        real z[S::MAXT];
+#pragma unroll
+        for (int t = 0; t < S::MAXT; ++t) {
+            if (t >= nt) break;
+            z[t] = fma(sg[t], eps[t], mu[t]);
+            acc[t * BLOCK] += bb_exp(z[t]);
+        }
+        if (neutral) {
+#pragma unroll
+            for (int t = 0; t < S::MAXT - 1; ++t) {
+                if (t >= nt - 1) break;
+                const real d = z[t + 1] - z[t];
+                acc[(nt + t) * BLOCK] += d;
+                acc[(2 * nt - 1 + t) * BLOCK] += d * d;
+            }
+        } else {
+            real zs[S::MAXE], w[S::MAXE];
+#pragma unroll
+            for (int e = 0; e < S::MAXE; ++e) {
+                if (e >= ne) break;
+                zs[e] = fma(sgb[2 * e], eps[nt + 2 * e], mub[2 * e]);
+                w[e] = bb_exp(real(-2) * fma(sgb[2 * e + 1], eps[nt + 2 * e + 1], mub[2 * e + 1]));
+            }
+#pragma unroll
+            for (int t = 0; t < S::MAXT - 1; ++t) {
+                if (t >= nt - 1) break;
+                const int e = NE == 1 ? 0 : env_of_t[t + 1];
+                acc[(nt + t) * BLOCK] += w[e] * (z[t + 1] - z[t] - zs[e]);
+                if (NE != 1) acc[(2 * nt - 1 + t) * BLOCK] += w[e];
+            }
+            if (NE == 1) acc[(2 * nt - 1) * BLOCK] += w[0];
+        }
+    }
+}
+
 // ===================================================================== optimiser
 // AdvancedVI 0.2 optimisers.jl (restated in oracle/advi_ref.py):
 //   DecayedADAGrad   acc = post*acc + pre*g^2 ; delta = eta*g / (sqrt(acc) + 1e-8)
@@ -295,9 +344,9 @@ __device__ __forceinline__ void opt_apply(const OptArgsT<real> &o, real g, real 
 // The mode is block-uniform, so each instantiation is a straight line of ~40 instructions.
 template <typename real, int MODE>
 __device__ __forceinline__ void finish_latent_mode(const OptArgsT<real> &o, real invK, real sgrad, real sgrade,
-                                                   vec2<real> th, vec2<real> ac, vec2<real> rg, vec2<real> *th_ptr,
+                                                   vec2<real> &th, vec2<real> ac, vec2<real> rg, vec2<real> *th_ptr,
                                                    vec2<real> *acc_ptr, vec2<real> *ring_ptr, vec2<real> *gout_ptr) {
-    // rg: the ring slot evicted this step (MODE 1 only)
+    // rg: the ring slot evicted this step (MODE 1 only); th is updated in place (MODE 0 / 1)
     if constexpr (MODE == 3) return;
     // d ELBO / d mu = mean_k g ; d ELBO / d omega = (mean_k g eps + 1/sigma) sigmoid(omega)
     real sigma, sgm;
@@ -346,8 +395,12 @@ __device__ __forceinline__ void finish_latent(const OptArgsT<real> &o, real invK
 // smem: ctx [K][3][tmax] of this block's replicate | ELBO private columns [K+1][BLOCK] (double) |
 //       2 staging buffers { theta [nt+nj][BLOCK], acc [nt+nj][BLOCK], counts [nt][BLOCK],
 //                           priors [nt+nj][BLOCK] (matrix priors only) }
-template <typename real, int NT, int NE, bool HIER, bool SUP, bool ELBO>
-__global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2Args<real> a) {
+// FUSE: after updating a column, accumulate the pass-1 sums of the NEXT step (noise of step + 1, the
+// freshly updated theta) -- the software-pipelined step: theta and its accumulators are read and
+// written exactly once per ADVI step (non-hierarchical models; the hyper latents of the hierarchical
+// ones are only known after every member column has been processed).
+template <typename real, int NT, int NE, bool HIER, bool SUP, bool ELBO, bool FUSE = false>
+__global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kernel(const P2Args<real> a) {
     using S = Shape<NT, NE, HIER>;
     using r2 = vec2<real>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -383,6 +436,14 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
     const size_t buf_bytes = (1 + nac + npr + nrg) * th_bytes + cn_bytes;   // theta, [acc], [priors], [ring], counts
     const int nbuf = a.nbuf;
     unsigned char *stage0 = smem_raw + ctx_bytes + sel_bytes;
+    // fused step: thread-private pass-1 accumulators behind the staging buffers, a.acc_slots rows of
+    // BLOCK reals sized for the mutant population ([K][pvs]); mutant blocks accumulate inline right
+    // after updating a column, the few neutral blocks (3 nt - 2 slots per sample) sweep their own
+    // columns again in sample chunks once their updates are written
+    const int pvs = seg.neutral ? 3 * nt - 2 : (NE == 1 ? 2 * nt : 3 * nt - 2);
+    real *facc = reinterpret_cast<real *>(stage0 + (size_t)nbuf * buf_bytes);
+    if constexpr (FUSE)
+        for (int i = tid; i < a.acc_slots * BLOCK; i += BLOCK) facc[i] = real(0);
 
     auto prefetch = [&](int tile, int buf) {
         const int i = tile * BLOCK + tid;
@@ -603,8 +664,10 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
                 const size_t o = (size_t)t * cpad + c;
                 const r2 ac = MODE >= 2 ? mk2<real>(0, 0) : (nac ? sac[t * BLOCK] : C.lam_acc[o]);
                 const r2 rg = MODE != 1 ? mk2<real>(0, 0) : (nrg ? srg[t * BLOCK] : C.lam_ring[o]);
-                finish_latent_mode<real, MODE>(a.opt, invK, sgr[t], sge[t], sth[t * BLOCK], ac, rg, C.lam_th + o,
+                r2 th = sth[t * BLOCK];
+                finish_latent_mode<real, MODE>(a.opt, invK, sgr[t], sge[t], th, ac, rg, C.lam_th + o,
                                                C.lam_acc + o, C.lam_ring + o, a.gout_lam + o);
+                if constexpr (FUSE) { mu[t] = th.x; sg[t] = softplus_only<real>(th.y); }
             }
             if (!seg.neutral) {
 #pragma unroll
@@ -613,8 +676,10 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
                     const size_t o = (size_t)j * cpad + c;
                     const r2 ac = MODE >= 2 ? mk2<real>(0, 0) : (nac ? sac[(nt + j) * BLOCK] : C.bc_acc[o]);
                     const r2 rg = MODE != 1 ? mk2<real>(0, 0) : (nrg ? srg[(nt + j) * BLOCK] : C.bc_ring[o]);
-                    finish_latent_mode<real, MODE>(a.opt, invK, sgrb[j], sgeb[j], sth[(nt + j) * BLOCK], ac, rg,
+                    r2 th = sth[(nt + j) * BLOCK];
+                    finish_latent_mode<real, MODE>(a.opt, invK, sgrb[j], sgeb[j], th, ac, rg,
                                                    C.bc_th + o, C.bc_acc + o, C.bc_ring + o, a.gout_bc + o);
+                    if constexpr (FUSE) { mub[j] = th.x; sgb[j] = softplus_only<real>(th.y); }
                 }
             }
         };
@@ -633,8 +698,55 @@ __global__ void __launch_bounds__(BLOCK, BB_P2_MIN_BLOCKS) pass2_kernel(const P2
                 }
             }
         }
+        if constexpr (FUSE && !HIER)
+            if (!seg.neutral)
+                pass1_column_direct<real, NT, NE>(mu, sg, mub, sgb, false, nt, ne, 0, a.K, colid, a.step + 1, a.key,
+                                                  a.env_of_t, facc + tid, pvs);
     }
     cp_async_wait<0>();
+    if constexpr (FUSE && !HIER) {
+        const int warp = tid >> 5, lane = tid & 31;
+        auto flush = [&](int k0, int k1) {          // block reduction of the private columns -> part
+            __syncthreads();
+            for (int row = warp; row < (k1 - k0) * pvs; row += BLOCK / 32) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j < BLOCK / 32; ++j) s += (double)facc[(size_t)row * BLOCK + j * 32 + lane];
+                s = warp_sum<double>(s);
+                if (lane == 0)
+                    a.part[((size_t)(k0 + row / pvs) * a.pv + row % pvs) * gridDim.x + blockIdx.x] = s;
+            }
+            __syncthreads();
+        };
+        if (!seg.neutral) {
+            flush(0, a.K);
+        } else {
+            const int kchunk = max(1, min(a.K, a.acc_slots / pvs));
+            for (int kc0 = 0; kc0 < a.K; kc0 += kchunk) {
+                const int kc1 = min(a.K, kc0 + kchunk);
+                if (kc0 > 0) {
+                    for (int i = tid; i < (kc1 - kc0) * pvs * BLOCK; i += BLOCK) facc[i] = real(0);
+                    __syncthreads();
+                }
+                for (int tile = blockIdx.x - seg.blk0; tile < ntile; tile += nblk) {
+                    const int i = tile * BLOCK + tid;
+                    if (i >= seg.ncol) continue;
+                    const int c = seg.col0 + i;
+                    const uint32_t colid = C.col_id ? C.col_id[c] : seg.colid0 + (uint32_t)i;
+                    real mu[S::MAXT], sg[S::MAXT];
+#pragma unroll
+                    for (int t = 0; t < S::MAXT; ++t) {
+                        if (t >= nt) break;
+                        const r2 th = C.lam_th[(size_t)t * cpad + c];      // this thread's own update, already written
+                        mu[t] = th.x; sg[t] = softplus_only<real>(th.y);
+                    }
+                    pass1_column_direct<real, NT, NE>(mu, sg, mu, sg, true, nt, ne, kc0, kc1, colid, a.step + 1,
+                                                      a.key, a.env_of_t, facc + tid, pvs);
+                }
+                flush(kc0, kc1);
+            }
+        }
+    }
     if (want_elbo) {
         __syncthreads();
         const int warp = tid >> 5, lane = tid & 31;
@@ -653,6 +765,7 @@ template <typename real> struct KernelSet {
     void (*pass1)(const P1Args<real>);
     void (*pass2)(const P2Args<real>);        // no ELBO partial sums (the production step)
     void (*pass2_elbo)(const P2Args<real>);   // also accumulates the log-density / entropy partials
+    void (*pass2_fused)(const P2Args<real>);  // pass 2 + pass 1 of the next step (non-hierarchical), or nullptr
 };
 
 template <typename real, int NT, int NE, bool HIER, bool SUP> KernelSet<real> make_kernel_set() {
@@ -662,6 +775,8 @@ template <typename real, int NT, int NE, bool HIER, bool SUP> KernelSet<real> ma
     // the caller-supplied-noise kernels are the parity path: always with the ELBO terms
     if constexpr (SUP) ks.pass2 = ks.pass2_elbo;
     else ks.pass2 = pass2_kernel<real, NT, NE, HIER, SUP, false>;
+    ks.pass2_fused = nullptr;
+    if constexpr (!SUP && !HIER) ks.pass2_fused = pass2_kernel<real, NT, NE, HIER, SUP, false, true>;
     return ks;
 }
 

@@ -150,3 +150,41 @@ def test_philox_steps_match_oracle_trajectory(bb):
     assert rel_err(trace, np.asarray(tr.elbo)) < 1e-9
     assert rel_err(mu_g, tr.mu) < 1e-8 and rel_err(om_g, tr.omega) < 1e-8
     eng.close()
+
+
+@pytest.mark.parametrize("opt", ["decayed", "truncated"])
+@pytest.mark.parametrize("model", ["fitness_normal", "multienv_fitness_normal"])
+def test_fused_pipelined_steps_match_oracle_and_unfused(bb, model, opt, monkeypatch):
+    """bb_step without an ELBO trace runs the software-pipelined kernel (pass 2 of step i + pass 1 of
+    step i+1).  It must follow the oracle's trajectory on the same noise lattice, agree with the
+    two-kernel path up to reduction order, and survive being split across several bb_step calls."""
+    from oracle import advi_ref
+    K, n_steps = 2, 5
+    kw = dict(eta=0.1, pre=1.0, post=0.9) if opt == "decayed" else dict(eta=0.1, tau=1.0, n=3)
+    ref_opt = advi_ref.DecayedADAGrad(0.1, 1.0, 0.9) if opt == "decayed" else advi_ref.TruncatedADAGrad(0.1, 1.0, 3)
+    results = {}
+    for mode in ("fused", "fused_split", "unfused"):
+        if mode == "unfused":
+            monkeypatch.setenv("BB_NO_FUSE", "1")
+        else:
+            monkeypatch.delenv("BB_NO_FUSE", raising=False)
+        da, eng = _setup(bb, model, K, "f64")
+        eng.init_params(5)
+        mu0, om0 = eng.get_params()
+        eng.set_optimizer(opt, **kw)
+        if mode == "fused_split":
+            eng.step(2)
+            eng.step(1)
+            _ = eng.get_posterior()            # a read between calls must not disturb the pipeline
+            eng.step(2)
+        else:
+            eng.step(n_steps)
+        results[mode] = eng.get_params()
+        assert eng.step_count == n_steps
+        eng.close()
+    prob = oracle_problem(da, model)
+    tr = advi_ref.advi_run(model, prob, n_steps, K, ref_opt, mu0, om0, seed=1234)
+    for mode, (mu_g, om_g) in results.items():
+        assert rel_err(mu_g, tr.mu) < 1e-8 and rel_err(om_g, tr.omega) < 1e-8, mode
+    assert np.array_equal(results["fused"][0], results["fused_split"][0])
+    assert rel_err(results["fused"][0], results["unfused"][0]) < 1e-10
