@@ -76,7 +76,6 @@ SYMBOLS = [
     ("bb_set_stream", C.c_int, [_P, _P]),
     ("bb_sync", C.c_int, [_P]),
     ("bb_launch_count", C.c_int64, [_P]),
-    ("bb_use_graph", C.c_int, [_P, C.c_int32]),
     ("bb_algorithmic_bytes_per_step", C.c_double, [_P]),
     ("bb_time_steps", C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("bb_comm_unique_id", C.c_int, [C.c_char * 128]),

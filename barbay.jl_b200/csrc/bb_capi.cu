@@ -125,9 +125,6 @@ int bb_sync(bb_handle *h) {
     return guarded(h, [&](bb::EngineBase &e) { e.sync(); });
 }
 int64_t bb_launch_count(const bb_handle *h) { return h && h->eng ? h->eng->launches : -1; }
-int bb_use_graph(bb_handle *h, int32_t enable) {
-    return guarded(h, [&](bb::EngineBase &e) { e.use_graph(enable); });
-}
 double bb_algorithmic_bytes_per_step(const bb_handle *h) { return h && h->eng ? h->eng->alg_bytes : -1.0; }
 int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_pass1, float *ms_pass2) {
     return guarded(h, [&](bb::EngineBase &e) {

@@ -107,7 +107,6 @@ class EngineBase {
     virtual void sync() = 0;
     virtual void time_steps(int n, float *ms_total, float *ms_pass1, float *ms_pass2) = 0;
     virtual void comm_init(const char id[128]) = 0;
-    virtual void use_graph(int enable) = 0;
     long long launches = 0;
     long long step_count = 0;
     double alg_bytes = 0.0;
@@ -139,7 +138,6 @@ template <typename real> class Engine : public EngineBase {
     void sync() override { BB_CUDA(cudaStreamSynchronize(stream_)); }
     void time_steps(int n, float *ms_total, float *ms_pass1, float *ms_pass2) override;
     void comm_init(const char id[128]) override;
-    void use_graph(int) override {}
 
   private:
     struct Group {                 // replicates sharing one T: one launch of each column kernel

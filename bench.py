@@ -288,28 +288,38 @@ def main():
     }
 
     # ---- end to end through the public API with HOST buffers: one complete advi()-equivalent call
-    # (pack -> bb_create: H2D of counts/maps -> init -> optimiser -> n steps with the ELBO trace read
-    # back -> bb_get_posterior: D2H), timed on the host clock around the whole call.
-    e2e = None
+    # (pack -> bb_create: H2D of counts/maps -> init -> optimiser -> n steps -> ELBO read-back ->
+    # bb_get_posterior: D2H), timed on the host clock around the whole call.
+    # (all ranks take part; host wall clock, max over ranks)
+    n_e2e = args.e2e_steps
+    barrier()
+    t0 = time.perf_counter()
+    eng2 = bb.Engine(da, model, n_samples=K, dtype=args.dtype, seed=20261018, device=local_rank, rank=rank, world=world)
+    if world > 1:
+        uid2 = [bb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid2, src=0)
+        eng2.comm_init(uid2[0])
+    eng2.init_params(1)
+    eng2.set_optimizer(args.opt)
+    eng2.step(n_e2e)
+    elbo_last = eng2.step(1, elbo_trace=True)            # the step's result read back (8 bytes)
+    m, s = eng2.get_posterior()
+    dt_e2e = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([dt_e2e], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt_e2e = float(tt.item())
+    n_tot = n_e2e + 1
+    h2d = (B * T * 4 + (B * T + 2 * (B - da.n_neutral)) * 4) / world / n_tot     # int32 counts + layout maps per rank
+    d2h = (2 * eng2.D * 8) / n_tot + 8.0 / n_tot                                  # posterior (m, sigma) + ELBO
+    e2e = {"value": units_step * n_tot / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": n_tot, "seconds": dt_e2e,
+           "what": "one complete advi()-equivalent call through the C ABI from HOST arrays on every rank: bb_create "
+                   "(pack + H2D of counts / maps) + [comm init] + bb_init_params + bb_set_optimizer + bb_step + "
+                   "ELBO read-back + bb_get_posterior (D2H); bytes are amortised over the steps of the call",
+           "elbo_last": float(elbo_last[-1]), "posterior_finite": bool(np.isfinite(m).all())}
+    eng2.close()
     if rank == 0 and world == 1:
-        n_e2e = args.e2e_steps
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        eng2 = bb.Engine(da, model, n_samples=K, dtype=args.dtype, seed=20261018, device=local_rank)
-        eng2.init_params(1)
-        eng2.set_optimizer(args.opt)
-        trace = eng2.step(n_e2e, elbo_trace=True)
-        m, s = eng2.get_posterior()
-        t1 = time.perf_counter()
-        w = 4 if args.dtype == "f32" else 8
-        h2d = (B * T * 4 + (B * T + 2 * (B - da.n_neutral)) * 4) / n_e2e          # counts + layout maps
-        d2h = (2 * eng2.D * 8) / n_e2e + 8.0                                      # posterior + ELBO per step
-        e2e = {"value": units_step * n_e2e / (t1 - t0), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": n_e2e, "seconds": t1 - t0,
-               "what": "one complete advi()-equivalent call through the C ABI from host arrays: bb_create (H2D) + "
-                       "init + optimiser + steps with ELBO trace + bb_get_posterior (D2H)",
-               "elbo_first_last": [float(trace[0]), float(trace[-1])], "posterior_finite": bool(np.isfinite(m).all())}
-        eng2.close()
         # streaming variant per the base contract: every step re-uploads that step's counts from pinned
         # host memory and reads the step's ELBO back
         cnt_host = torch.from_numpy(np.ascontiguousarray(np.asarray(da.bc_count).astype(np.int32))).pin_memory()
@@ -324,8 +334,8 @@ def main():
         t1 = time.perf_counter()
         e2e["streaming"] = {"value": units_step * n_s / (t1 - t0), "unit": UNIT,
                             "h2d_bytes_per_step": int(cnt_host.numel() * 4), "d2h_bytes_per_step": 8 * (K + 1),
-                            "steps": n_s, "what": "per step: pinned-host -> device copy of the count matrix + bb_step + "
-                            "ELBO read-back"}
+                            "steps": n_s, "what": "per step: pinned-host -> device copy of the count matrix + bb_step "
+                            "(with ELBO terms) + ELBO read-back"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

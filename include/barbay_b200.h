@@ -130,7 +130,6 @@ int bb_set_state(bb_handle *h, const double *state);
 int bb_set_stream(bb_handle *h, void *cuda_stream);     /* run on the caller's cudaStream_t (NULL -> library stream) */
 int bb_sync(bb_handle *h);
 int64_t bb_launch_count(const bb_handle *h);            /* kernels launched by this handle so far */
-int bb_use_graph(bb_handle *h, int32_t enable);         /* capture the step sequence in a CUDA graph */
 double bb_algorithmic_bytes_per_step(const bb_handle *h);   /* SURVEY §8d figure for this shard */
 /* n_steps of bb_step timed with CUDA events on the launching stream: whole region, and the summed
  * durations of the pass-1 and pass-2 column kernels (the roofline numerators of bench.py). */

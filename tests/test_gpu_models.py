@@ -119,7 +119,15 @@ def test_full_size_properties(bb):
             eng2.set_optimizer("decayed")
             eng2.step(5)
             m2, s2 = eng2.get_posterior()
-            assert np.array_equal(m2, out[dtype][1]) and np.array_equal(s2, out[dtype][2])   # bitwise
+            eng3 = bb.Engine(da, model, n_samples=2, dtype=dtype, seed=3)
+            eng3.init_params(1)
+            eng3.set_optimizer("decayed")
+            eng3.step(5)
+            m3b, s3b = eng3.get_posterior()
+            eng3.close()
+            assert np.array_equal(m2, m3b) and np.array_equal(s2, s3b)        # same calls => bitwise same theta
+            # the traced (two-kernel, ELBO) path sums the partials in another order: equal up to fp32 rounding
+            assert np.mean(np.abs(m2 - out[dtype][1]) > 1e-3) < 1e-3
             state = eng2.get_state()
             eng2.step(2)
             eng2.set_state(state)
@@ -135,3 +143,56 @@ def test_full_size_properties(bb):
     dm, ds = np.abs(m32 - m64), np.abs(s32 - s64) / s64
     assert np.median(dm) < 1e-5 and np.mean(dm > 1e-3) < 1e-3
     assert np.median(ds) < 1e-5 and np.mean(ds > 1e-3) < 1e-3
+
+
+@pytest.mark.parametrize("n_neutral,n_bc,n_time", [(0, 6, 4), (5, 0, 4), (1, 1, 2), (3, 2, 2), (33, 95, 5)])
+def test_edge_shapes(bb, n_neutral, n_bc, n_time):
+    """Empty populations, the minimal two time points, sizes around the 32-column padding."""
+    da, _ = bb.synth.simulate("fitness_normal", max(n_neutral, 1), max(n_bc, 1), n_time, seed=1)
+    R = np.asarray(da.bc_count)
+    # carve the requested (possibly empty) populations out of the simulated block
+    cols = list(range(n_neutral)) + list(range(da.n_neutral, da.n_neutral + n_bc))
+    da.bc_count = np.ascontiguousarray(R[:, cols])
+    da.bc_total = da.bc_count.sum(axis=1)
+    da.n_neutral, da.n_bc = n_neutral, n_bc
+    da.neutral_ids, da.bc_ids = da.neutral_ids[:n_neutral], da.bc_ids[:n_bc]
+    _check_logjoint(bb, da, "fitness_normal", {}, None)
+    eng = bb.Engine(da, "fitness_normal", n_samples=3, dtype="f32", seed=2)
+    eng.init_params(1)
+    eng.step(3)
+    m, s = eng.get_posterior()
+    assert np.isfinite(m).all() and (s > 0).all()
+    eng.close()
+
+
+def test_zero_counts_and_large_counts(bb):
+    da, _ = bb.synth.simulate("fitness_normal", 4, 12, 5, seed=6, mean_reads=0.7)       # many zero counts
+    assert (np.asarray(da.bc_count) == 0).any()
+    _check_logjoint(bb, da, "fitness_normal", {}, None)
+    da2, _ = bb.synth.simulate("fitness_normal", 4, 12, 5, seed=6, mean_reads=2e7)      # counts ~ 10^8
+    assert 5e7 < np.asarray(da2.bc_count).max() < 2 ** 31
+    _check_logjoint(bb, da2, "fitness_normal", {}, None)
+
+
+def test_c_abi_rejects_bad_arguments(bb):
+    """Errors come back as BarBayError with the library's message (the Julia glue would raise error(msg))."""
+    da, _ = bb.synth.simulate("fitness_normal", 4, 12, 5, seed=1)
+    with pytest.raises(bb.BarBayError, match="samples_per_step"):
+        bb.Engine(da, "fitness_normal", n_samples=0)
+    with pytest.raises(bb.BarBayError, match="rows"):
+        bb.Engine(da, "fitness_normal", {"s_bc_prior": np.ones((5, 2))})
+    with pytest.raises(bb.BarBayError, match="> 0"):
+        bb.Engine(da, "fitness_normal", {"s_pop_prior": [0.0, -1.0]})
+    with pytest.raises(bb.BarBayError, match="single replicate"):
+        bb.Engine(bb.synth.simulate("replicate_fitness_normal", 4, 8, 5, n_rep=2, seed=1)[0], "fitness_normal")
+    big = bb.synth.simulate("fitness_normal", 2, 4, 5, seed=1)[0]
+    big.bc_count = big.bc_count.copy()
+    big.bc_count[0, 0] = 2 ** 31
+    with pytest.raises(bb.BarBayError, match="2\\^31"):
+        bb.Engine(big, "fitness_normal")
+    eng = bb.Engine(da, "fitness_normal", n_samples=2)
+    with pytest.raises(bb.BarBayError, match="length D"):
+        eng.set_params(np.zeros(3), np.zeros(3))
+    with pytest.raises(bb.BarBayError, match="TruncatedADAGrad or DecayedADAGrad"):
+        eng.set_optimizer("adam")
+    eng.close()

@@ -117,7 +117,7 @@ def test_c_abi_exports_every_declared_symbol(bb):
     hdr = open(os.path.join(ROOT, "include", "barbay_b200.h"), encoding="utf8").read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     declared = set(re.findall(r"\b(bb_[a-z_0-9]+)\s*\(", hdr))
-    assert len(declared) >= 27
+    assert len(declared) >= 26
     lib = bb.load_library()
     bound = {name for name, _, _ in bb._lib.SYMBOLS}
     assert declared == bound, declared ^ bound
@@ -133,9 +133,8 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".jl")):
                 src = open(os.path.join(dirpath, f), encoding="utf8").read()
-                assert "oracle" not in src.replace("oracle restates", "").replace("the oracle", "").replace(
-                    "oracle/", "ORACLEDOC/") or "import oracle" not in src and "from oracle" not in src
-                assert "from oracle" not in src and "import oracle" not in src
+                assert "from oracle" not in src and "import oracle" not in src, f
+                assert "advi_port" not in src and "oracle/c" not in src, f      # nor link / execute it
 
 
 def test_synthetic_configs_shapes(bb):
