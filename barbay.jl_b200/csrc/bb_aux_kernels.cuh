@@ -45,12 +45,76 @@ static __global__ void __launch_bounds__(128) reduce_kernel(const ReduceArgs a, 
     if (lane == 0) a.sums[((size_t)(r * a.K + k) * NQ + q) * a.tmax + t] = s;
 }
 
+// ------------------------------------------------------------------ peer-memory exchange of the step's sums
+// One-shot all-reduce over NVLink peer memory (one process per GPU, buffers shared through CUDA IPC):
+// after its local reduction every rank stores its `P` partial sums into slot [parity][rank] of EVERY
+// peer's exchange buffer and then raises flag [parity][rank] = seq on that peer.  The shared-latent
+// kernel of each rank waits for the `world` flags of this exchange, adds the slots in rank order
+// (deterministic and identical on all ranks) and carries on -- the collective is fused into the kernel
+// that consumes it, nothing but two NVLink stores is on the critical path.  Two parities suffice: a
+// rank cannot start exchange seq + 2 before every peer has finished reading seq (it needs their
+// seq + 1 data first).
+constexpr int MAX_WORLD = 16;
+
+struct XchgPostArgs {
+    const double *sums;                       // this rank's partial sums [P]
+    int P, world, rank, parity;
+    unsigned long long seq;
+    double *peer_buf[MAX_WORLD];              // peer r's exchange buffer [2][world][P] (own buffer for r == rank)
+    unsigned long long *peer_flag[MAX_WORLD]; // peer r's flags [2][world]
+};
+
+static __global__ void __launch_bounds__(256) xchg_post_kernel(const XchgPostArgs a) {
+    const int tid = threadIdx.x;
+    for (int r = 0; r < a.world; ++r) {
+        double *dst = a.peer_buf[r] + (size_t)(a.parity * a.world + a.rank) * a.P;
+        for (int i = tid; i < a.P; i += blockDim.x) dst[i] = a.sums[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < a.world) {
+        volatile unsigned long long *f = a.peer_flag[tid] + (a.parity * a.world + a.rank);
+        *f = a.seq;
+    }
+}
+
+struct XchgWaitArgs {
+    const double *buf;                        // local exchange buffer [2][world][P], or nullptr (no exchange)
+    const unsigned long long *flag;           // local flags [2][world]
+    int P, world, parity;
+    unsigned long long seq;
+    int *err;                                 // set to 1 if a peer never showed up (bounded spin)
+};
+
+// executed by one CTA at the top of the consumer kernel; totals land in `sums`
+__device__ __forceinline__ void xchg_wait_and_sum(const XchgWaitArgs &x, double *sums) {
+    if (!x.buf) return;
+    const int tid = threadIdx.x;
+    if (tid < x.world) {
+        const volatile unsigned long long *f = x.flag + (x.parity * x.world + tid);
+        const long long t0 = clock64();
+        while (*f != x.seq) {
+            if (clock64() - t0 > 6000000000LL) { *x.err = 1; break; }      // ~3 s: never hang the GPU
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    for (int i = tid; i < x.P; i += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < x.world; ++r)
+            s += *reinterpret_cast<const volatile double *>(x.buf + (size_t)(x.parity * x.world + r) * x.P + i);
+        sums[i] = s;
+    }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------ shared latents
 template <typename real> struct SharedArgs {
     int R, K, tmax, nst;          // nst = sum_r (T_r - 1)
     int nt[MAX_SEG], sh0[MAX_SEG];
     double n_neutral;             // N over all shards
-    const double *sums;           // all-reduced
+    double *sums;                 // all-reduced (NCCL), or this rank's partials to be completed by `xchg`
+    XchgWaitArgs xchg;
     double2 *sh_th, *sh_acc, *sh_ring;   // [2 nst] (s-bar block, then log-sigma-bar block); ring [n][2 nst]
     const double2 *sh_pr;         // (mean, 1/var)
     PhiloxKey key;
@@ -82,6 +146,7 @@ __global__ void __launch_bounds__(256) shared_kernel(const SharedArgs<real> a) {
     double *u_t = z_t + (size_t)a.K * n2;                    // [R][K][tmax] sum_all w res
     double *lp_t = u_t + (size_t)a.R * a.K * a.tmax;         // [R][K][tmax] log-density pieces
     double *lsig_t = lp_t + (size_t)a.R * a.K * a.tmax;      // [n2] log sigma before the update
+    xchg_wait_and_sum(a.xchg, a.sums);                       // multi-GPU: complete the sums over NVLink peer memory
     // ---- phase 0
     for (int j = tid; j < a.K * n2; j += nthr) {
         const int k = j / n2, i = j % n2;

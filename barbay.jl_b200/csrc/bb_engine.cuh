@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -35,6 +36,7 @@ struct NcclApi {
     int (*GetUniqueId)(UniqueId *) = nullptr;
     int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, Comm, cudaStream_t) = nullptr;
     int (*CommDestroy)(Comm) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     void *lib = nullptr;
@@ -53,6 +55,7 @@ struct NcclApi {
             api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
             api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
             api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+            api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
             api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
             api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
         }
@@ -210,6 +213,15 @@ template <typename real> class Engine : public EngineBase {
     DBuf<double> trace_;
     // comm
     NcclApi::Comm comm_ = nullptr;
+    // peer-memory exchange (see bb_aux_kernels.cuh): local buffer + IPC-mapped peer buffers
+    bool xchg_on_ = false;
+    unsigned long long xchg_seq_ = 0;
+    void *xchg_mem_ = nullptr;
+    std::vector<void *> xchg_peer_mem_;
+    DBuf<int> xchg_err_;
+    size_t xchg_flag_off_ = 0;
+    void setup_peer_exchange();
+    void check_peer_exchange();
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> tev_;   // per-step kernel brackets while timing
     int tev_pos_ = -1;               // >= 0: record pass brackets into tev_
@@ -284,6 +296,9 @@ template <typename real> Engine<real>::Engine(const bb_desc &d) {
 }
 
 template <typename real> Engine<real>::~Engine() {
+    for (size_t r = 0; r < xchg_peer_mem_.size(); ++r)
+        if (xchg_peer_mem_[r] && (int)r != L.rank) cudaIpcCloseMemHandle(xchg_peer_mem_[r]);
+    if (xchg_mem_) cudaFree(xchg_mem_);
     if (comm_) NcclApi::get().CommDestroy(comm_);
     for (auto &e : ev_) if (e) cudaEventDestroy(e);
     for (auto &e : tev_) cudaEventDestroy(e);
@@ -507,6 +522,7 @@ void Engine<real>::gather_to_ref(const r2 *lam, const r2 *bc, const r2 *hy, cons
 }
 
 template <typename real> void Engine<real>::get_params(double *mu, double *omega, bool posterior) {
+    check_peer_exchange();
     hostvec_a_.ensure(L.D); hostvec_b_.ensure(L.D);
     gather_to_ref(lam_th_.p, bc_th_.p, hy_th_.p, sh_th_.p, hostvec_a_.p, hostvec_b_.p, posterior);
     BB_CUDA(cudaMemcpyAsync(mu, hostvec_a_.p, sizeof(double) * L.D, cudaMemcpyDeviceToHost, stream_));
@@ -640,7 +656,23 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         reduce_kernel<<<cdiv((long long)nwarps * 32, 128), 128, 0, stream_>>>(ra, L.R);
         ++launches;
     }
-    if (comm_) {
+    XchgWaitArgs xw{};
+    if (comm_ && xchg_on_) {
+        // one-shot all-reduce over NVLink peer memory, completed inside shared_kernel
+        ++xchg_seq_;
+        XchgPostArgs xp{};
+        xp.sums = sums_.p; xp.P = (int)sums_.n; xp.world = L.world; xp.rank = L.rank;
+        xp.parity = (int)(xchg_seq_ & 1ull); xp.seq = xchg_seq_;
+        for (int r = 0; r < L.world; ++r) {
+            xp.peer_buf[r] = reinterpret_cast<double *>(xchg_peer_mem_[r]);
+            xp.peer_flag[r] = reinterpret_cast<unsigned long long *>(static_cast<char *>(xchg_peer_mem_[r]) + xchg_flag_off_);
+        }
+        xchg_post_kernel<<<1, 256, 0, stream_>>>(xp);
+        ++launches;
+        xw.buf = reinterpret_cast<const double *>(xchg_mem_);
+        xw.flag = reinterpret_cast<const unsigned long long *>(static_cast<char *>(xchg_mem_) + xchg_flag_off_);
+        xw.P = (int)sums_.n; xw.world = L.world; xw.parity = xp.parity; xw.seq = xchg_seq_; xw.err = xchg_err_.p;
+    } else if (comm_) {
         int rc = NcclApi::get().AllReduce(sums_.p, sums_.p, sums_.n, kNcclFloat64, kNcclSum, comm_, stream_);
         if (rc != 0) throw std::runtime_error(std::string("ncclAllReduce: ") + NcclApi::get().GetErrorString(rc));
     }
@@ -650,7 +682,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         sa.R = L.R; sa.K = L.K; sa.tmax = L.tmax; sa.nst = L.nst;
         for (int r = 0; r < L.R; ++r) { sa.nt[r] = L.nt[r]; sa.sh0[r] = L.sh0[r]; }
         sa.n_neutral = (double)L.N;
-        sa.sums = sums_.p; sa.sh_th = sh_th_.p; sa.sh_acc = sh_acc_.p;
+        sa.sums = sums_.p; sa.xchg = xw; sa.sh_th = sh_th_.p; sa.sh_acc = sh_acc_.p;
         sa.sh_ring = sh_ring_.p ? sh_ring_.p + (size_t)ring_slot_ * 2 * L.nst : nullptr; sa.sh_pr = sh_pr_.p;
         sa.key = pkey; sa.step = m.step;
         sa.eps_sh = m.sup ? sup_sh_.p : nullptr; sa.z_direct = m.z_direct ? 1 : 0;
@@ -925,6 +957,70 @@ template <typename real> void Engine<real>::comm_init(const char id[128]) {
     BB_CUDA(cudaSetDevice(device_));
     int rc = api.CommInitRank(&comm_, L.world, uid, L.rank);
     if (rc != 0) throw std::runtime_error(std::string("ncclCommInitRank: ") + api.GetErrorString(rc));
+    if (!getenv("BB_NO_P2P")) setup_peer_exchange();
+}
+
+// Exchange buffer [2][world][P] doubles + flags [2][world], shared with every peer through CUDA IPC
+// (handles all-gathered over the NCCL communicator just created).  Any failure leaves the NCCL
+// all-reduce in place.
+template <typename real> void Engine<real>::setup_peer_exchange() {
+    if (L.world > MAX_WORLD) return;
+    NcclApi &api = NcclApi::get();
+    const size_t P = sums_.n;
+    xchg_flag_off_ = ((size_t)2 * L.world * P * sizeof(double) + 255) / 256 * 256;
+    const size_t bytes = xchg_flag_off_ + (size_t)2 * L.world * sizeof(unsigned long long);
+    BB_CUDA(cudaMalloc(&xchg_mem_, bytes));
+    BB_CUDA(cudaMemset(xchg_mem_, 0, bytes));
+    xchg_err_.alloc(1);
+    cudaIpcMemHandle_t mine;
+    const bool dbg = getenv("BB_DEBUG") != nullptr;
+    cudaError_t ge = cudaIpcGetMemHandle(&mine, xchg_mem_);
+    int ok = ge == cudaSuccess ? 1 : 0;
+    if (!ok) { cudaGetLastError(); if (dbg) fprintf(stderr, "[bb rank %d] cudaIpcGetMemHandle: %s\n", L.rank, cudaGetErrorString(ge)); }
+    DBuf<unsigned char> send, recv;
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    send.alloc(rec); recv.alloc(rec * L.world);
+    std::vector<unsigned char> h(rec, 0);
+    std::memcpy(h.data(), &mine, sizeof(mine));
+    h[sizeof(mine)] = (unsigned char)ok;
+    BB_CUDA(cudaMemcpyAsync(send.p, h.data(), rec, cudaMemcpyHostToDevice, stream_));
+    int rc = api.AllGather(send.p, recv.p, rec, /*ncclUint8*/ 1, comm_, stream_);
+    if (rc != 0) throw std::runtime_error(std::string("ncclAllGather: ") + api.GetErrorString(rc));
+    std::vector<unsigned char> all(rec * L.world);
+    BB_CUDA(cudaMemcpyAsync(all.data(), recv.p, all.size(), cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaStreamSynchronize(stream_));
+    for (int r = 0; r < L.world; ++r) ok &= all[r * rec + sizeof(mine)];
+    xchg_peer_mem_.assign(L.world, nullptr);
+    for (int r = 0; r < L.world && ok; ++r) {
+        if (r == L.rank) { xchg_peer_mem_[r] = xchg_mem_; continue; }
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, all.data() + r * rec, sizeof(hd));
+        cudaError_t oe = cudaIpcOpenMemHandle(&xchg_peer_mem_[r], hd, cudaIpcMemLazyEnablePeerAccess);
+        if (oe != cudaSuccess) {
+            if (dbg) fprintf(stderr, "[bb rank %d] cudaIpcOpenMemHandle(peer %d): %s\n", L.rank, r, cudaGetErrorString(oe));
+            cudaGetLastError();
+            xchg_peer_mem_[r] = nullptr;
+            ok = 0;
+        }
+    }
+    // every rank must take the same path: agree on success with one more (tiny) collective
+    DBuf<int> flag;
+    flag.alloc(1);
+    BB_CUDA(cudaMemcpyAsync(flag.p, &ok, sizeof(int), cudaMemcpyHostToDevice, stream_));
+    rc = api.AllReduce(flag.p, flag.p, 1, /*ncclInt32*/ 2, /*ncclMin*/ 3, comm_, stream_);
+    if (rc != 0) throw std::runtime_error(std::string("ncclAllReduce: ") + api.GetErrorString(rc));
+    BB_CUDA(cudaMemcpyAsync(&ok, flag.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaStreamSynchronize(stream_));
+    xchg_on_ = ok != 0;
+    if (dbg) fprintf(stderr, "[bb rank %d] peer-memory exchange %s\n", L.rank, xchg_on_ ? "enabled" : "disabled (NCCL all-reduce)");
+}
+
+template <typename real> void Engine<real>::check_peer_exchange() {
+    if (!xchg_on_) return;
+    int err = 0;
+    BB_CUDA(cudaMemcpyAsync(&err, xchg_err_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaStreamSynchronize(stream_));
+    if (err) throw std::runtime_error("peer-memory exchange timed out: a rank did not post its partial sums");
 }
 
 }  // namespace bb
