@@ -413,10 +413,12 @@ __global__ void noise_columns_kernel(const SegList segs, int cpad, int row, int 
     const uint32_t colid = col_id ? col_id[c] : sg.colid0 + (uint32_t)(c - sg.col0);
     const int slot = is_bc ? sg.nt + row : row;
     for (int k = 0; k < K; ++k) {
-        real n[4];
-        normals4<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)(slot >> 2), (uint32_t)k, step, key, n);
-        const int l = slot & 3;
-        eps[(size_t)k * D + m] = (double)(l == 0 ? n[0] : l == 1 ? n[1] : l == 2 ? n[2] : n[3]);
+        real n[8];
+        normals8<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)(slot >> 3), (uint32_t)k, step, key, n);
+        real r = n[0];
+#pragma unroll
+        for (int l = 1; l < 8; ++l) r = (slot & 7) == l ? n[l] : r;
+        eps[(size_t)k * D + m] = (double)r;
     }
 }
 

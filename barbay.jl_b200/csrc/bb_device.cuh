@@ -55,46 +55,59 @@ __device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ft
 __device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// uniform in (0,1) from the top 23 bits: ((x >> 9) + 0.5) / 2^23
-__device__ __forceinline__ float u23(uint32_t x, float) {
-    return __uint_as_float(0x3f800000u | (x >> 9)) - 0.99999994039535522f;   // f - (1 - 2^-24), exact
+// One 32-bit Philox word feeds one Box-Muller pair: the top 21 bits give the radius uniform
+// u = (j + 0.5) / 2^21 (largest radius 5.5 sigma), the low 11 bits the angle v = (a + 0.5) / 2^11.
+// With 2048 equispaced angles every trigonometric moment up to order 2047 equals that of a continuous
+// angle, so the pair is exactly uncorrelated with exact second and fourth moments; one Philox4x32-10
+// call therefore yields eight standard normals.  Identical definition in fp32 and fp64.
+__device__ __forceinline__ void word_uniforms(uint32_t x, float &u, float &v) {
+    u = __uint_as_float(0x3f800000u | ((x >> 9) & 0x7ffffcu)) - 0.99999976158142089844f;   // f - (1 - 2^-22), exact
+    v = __uint_as_float(0x3f800000u | ((x << 12) & 0x7ff000u)) - 0.999755859375f;          // f - (1 - 2^-12), exact
 }
-__device__ __forceinline__ double u23(uint32_t x, double) {
-    return (static_cast<double>(x >> 9) + 0.5) * (1.0 / 8388608.0);
+__device__ __forceinline__ void word_uniforms(uint32_t x, double &u, double &v) {
+    u = (static_cast<double>(x >> 11) + 0.5) * (1.0 / 2097152.0);
+    v = (static_cast<double>(x & 0x7ffu) + 0.5) * (1.0 / 2048.0);
 }
 
-__device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, float &n0, float &n1) {
-    const float u = u23(xa, 0.f), v = u23(xb, 0.f);
+__device__ __forceinline__ void box_muller(uint32_t x, float &n0, float &n1) {
+    float u, v;
+    word_uniforms(x, u, v);
     const float radius = fast_sqrt(-1.3862943611198906f * fast_lg2(u));   // sqrt(-2 ln u)
     float s, c;
     __sincosf(6.2831853071795865f * v, &s, &c);
     n0 = radius * c; n1 = radius * s;
 }
-__device__ __forceinline__ void box_muller(uint32_t xa, uint32_t xb, double &n0, double &n1) {
-    const double u = u23(xa, 0.0), v = u23(xb, 0.0);
+__device__ __forceinline__ void box_muller(uint32_t x, double &n0, double &n1) {
+    double u, v;
+    word_uniforms(x, u, v);
     const double radius = sqrt(-2.0 * log(u));
     double s, c;
     sincospi(2.0 * v, &s, &c);
     n0 = radius * c; n1 = radius * s;
 }
 
+// eight normals per counter: word w -> lanes 2w (radius * cos) and 2w + 1 (radius * sin)
 template <typename real>
-__device__ __forceinline__ void normals4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                         const PhiloxKey &key, real (&n)[4]) {
+__device__ __forceinline__ void normals8(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                         const PhiloxKey &key, real (&n)[8]) {
     uint32_t x[4];
     philox4x32_10(c0, c1, c2, c3, key, x);
-    box_muller(x[0], x[1], n[0], n[1]);
-    box_muller(x[2], x[3], n[2], n[3]);
+    box_muller(x[0], n[0], n[1]);
+    box_muller(x[1], n[2], n[3]);
+    box_muller(x[2], n[4], n[5]);
+    box_muller(x[3], n[6], n[7]);
 }
 
 // normal attached to slot `i` of a non-column stream (shared / hyper / init)
 template <typename real>
 __device__ __forceinline__ real stream_normal(uint32_t stream, uint32_t i, uint32_t k, uint32_t step,
                                               const PhiloxKey &key) {
-    real n[4];
-    normals4<real>(i >> 2, stream << 24, k, step, key, n);
-    const uint32_t lane = i & 3u;
-    return lane == 0 ? n[0] : lane == 1 ? n[1] : lane == 2 ? n[2] : n[3];
+    real n[8];
+    normals8<real>(i >> 3, stream << 24, k, step, key, n);
+    real r = n[0];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) r = (i & 7u) == (uint32_t)l ? n[l] : r;
+    return r;
 }
 
 // ---------------------------------------------------------------- scalar math

@@ -38,7 +38,7 @@ template <int NT, int NE, bool HIER> struct Shape {
     static constexpr int MAXT = TD<NT>::MAX;
     static constexpr int MAXE = ED<NE>::MAX;
     static constexpr int MAXJ = PER * MAXE;
-    static constexpr int MAXC = ((MAXT + MAXJ + 3) / 4) * 4;   // noise slots, padded to whole Philox quads
+    static constexpr int MAXC = ((MAXT + MAXJ + 7) / 8) * 8;   // noise slots, padded to whole Philox calls (8 normals)
 };
 
 __device__ __forceinline__ int find_segment(const SegList &sl, int blk) {
@@ -62,11 +62,12 @@ __device__ __forceinline__ void column_noise(real (&eps)[MAXC], int nclass, int 
         }
     } else {
 #pragma unroll
-        for (int q = 0; q < MAXC / 4; ++q) {
-            if (q * 4 >= nclass) break;
-            real n[4];
-            normals4<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k, step, key, n);
-            eps[4 * q + 0] = n[0]; eps[4 * q + 1] = n[1]; eps[4 * q + 2] = n[2]; eps[4 * q + 3] = n[3];
+        for (int q = 0; q < MAXC / 8; ++q) {
+            if (q * 8 >= nclass) break;
+            real n[8];
+            normals8<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k, step, key, n);
+#pragma unroll
+            for (int l = 0; l < 8; ++l) eps[8 * q + l] = n[l];
         }
     }
 }

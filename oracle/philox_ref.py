@@ -47,45 +47,50 @@ def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
     return (c0.astype(np.uint32), c1.astype(np.uint32), c2.astype(np.uint32), c3.astype(np.uint32))
 
 
-def u23(x: np.ndarray) -> np.ndarray:
-    """Open-interval uniform from the top 23 bits: ((x >> 9) + 0.5) / 2^23."""
-    return ((x >> np.uint32(9)).astype(np.float64) + 0.5) / 8388608.0
+def word_uniforms(x: np.ndarray):
+    """One Philox word -> (radius uniform from the top 21 bits, angle uniform from the low 11 bits)."""
+    u = ((x >> np.uint32(11)).astype(np.float64) + 0.5) / 2097152.0
+    v = ((x & np.uint32(0x7FF)).astype(np.float64) + 0.5) / 2048.0
+    return u, v
 
 
-def box_muller(xa: np.ndarray, xb: np.ndarray):
-    """(xa, xb) -> (radius*cos(angle), radius*sin(angle))."""
-    radius = np.sqrt(-2.0 * np.log(u23(xa)))
-    angle = 2.0 * np.pi * u23(xb)
+def box_muller(x: np.ndarray):
+    """word -> (radius*cos(angle), radius*sin(angle))."""
+    u, v = word_uniforms(x)
+    radius = np.sqrt(-2.0 * np.log(u))
+    angle = 2.0 * np.pi * v
     return radius * np.cos(angle), radius * np.sin(angle)
 
 
-def normals4(c0, c1, c2, c3, seed: int):
-    """Four standard normals per counter: lanes 0,1 from words (0,1); 2,3 from (2,3)."""
-    x0, x1, x2, x3 = philox4x32_10(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    n0, n1 = box_muller(x0, x1)
-    n2, n3 = box_muller(x2, x3)
-    return np.stack([n0, n1, n2, n3], axis=-1)
+def normals8(c0, c1, c2, c3, seed: int):
+    """Eight standard normals per counter: word w -> lanes 2w, 2w + 1."""
+    xs = philox4x32_10(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    out = []
+    for x in xs:
+        a, b = box_muller(x)
+        out += [a, b]
+    return np.stack(out, axis=-1)
 
 
 def lattice_normal(entity, slot, stream: int, k: int, step: int, seed: int) -> np.ndarray:
     """Normal attached to (stream, entity, slot) for MC sample k of ADVI step ``step``.
 
-    counter = (entity_word, stream << 24 | quad, k, step) with
-      column stream : entity_word = column id, quad = slot >> 2, lane = slot & 3
-      other streams : entity_word = slot >> 2 (entity unused), quad = 0, lane = slot & 3
+    counter = (entity_word, stream << 24 | call, k, step) with
+      column stream : entity_word = column id, call = slot >> 3, lane = slot & 7
+      other streams : entity_word = slot >> 3 (entity unused), call = 0, lane = slot & 7
     """
     entity = np.asarray(entity, dtype=np.uint32)
     slot = np.asarray(slot, dtype=np.uint32)
     if stream == STREAM_COLUMN:
         c0 = entity
-        quad = slot >> np.uint32(2)
+        call = slot >> np.uint32(3)
     else:
-        c0 = slot >> np.uint32(2)
-        quad = np.zeros_like(slot)
-    c1 = (np.uint32(stream) << np.uint32(24)) | quad
-    lane = (slot & np.uint32(3)).astype(np.int64)
-    n4 = normals4(c0, c1, np.uint32(k), np.uint32(step), seed)
-    return np.take_along_axis(n4, lane[..., None], axis=-1)[..., 0]
+        c0 = slot >> np.uint32(3)
+        call = np.zeros_like(slot)
+    c1 = (np.uint32(stream) << np.uint32(24)) | call
+    lane = (slot & np.uint32(7)).astype(np.int64)
+    n8 = normals8(c0, c1, np.uint32(k), np.uint32(step), seed)
+    return np.take_along_axis(n8, lane[..., None], axis=-1)[..., 0]
 
 
 # --------------------------------------------------------------------------

@@ -18,10 +18,14 @@ def test_philox4x32_10_known_answers():
         assert tuple(int(x) for x in out) == exp
 
 
-def test_u23_is_open_interval_and_box_muller_moments():
-    x = np.array([0, 0xFFFFFFFF, 0x80000000], dtype=np.uint32)
-    u = philox_ref.u23(x)
-    assert u.min() > 0 and u.max() < 1
+def test_uniforms_open_interval_and_box_muller_moments():
+    x = np.array([0, 0xFFFFFFFF, 0x80000000, 0x7FF, 0xFFFFF800], dtype=np.uint32)
+    u, v = philox_ref.word_uniforms(x)
+    assert u.min() > 0 and u.max() < 1 and v.min() > 0 and v.max() < 1
+    # 2048 equispaced angles: trigonometric moments are exact (cos^2 -> 1/2, cos^4 -> 3/8, cos*sin -> 0)
+    ang = 2 * np.pi * (np.arange(2048) + 0.5) / 2048
+    assert abs(np.mean(np.cos(ang) ** 2) - 0.5) < 1e-14 and abs(np.mean(np.cos(ang) ** 4) - 0.375) < 1e-14
+    assert abs(np.mean(np.cos(ang) * np.sin(ang))) < 1e-14
     idx = np.arange(200_000, dtype=np.uint32)
     n = philox_ref.lattice_normal(idx, np.zeros_like(idx), philox_ref.STREAM_COLUMN, 0, 0, 12345)
     assert abs(n.mean()) < 0.01 and abs(n.std() - 1) < 0.01
