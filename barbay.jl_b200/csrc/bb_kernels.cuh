@@ -345,13 +345,13 @@ __device__ __forceinline__ void opt_apply(const OptArgsT<real> &o, real g, real 
 // The mode is block-uniform, so each instantiation is a straight line of ~40 instructions.
 template <typename real, int MODE>
 __device__ __forceinline__ void finish_latent_mode(const OptArgsT<real> &o, real invK, real sgrad, real sgrade,
-                                                   vec2<real> &th, vec2<real> ac, vec2<real> rg, vec2<real> *th_ptr,
+                                                   real sigma, vec2<real> &th, vec2<real> ac, vec2<real> rg, vec2<real> *th_ptr,
                                                    vec2<real> *acc_ptr, vec2<real> *ring_ptr, vec2<real> *gout_ptr) {
     // rg: the ring slot evicted this step (MODE 1 only); th is updated in place (MODE 0 / 1)
     if constexpr (MODE == 3) return;
-    // d ELBO / d mu = mean_k g ; d ELBO / d omega = (mean_k g eps + 1/sigma) sigmoid(omega)
-    real sigma, sgm;
-    softplus_sigmoid(th.y, sigma, sgm);
+    // d ELBO / d mu = mean_k g ; d ELBO / d omega = (mean_k g eps + 1/sigma) sigmoid(omega), and
+    // sigmoid(w) = exp(w - softplus(w)): sigma is already at hand from the prologue
+    const real sgm = bb_exp(th.y - sigma);
     const real gm = sgrad * invK;
     const real go = (sgrade * invK + bb_rcp(sigma)) * sgm;
     if constexpr (MODE == 2) {
@@ -383,12 +383,13 @@ template <typename real>
 __device__ __forceinline__ void finish_latent(const OptArgsT<real> &o, real invK, real sgrad, real sgrade,
                                               vec2<real> th, vec2<real> ac, vec2<real> *th_ptr,
                                               vec2<real> *acc_ptr, vec2<real> *ring_ptr, vec2<real> *gout_ptr) {
+    const real sigma = softplus_only<real>(th.y);
     if (o.update) {
         const vec2<real> z2 = mk2<real>(0, 0);
-        if (o.kind == 1) finish_latent_mode<real, 0>(o, invK, sgrad, sgrade, th, ac, z2, th_ptr, acc_ptr, ring_ptr, gout_ptr);
-        else finish_latent_mode<real, 1>(o, invK, sgrad, sgrade, th, ac, *ring_ptr, th_ptr, acc_ptr, ring_ptr, gout_ptr);
+        if (o.kind == 1) finish_latent_mode<real, 0>(o, invK, sgrad, sgrade, sigma, th, ac, z2, th_ptr, acc_ptr, ring_ptr, gout_ptr);
+        else finish_latent_mode<real, 1>(o, invK, sgrad, sgrade, sigma, th, ac, *ring_ptr, th_ptr, acc_ptr, ring_ptr, gout_ptr);
     } else if (gout_ptr) {
-        finish_latent_mode<real, 2>(o, invK, sgrad, sgrade, th, ac, mk2<real>(0, 0), th_ptr, acc_ptr, ring_ptr, gout_ptr);
+        finish_latent_mode<real, 2>(o, invK, sgrad, sgrade, sigma, th, ac, mk2<real>(0, 0), th_ptr, acc_ptr, ring_ptr, gout_ptr);
     }
 }
 
@@ -542,6 +543,9 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
         }
         const int nclass = seg.neutral ? nt : nt + nj;
 
+        // the K samples; instantiated twice so the common vector-prior case carries no per-latent prior loads
+        auto sample_loop = [&](auto matpr_tag) {
+        constexpr bool MATPR = decltype(matpr_tag)::value;
 #pragma unroll kP2Unroll
         for (int k = 0; k < a.K; ++k) {
             real eps[S::MAXC];
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
                 z[t] = fma(sg[t], eps[t], mu[t]);
                 const real lam = bb_exp(z[t]);
                 r2 p = C.lam_pr_s;
-                if (lam_mat) p = npr ? spr[t * BLOCK] : C.lam_pr[(size_t)t * cpad + c];
+                if constexpr (MATPR) if (lam_mat) p = npr ? spr[t * BLOCK] : C.lam_pr[(size_t)t * cpad + c];
                 const real dz = z[t] - p.x;
                 // Poisson (collapsed Poisson x Multinomial) + logLambda coupling + Normal prior
                 g[t] = (cnt[t] - lam) + lam * cG[t] - dz * p.y;
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
                 for (int j = 0; j < S::MAXJ; ++j) {
                     if (j >= nj) break;
                     r2 p = C.bc_pr_s[j % S::PER];
-                    if (bc_mat) p = npr ? spr[(nt + j) * BLOCK] : C.bc_pr[(size_t)j * cpad + c];
+                    if constexpr (MATPR) if (bc_mat) p = npr ? spr[(nt + j) * BLOCK] : C.bc_pr[(size_t)j * cpad + c];
                     const real dz = zb[j] - p.x;
                     gb[j] -= dz * p.y;
                     if (want_elbo) lp -= real(0.5) * dz * dz * p.y;
@@ -653,6 +657,9 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
             }
             if (want_elbo) sel[k * BLOCK + tid] += (double)lp;
         }
+        };
+        if (lam_mat || bc_mat) sample_loop(std::true_type{});
+        else sample_loop(std::false_type{});
         if (want_elbo) sel[a.K * BLOCK + tid] += lsig_sum;
 
         // fused optimiser update of every latent of the column (theta / accumulators re-read from the
@@ -666,7 +673,7 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
                 const r2 ac = MODE >= 2 ? mk2<real>(0, 0) : (nac ? sac[t * BLOCK] : C.lam_acc[o]);
                 const r2 rg = MODE != 1 ? mk2<real>(0, 0) : (nrg ? srg[t * BLOCK] : C.lam_ring[o]);
                 r2 th = sth[t * BLOCK];
-                finish_latent_mode<real, MODE>(a.opt, invK, sgr[t], sge[t], th, ac, rg, C.lam_th + o,
+                finish_latent_mode<real, MODE>(a.opt, invK, sgr[t], sge[t], sg[t], th, ac, rg, C.lam_th + o,
                                                C.lam_acc + o, C.lam_ring + o, a.gout_lam + o);
                 if constexpr (FUSE) { mu[t] = th.x; sg[t] = softplus_only<real>(th.y); }
             }
@@ -678,7 +685,7 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
                     const r2 ac = MODE >= 2 ? mk2<real>(0, 0) : (nac ? sac[(nt + j) * BLOCK] : C.bc_acc[o]);
                     const r2 rg = MODE != 1 ? mk2<real>(0, 0) : (nrg ? srg[(nt + j) * BLOCK] : C.bc_ring[o]);
                     r2 th = sth[(nt + j) * BLOCK];
-                    finish_latent_mode<real, MODE>(a.opt, invK, sgrb[j], sgeb[j], th, ac, rg,
+                    finish_latent_mode<real, MODE>(a.opt, invK, sgrb[j], sgeb[j], sgb[j], th, ac, rg,
                                                    C.bc_th + o, C.bc_acc + o, C.bc_ring + o, a.gout_bc + o);
                     if constexpr (FUSE) { mub[j] = th.x; sgb[j] = softplus_only<real>(th.y); }
                 }
