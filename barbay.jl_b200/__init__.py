@@ -9,10 +9,10 @@ kernels behind the C ABI of include/barbay_b200.h); there is no CPU fallback.
 The directory name carries a dot, so import it through the ``barbay_b200`` shim
 at the repository root (``import barbay_b200 as bb``).
 """
-from . import _lib, model, utils, vi, engine, synth   # noqa: F401
+from . import _lib, model, utils, vi, engine, synth, stats   # noqa: F401
 from ._lib import BarBayError, LIB_PATH, load as load_library   # noqa: F401
 from .engine import Engine, comm_unique_id   # noqa: F401
 from .vi import ADVI, DecayedADAGrad, TruncatedADAGrad, advi   # noqa: F401
 
-__all__ = ["model", "utils", "vi", "engine", "synth", "Engine", "advi", "ADVI", "TruncatedADAGrad",
+__all__ = ["model", "utils", "vi", "engine", "synth", "stats", "Engine", "advi", "ADVI", "TruncatedADAGrad",
            "DecayedADAGrad", "BarBayError", "load_library", "LIB_PATH", "comm_unique_id"]

@@ -101,3 +101,17 @@ def test_recovers_simulator_ground_truth(bb):
     F = (R + 1.0) / (R + 1.0).sum(axis=1, keepdims=True)
     naive = -np.log(F[1:, :da.n_neutral] / F[:-1, :da.n_neutral]).mean(axis=1)   # stats.naive_fitness idea
     assert np.max(np.abs(pop - naive)) < 0.25, np.max(np.abs(pop - naive))
+
+
+def test_documented_workflow_with_naive_priors(bb):
+    """docs/src/examples.md:121-160: naive_prior -> matrix priors -> advi(TruncatedADAGrad).  The
+    population mean fitness posterior must stay near its informative prior and the output keep the
+    reference's columns."""
+    df, _ = load_fixture("fitness_normal")
+    pri = bb.stats.prior_matrices(bb.stats.naive_prior(df.copy()))
+    out = bb.advi(data=df, model=bb.model.fitness_normal, model_kwargs=pri, advi=bb.ADVI(1, 3000),
+                  opt=bb.TruncatedADAGrad(), verbose=False, seed=11, dtype="f32")
+    pop = out[out.vartype == "pop_mean_fitness"]
+    assert np.all(np.abs(pop["mean"].to_numpy() - pri["s_pop_prior"][:, 0]) < 0.2)
+    assert list(out.columns) == ["mean", "std", "varname", "vartype", "id"]
+    assert np.isfinite(out["mean"]).all() and (out["std"] > 0).all()
