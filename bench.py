@@ -265,27 +265,56 @@ def main():
         ms = float(t.item())
     value = units_step * args.steps / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (pass 2: gradient + fused update), live CUDA-event brackets
+    # ---- roofline of the dominant kernel, live CUDA-event brackets on the launching stream.
+    # For non-hierarchical models the step runs one fused kernel (pass 2 of step i + pass 1 of step i+1:
+    # theta, accumulators and counts cross HBM exactly once per step) plus two small kernels.
     n_prof = min(200, max(10, args.steps))
     ms_tot, ms_p1, ms_p2 = eng.time_steps(n_prof)
     barrier()
-    clocks = sampler.summary(t_wall0, time.time()) if sampler else None
     peak, peak_src = measured_peak_gbs()
     t_p2 = ms_p2 / n_prof * 1e-3
     t_p1 = ms_p1 / n_prof * 1e-3
     achieved = alg_bytes / t_p2 / 1e9
     step_achieved = alg_bytes / (ms / args.steps * 1e-3) / 1e9
+    fused = t_p1 < 0.1 * t_p2
     roofline = {
-        "bound": "hbm", "kernel": "pass2_kernel (gradient + fused optimiser update)",
+        "bound": "hbm",
+        "kernel": "pass2_kernel<..., FUSE=1> (gradient + fused optimiser update + next step's pass-1 sums)" if fused
+                  else "pass2_kernel (gradient + fused optimiser update)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of pass2_kernel from the committed ncu --set full capture
-        # (profiles/r1_ncu_pass_kernels.csv; cfg2 fp32 K=8 DecayedADAGrad, 1 GPU) -- null for other configurations
-        "traffic": 186.5e6 if (world == 1 and args.dtype == "f32" and args.opt == "decayed") else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
+        # (profiles/r1_ncu_fused_kernel.csv; cfg2 fp32 K=8 DecayedADAGrad, 1 GPU) -- null for other configurations
+        "traffic": 186.7e6 if (world == 1 and args.dtype == "f32" and args.opt == "decayed" and K == 8) else None,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
         "kernel_us": t_p2 * 1e6, "pass1_us": t_p1 * 1e6, "step_us": ms / args.steps * 1e3,
         "kernel_share_of_step": t_p2 / (ms_tot / n_prof * 1e-3),
         "step_achieved": step_achieved, "step_frac": step_achieved / peak,
+        "note": "K=8: issue/MUFU-bound (noise generated in both passes), see profiles/; roofline_k1 shows the "
+                "bandwidth-bound regime of the reference's default samples_per_step=1",
     }
+    # the same measurement at the reference's default samples_per_step = 1 (src/vi.jl:98), for context
+    roofline_k1 = None
+    if world == 1 and K != 1:
+        eng1 = bb.Engine(da, model, n_samples=1, dtype=args.dtype, seed=20261018, device=local_rank)
+        eng1.set_stream(stream.cuda_stream)
+        eng1.init_params(1)
+        eng1.set_optimizer(args.opt)
+        eng1.step(20)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        eng1.step(n_prof)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        step1 = a0.elapsed_time(a1) / n_prof * 1e-3
+        _, _, k1_p2 = eng1.time_steps(n_prof)
+        ab1 = eng1.algorithmic_bytes_per_step
+        roofline_k1 = {"bound": "hbm", "achieved": ab1 / (k1_p2 / n_prof * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": ab1 / (k1_p2 / n_prof * 1e-3) / 1e9 / peak, "kernel_us": k1_p2 / n_prof * 1e3,
+                       "step_us": step1 * 1e6, "step_achieved": ab1 / step1 / 1e9, "step_frac": ab1 / step1 / 1e9 / peak,
+                       "value": B * T / step1, "mc_samples": 1}
+        eng1.close()
+    clocks = sampler.summary(t_wall0, time.time()) if sampler else None
 
     # ---- end to end through the public API with HOST buffers: one complete advi()-equivalent call
     # (pack -> bb_create: H2D of counts/maps -> init -> optimiser -> n steps -> ELBO read-back ->
@@ -355,7 +384,7 @@ def main():
                        "l2": "inputs_exceed_l2 (per-step working set > 126 MB, no flush needed)",
                        "parallelism": f"barcode-sharded x{world}, one NCCL all-reduce of {5 * T * K} doubles per step"
                        if world > 1 else "single GPU"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "roofline_k1": roofline_k1, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
     eng.close()
