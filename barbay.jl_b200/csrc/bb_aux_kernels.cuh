@@ -414,7 +414,7 @@ __global__ void noise_columns_kernel(const SegList segs, int cpad, int row, int 
     const int slot = is_bc ? sg.nt + row : row;
     for (int k = 0; k < K; ++k) {
         real n[8];
-        normals8<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)(slot >> 3), (uint32_t)k, step, key, n);
+        normals8<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)(slot >> 3), (uint32_t)k, step, key, key.trig, n);
         real r = n[0];
 #pragma unroll
         for (int l = 1; l < 8; ++l) r = (slot & 7) == l ? n[l] : r;

@@ -29,11 +29,13 @@ template <typename real> __device__ __forceinline__ vec2<real> mk2(real a, real 
 // and sit in the kernel's constant bank, so a round is 2 IMAD.WIDE + 2 LOP3.
 struct PhiloxKey {
     uint32_t k0[10], k1[10];
+    const float2 *trig;     // fp32 Box-Muller direction table in global memory (TRIG_N entries), see box_muller
 };
 inline PhiloxKey make_philox_key(uint64_t seed) {
     PhiloxKey k;
     uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
     for (int r = 0; r < 10; ++r) { k.k0[r] = a; k.k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+    k.trig = nullptr;
     return k;
 }
 
@@ -60,26 +62,22 @@ __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ft
 // With 2048 equispaced angles every trigonometric moment up to order 2047 equals that of a continuous
 // angle, so the pair is exactly uncorrelated with exact second and fourth moments; one Philox4x32-10
 // call therefore yields eight standard normals.  Identical definition in fp32 and fp64.
-__device__ __forceinline__ void word_uniforms(uint32_t x, float &u, float &v) {
-    u = __uint_as_float(0x3f800000u | ((x >> 9) & 0x7ffffcu)) - 0.99999976158142089844f;   // f - (1 - 2^-22), exact
-    v = __uint_as_float(0x3f800000u | ((x << 12) & 0x7ff000u)) - 0.999755859375f;          // f - (1 - 2^-12), exact
-}
-__device__ __forceinline__ void word_uniforms(uint32_t x, double &u, double &v) {
-    u = (static_cast<double>(x >> 11) + 0.5) * (1.0 / 2097152.0);
-    v = (static_cast<double>(x & 0x7ffu) + 0.5) * (1.0 / 2048.0);
-}
-
-__device__ __forceinline__ void box_muller(uint32_t x, float &n0, float &n1) {
-    float u, v;
-    word_uniforms(x, u, v);
+// fp32: the 2048 directions (cos, sin)(2 pi (a + 0.5) / 2048) come from a table instead of two MUFU ops
+// (the XU pipe is the scarce one in the column kernels): TRIG_N = 1024 correctly rounded entries cover
+// the half turn a & 1023, bit 10 of the word flips the sign of the radius.  `tab` is the table -- the
+// column kernels pass their shared-memory copy, everything else the global one of the key.
+constexpr int TRIG_N = 1024;
+__device__ __forceinline__ void box_muller(uint32_t x, float &n0, float &n1, const float2 *tab) {
+    // j = x >> 11 dropped into the mantissa of 4.0f by one funnel shift: 4 + j 2^-21, minus (4 - 2^-22) -> (j + 0.5) / 2^21, exact
+    const float u = __uint_as_float(__funnelshift_r(x, 0x204u, 11)) - 3.9999997615814208984375f;
     const float radius = fast_sqrt(-1.3862943611198906f * fast_lg2(u));   // sqrt(-2 ln u)
-    float s, c;
-    __sincosf(6.2831853071795865f * v, &s, &c);
-    n0 = radius * c; n1 = radius * s;
+    const float rs = __uint_as_float(__float_as_uint(radius) | ((x << 21) & 0x80000000u));
+    const float2 d = tab[x & (TRIG_N - 1)];
+    n0 = rs * d.x; n1 = rs * d.y;
 }
-__device__ __forceinline__ void box_muller(uint32_t x, double &n0, double &n1) {
-    double u, v;
-    word_uniforms(x, u, v);
+__device__ __forceinline__ void box_muller(uint32_t x, double &n0, double &n1, const float2 *) {
+    const double u = (static_cast<double>(x >> 11) + 0.5) * (1.0 / 2097152.0);
+    const double v = (static_cast<double>(x & 0x7ffu) + 0.5) * (1.0 / 2048.0);
     const double radius = sqrt(-2.0 * log(u));
     double s, c;
     sincospi(2.0 * v, &s, &c);
@@ -89,13 +87,13 @@ __device__ __forceinline__ void box_muller(uint32_t x, double &n0, double &n1) {
 // eight normals per counter: word w -> lanes 2w (radius * cos) and 2w + 1 (radius * sin)
 template <typename real>
 __device__ __forceinline__ void normals8(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                         const PhiloxKey &key, real (&n)[8]) {
+                                         const PhiloxKey &key, const float2 *tab, real (&n)[8]) {
     uint32_t x[4];
     philox4x32_10(c0, c1, c2, c3, key, x);
-    box_muller(x[0], n[0], n[1]);
-    box_muller(x[1], n[2], n[3]);
-    box_muller(x[2], n[4], n[5]);
-    box_muller(x[3], n[6], n[7]);
+    box_muller(x[0], n[0], n[1], tab);
+    box_muller(x[1], n[2], n[3], tab);
+    box_muller(x[2], n[4], n[5], tab);
+    box_muller(x[3], n[6], n[7], tab);
 }
 
 // normal attached to slot `i` of a non-column stream (shared / hyper / init)
@@ -103,7 +101,7 @@ template <typename real>
 __device__ __forceinline__ real stream_normal(uint32_t stream, uint32_t i, uint32_t k, uint32_t step,
                                               const PhiloxKey &key) {
     real n[8];
-    normals8<real>(i >> 3, stream << 24, k, step, key, n);
+    normals8<real>(i >> 3, stream << 24, k, step, key, key.trig, n);
     real r = n[0];
 #pragma unroll
     for (int l = 1; l < 8; ++l) r = (i & 7u) == (uint32_t)l ? n[l] : r;

@@ -202,6 +202,8 @@ template <typename real> class Engine : public EngineBase {
     DBuf<double2> sh_th_, sh_acc_, sh_ring_, sh_pr_, sh_gout_;
     DBuf<r2> lam_pr_, bc_pr_, hy_pr_;
     DBuf<int> cnt_, map_lam_, map_bc_, map_hy_, map_sh_, hgroup_, csr_off_, csr_mem_;
+    DBuf<float2> trig_;        // Box-Muller direction table of the fp32 noise lattice (bb_device.cuh)
+    PhiloxKey philox_key(uint64_t seed) const { PhiloxKey k = make_philox_key(seed); k.trig = trig_.p; return k; }
     DBuf<uint32_t> col_id_;
     DBuf<double> part_, sums_, epart_, hy_epart_, elbo_sh_, elbo_out_, sh_scratch_;
     DBuf<real> ctx_;
@@ -243,6 +245,15 @@ template <typename real> Engine<real>::Engine(const bb_desc &d) {
     stream_ = own_stream_;
     for (auto &e : ev_) BB_CUDA(cudaEventCreate(&e));
 
+    {
+        // directions (cos, sin)(2 pi (a + 0.5) / 2048), a < TRIG_N, correctly rounded to fp32
+        std::vector<float2> t(TRIG_N);
+        for (int a = 0; a < TRIG_N; ++a) {
+            const double ang = 6.283185307179586476925286766559 * ((double)a + 0.5) / 2048.0;
+            t[a] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+        trig_.upload(t);
+    }
     const size_t nlam = (size_t)L.tmax * L.cpad, nbc = (size_t)L.nj * L.cpad;
     lam_th_.alloc(nlam); lam_acc_.alloc(nlam);
     bc_th_.alloc(nbc); bc_acc_.alloc(nbc);
@@ -354,13 +365,14 @@ template <typename real> void Engine<real>::build_groups() {
             const int sweeps = (slots + max_slots - 1) / max_slots;
             slots = ((L.K + sweeps - 1) / sweeps) * pv_m;
         }
-        slots = std::max(slots, g.pv);           // at least one sample of the widest population
+        slots = std::max(slots, (g.pv + 1) & ~1);   // at least one sample of the widest population (pair layout: even)
         g.kchunk = slots;
         // + two cp.async staging buffers (see bb_kernels.cuh)
         const size_t th_b = (size_t)(L.tmax + L.nj) * BLOCK * sizeof(r2);
         const size_t p1acc = ((size_t)g.kchunk * slot_b + 15) / 16 * 16;
-        g.p1nbuf = p1acc + 2 * th_b <= kMaxSmem ? 2 : 1;
-        g.p1smem = p1acc + g.p1nbuf * th_b;
+        const size_t trig_b = TrigTab<real>::BYTES;      // fp32: Box-Muller direction table at the head of smem
+        g.p1nbuf = trig_b + p1acc + 2 * th_b <= kMaxSmem ? 2 : 1;
+        g.p1smem = trig_b + p1acc + g.p1nbuf * th_b;
         if (g.p1smem > kMaxSmem) throw std::runtime_error("T x E too large for the column kernels' shared memory");
         BB_CUDA(cudaFuncSetAttribute((const void *)g.ks.pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p1smem));
         BB_CUDA(cudaFuncSetAttribute((const void *)g.ks_sup.pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p1smem));
@@ -379,7 +391,9 @@ template <typename real> void Engine<real>::build_groups() {
 // by set_optimizer
 template <typename real> void Engine<real>::size_pass2() {
     const size_t th_b = (size_t)(L.tmax + L.nj) * BLOCK * sizeof(r2);
-    const size_t ctx_b = (((size_t)L.K * 3 * L.tmax * sizeof(real)) + 15) / 16 * 16;
+    // fixed head of the pass-2 shared memory: fp32 Box-Muller direction table + the per-sample context
+    constexpr int kVW = 16 / (int)sizeof(real);           // context rows are padded to 16 bytes (bb_kernels.cuh)
+    const size_t ctx_b = TrigTab<real>::BYTES + (size_t)L.K * (((3 * L.tmax + kVW - 1) / kVW) * kVW) * sizeof(real);
     const int npr = (L.lam_pr_matrix || L.bc_pr_matrix) ? 1 : 0;
     const int nrg = opt_.kind == BB_OPT_TRUNCATED_ADAGRAD ? 1 : 0;
     size_t epart_off = 0;
@@ -388,10 +402,11 @@ template <typename real> void Engine<real>::size_pass2() {
         // (1 buffer, theta + counts only; accumulators / priors / ring read from global)
         const size_t cn_b = (size_t)L.tmax * BLOCK * sizeof(int);
         const size_t sel_b = (size_t)(L.K + 1) * BLOCK * sizeof(double);
-        const size_t full_b = (2 + npr + nrg) * th_b + cn_b;
+        // prefetched set (theta, priors, counts: one or two buffers) + epilogue set (accumulators, ring: one)
+        const size_t pre_b = (1 + npr) * th_b + cn_b, epi_b = (1 + nrg) * th_b;
         g.p2nbuf = 2; g.p2stage_acc = 1;
-        size_t stage_b = 2 * full_b;
-        if (ctx_b + sel_b + stage_b > kMaxSmem) { g.p2nbuf = 1; stage_b = full_b; }
+        size_t stage_b = 2 * pre_b + epi_b;
+        if (ctx_b + sel_b + stage_b > kMaxSmem) { g.p2nbuf = 1; stage_b = pre_b + epi_b; }
         if (ctx_b + sel_b + stage_b > kMaxSmem) { g.p2stage_acc = 0; stage_b = th_b + cn_b; }
         if (ctx_b + sel_b + stage_b > kMaxSmem)
             throw std::runtime_error("T x E too large for the column kernels' shared memory");
@@ -401,7 +416,7 @@ template <typename real> void Engine<real>::size_pass2() {
         g.facc_slots = 0;
         if (g.ks.pass2_fused && !getenv("BB_NO_FUSE")) {
             const int pv_m = L.E == 1 ? 2 * g.nt : g.pv;
-            const int slots = std::max(L.K * pv_m, g.pv);
+            const int slots = std::max(L.K * pv_m, (g.pv + 1) & ~1);
             const size_t fs = g.p2smem + (size_t)slots * BLOCK * sizeof(real);
             if (fs <= kMaxSmem && (size_t)slots * BLOCK * sizeof(real) <= 64 * 1024) {
                 BB_CUDA(cudaFuncSetAttribute((const void *)g.ks.pass2_fused,
@@ -452,7 +467,7 @@ template <typename real> ColArrays<real> Engine<real>::col_arrays() const {
 // ------------------------------------------------------------------ parameters
 template <typename real> void Engine<real>::init_params(uint64_t seed) {
     part_step_ = -1;
-    const PhiloxKey ikey = make_philox_key(seed);
+    const PhiloxKey ikey = philox_key(seed);
     auto run = [&](r2 *dst, const int *map, size_t n) {
         if (!n) return;
         init_params_kernel<real><<<cdiv(n, 256), 256, 0, stream_>>>(dst, map, (long long)n, L.D, ikey);
@@ -606,7 +621,7 @@ template <typename real> void Engine<real>::upload_supplied(const double *x, int
 // ------------------------------------------------------------------ the step pipeline
 template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
     if (!m.fuse) part_step_ = -1;     // anything but a fused step invalidates the pipelined partial sums
-    const PhiloxKey pkey = make_philox_key(seed_);
+    const PhiloxKey pkey = philox_key(seed_);
     const ColArrays<real> C = col_arrays();
     SupArgs<real> sup{};
     if (m.sup) {
@@ -804,7 +819,7 @@ template <typename real> void Engine<real>::elbo_grad(const double *eps, long lo
 }
 
 template <typename real> void Engine<real>::get_noise(long long step, double *eps) {
-    const PhiloxKey pkey = make_philox_key(seed_);
+    const PhiloxKey pkey = philox_key(seed_);
     const size_t n = (size_t)L.K * L.D;
     hostvec_a_.ensure(n);
     BB_CUDA(cudaMemsetAsync(hostvec_a_.p, 0, sizeof(double) * n, stream_));

@@ -26,9 +26,16 @@ namespace bb {
 #ifndef BB_P2_UNROLL
 #define BB_P2_UNROLL 1
 #endif
+#ifndef BB_FUSE_MIN_BLOCKS
+#define BB_FUSE_MIN_BLOCKS 3
+#endif
+#ifndef BB_FUSE_UNROLL
+#define BB_FUSE_UNROLL 1
+#endif
 
 constexpr int kP1Unroll = BB_P1_UNROLL;   // MC samples of pass 1 interleaved per thread (ILP)
 constexpr int kP2Unroll = BB_P2_UNROLL;
+constexpr int kFuseUnroll = BB_FUSE_UNROLL;   // sample loops of the fused step kernel
 
 template <int NT> struct TD { static constexpr int MAX = NT > 0 ? NT : MAX_NT_DYN; };
 template <int NE> struct ED { static constexpr int MAX = NE > 0 ? NE : MAX_NE_DYN; };
@@ -51,8 +58,8 @@ __device__ __forceinline__ int find_segment(const SegList &sl, int blk) {
 // eps for every latent of one column and one MC sample
 template <typename real, int MAXC, bool SUP>
 __device__ __forceinline__ void column_noise(real (&eps)[MAXC], int nclass, int nt, uint32_t colid, uint32_t k,
-                                             uint32_t step, const PhiloxKey &key, const SupArgs<real> &sup,
-                                             int c, int cpad, int tmax, int nj) {
+                                             uint32_t step, const PhiloxKey &key, const float2 *tab,
+                                             const SupArgs<real> &sup, int c, int cpad, int tmax, int nj) {
     if constexpr (SUP) {
 #pragma unroll
         for (int i = 0; i < MAXC; ++i) {
@@ -65,7 +72,7 @@ __device__ __forceinline__ void column_noise(real (&eps)[MAXC], int nclass, int 
         for (int q = 0; q < MAXC / 8; ++q) {
             if (q * 8 >= nclass) break;
             real n[8];
-            normals8<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k, step, key, n);
+            normals8<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k, step, key, tab, n);
 #pragma unroll
             for (int l = 0; l < 8; ++l) eps[8 * q + l] = n[l];
         }
@@ -89,16 +96,44 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// softplus(w) and its derivative sigmoid(w) from one ex2 (fp32: MUFU ex2 / lg2 / rcp; the
-// log1p is compensated -- log1p(x) = log(u) x / (u - 1), u = fl(1 + x) -- so small sigma keeps
-// full relative accuracy); fp64: libm.
+// fp32 kernels keep the Box-Muller direction table (bb_device.cuh) at the head of their dynamic shared
+// memory; the fp64 kernels use sincospi and reserve nothing.  stage() starts the copy as ONE cp.async group
+// (all loads in flight at once: the kernel start is pure latency); the caller waits for that group and
+// publishes it with a __syncthreads before the first draw.
+template <typename real> struct TrigTab {
+    static constexpr size_t BYTES = std::is_same<real, float>::value ? TRIG_N * sizeof(float2) : 0;
+    template <bool LOAD> static __device__ __forceinline__ const float2 *stage(unsigned char *smem, const PhiloxKey &key) {
+        if constexpr (BYTES == 0) return nullptr;
+        float2 *t = reinterpret_cast<float2 *>(smem);
+        if constexpr (LOAD) {
+#pragma unroll
+            for (int i = 0; i < TRIG_N / BLOCK; ++i)
+                cp_async<sizeof(float2)>(t + i * BLOCK + threadIdx.x, key.trig + i * BLOCK + threadIdx.x);
+        }
+        cp_async_commit();
+        return t;
+    }
+};
+
+// softplus(w) = max(w, 0) + log1p(e^{-|w|}) and its derivative sigmoid(w).  fp32: x = e^{-|w|} from one
+// MUFU ex2; log1p(x) is the alternating series to x^6 below x = 1/16 (truncation < 1e-8 relative, so a
+// small sigma keeps full relative accuracy) and ln2 * lg2(1 + x) above it -- two MUFU ops, and the
+// polynomial runs beside the lg2.  fp64: libm.
+__device__ __forceinline__ float softplus_f32(float w, float &x) {
+    x = fast_ex2(-fabsf(w) * 1.4426950408889634f);                  // e^{-|w|} in (0, 1]
+    const float big = 0.6931471805599453f * fast_lg2(1.0f + x);
+    float p = fmaf(x, -1.0f / 6.0f, 0.2f);
+    p = fmaf(x, p, -0.25f);
+    p = fmaf(x, p, 1.0f / 3.0f);
+    p = fmaf(x, p, -0.5f);
+    p = fmaf(x, p, 1.0f);
+    const float l1p = x < 0.0625f ? x * p : big;
+    return fmaxf(w, 0.0f) + l1p;
+}
 __device__ __forceinline__ void softplus_sigmoid(float w, float &sp, float &sgm) {
-    const float x = fast_ex2(-fabsf(w) * 1.4426950408889634f);      // e^{-|w|} in (0, 1]
-    const float u = 1.0f + x;
-    const float um1 = u - 1.0f;
-    const float l1p = um1 == 0.0f ? x : 0.6931471805599453f * fast_lg2(u) * x * fast_rcp(um1);
-    sp = fmaxf(w, 0.0f) + l1p;
-    const float ru = fast_rcp(u);
+    float x;
+    sp = softplus_f32(w, x);
+    const float ru = fast_rcp(1.0f + x);
     sgm = w >= 0.0f ? ru : x * ru;
 }
 __device__ __forceinline__ void softplus_sigmoid(double w, double &sp, double &sgm) {
@@ -112,6 +147,116 @@ template <typename real> __device__ __forceinline__ real softplus_only(real w) {
 }
 
 // ===================================================================== pass 1
+// Accumulator layout of one sample: `pva` rows of BLOCK reals.  Scalar layout: slot v of thread t at
+// v * BLOCK + t.  Pair layout (compile-time T, one environment): slots 2p, 2p+1 of thread t sit side by side
+// at (p * BLOCK + t) * 2, so a sample's read-modify-write is one 64/128-bit LDS + STS per pair.
+template <int NT, int NE> struct AccLayout {
+    static constexpr bool PAIRS = NT > 0 && NE == 1;
+    static __device__ __forceinline__ int rows(int pvs) { return PAIRS ? (pvs + 1) & ~1 : pvs; }
+};
+
+// Block reduction of the thread-private accumulators -> part[(k0 + k) * pv + v][block], in double and in a
+// fixed order (thread j*32 + lane ascending in j, then the lane butterfly).  Four rows per warp and
+// iteration keep four independent chains in flight: the kernel tail is pure latency.
+template <typename real, bool PAIRS>
+__device__ __forceinline__ void flush_rows(const real *sacc, int nk, int pvs, int pva, int k0, int pv, double *part) {
+    constexpr int NW = BLOCK / 32, U = 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nrow = nk * pvs;
+    for (int r0 = warp * U; r0 < nrow; r0 += NW * U) {
+        double s[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            s[u] = 0.0;
+            if (r0 + u < nrow) {
+                const int k = (r0 + u) / pvs, v = (r0 + u) - k * pvs;
+                const real *rp = sacc + (size_t)k * pva * BLOCK + (PAIRS ? (v >> 1) * 2 * BLOCK + (v & 1) : v * BLOCK);
+#pragma unroll
+                for (int j = 0; j < NW; ++j) s[u] += (double)rp[(j * 32 + lane) * (PAIRS ? 2 : 1)];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+        }
+        double val = s[0];
+#pragma unroll
+        for (int u = 1; u < U; ++u) val = lane == u ? s[u] : val;
+        const int row = r0 + lane;
+        if (lane < U && row < nrow)
+            part[((size_t)(k0 + row / pvs) * pv + row % pvs) * gridDim.x + blockIdx.x] = val;   // [k][v][block]: coalesced for the reducer
+    }
+}
+
+// One MC sample of one column for pass 1: z = mu + sigma eps and the column's contribution to every slot,
+// added into the thread-private accumulators `acc` (already offset to this sample and thread).
+// zth[e]: the hyper latent's draw (hierarchical models).
+template <typename real, int NT, int NE, bool HIER>
+__device__ __forceinline__ void pass1_sample(const real *eps, const real *mu, const real *sg, const real *mub,
+                                             const real *sgb, const real *zth, bool neutral, int nt, int ne,
+                                             const int *env_of_t, real *acc) {
+    using S = Shape<NT, NE, HIER>;
+    using r2 = vec2<real>;
+    constexpr bool PAIRS = AccLayout<NT, NE>::PAIRS;
+    constexpr int NV = PAIRS ? ((3 * NT - 2 + 1) & ~1) : 2;
+    real v[NV];
+    if constexpr (PAIRS) v[NV - 1] = real(0);        // pad slot of an odd population
+    auto add = [&](int slot, real x) {
+        if constexpr (PAIRS) v[slot] = x; else acc[slot * BLOCK] += x;
+    };
+    real z[S::MAXT];
+#pragma unroll
+    for (int t = 0; t < S::MAXT; ++t) {
+        if (t >= nt) break;
+        z[t] = fma(sg[t], eps[t], mu[t]);
+        add(t, bb_exp(z[t]));
+    }
+    if (neutral) {
+#pragma unroll
+        for (int t = 0; t < S::MAXT - 1; ++t) {
+            if (t >= nt - 1) break;
+            const real d = z[t + 1] - z[t];
+            add(nt + t, d);
+            add(2 * nt - 1 + t, d * d);
+        }
+    } else {
+        real zs[S::MAXE], w[S::MAXE];
+#pragma unroll
+        for (int e = 0; e < S::MAXE; ++e) {
+            if (e >= ne) break;
+            if constexpr (HIER) {
+                const real ztt = fma(sgb[3 * e], eps[nt + 3 * e], mub[3 * e]);
+                const real ztau = fma(sgb[3 * e + 1], eps[nt + 3 * e + 1], mub[3 * e + 1]);
+                zs[e] = fma(bb_exp(ztau), ztt, zth[e]);
+                w[e] = bb_exp(real(-2) * fma(sgb[3 * e + 2], eps[nt + 3 * e + 2], mub[3 * e + 2]));
+            } else {
+                zs[e] = fma(sgb[2 * e], eps[nt + 2 * e], mub[2 * e]);
+                w[e] = bb_exp(real(-2) * fma(sgb[2 * e + 1], eps[nt + 2 * e + 1], mub[2 * e + 1]));
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < S::MAXT - 1; ++t) {
+            if (t >= nt - 1) break;
+            const int e = NE == 1 ? 0 : env_of_t[t + 1];
+            add(nt + t, w[e] * (z[t + 1] - z[t] - zs[e]));
+            if (NE != 1) add(2 * nt - 1 + t, w[e]);
+        }
+        if (NE == 1) add(2 * nt - 1, w[0]);
+    }
+    if constexpr (PAIRS) {
+        r2 *a2 = reinterpret_cast<r2 *>(acc);
+        const int np = neutral ? (3 * NT - 1) / 2 : NT;
+#pragma unroll
+        for (int q = 0; q < NV / 2; ++q) {
+            if (q >= np) break;
+            r2 t2 = a2[q * BLOCK];
+            t2.x += v[2 * q]; t2.y += v[2 * q + 1];
+            a2[q * BLOCK] = t2;
+        }
+    }
+}
+
 // Slots per sample (pv = nt + 2 (nt-1)):
 //   [0, nt)              Lambda_t partial            (both populations)
 //   [nt, 2nt-1)          neutral: sum d_t            mutant: sum w (d_t - s)
@@ -121,7 +266,9 @@ template <typename real, int NT, int NE, bool HIER, bool SUP>
 __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
     using S = Shape<NT, NE, HIER>;
     using r2 = vec2<real>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    const float2 *strig = TrigTab<real>::template stage<!SUP>(smem_all, a.key);   // published by the first barrier below
+    unsigned char *smem_raw = smem_all + TrigTab<real>::BYTES;
     real *sacc = reinterpret_cast<real *>(smem_raw);
 
     const int tid = threadIdx.x;
@@ -139,7 +286,9 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
     // BLOCK reals) is sized by the host for the mutant population, the few neutral blocks sweep K in
     // smaller chunks instead of inflating every block's shared memory
     const int pvs = seg.neutral ? 3 * nt - 2 : (NE == 1 ? 2 * nt : 3 * nt - 2);
-    const int kchunk = max(1, min(a.K, a.acc_slots / pvs));
+    constexpr bool PAIRS = AccLayout<NT, NE>::PAIRS;
+    const int pva = AccLayout<NT, NE>::rows(pvs);
+    const int kchunk = max(1, min(a.K, a.acc_slots / pva));
     const size_t acc_bytes = (((size_t)a.acc_slots * BLOCK * sizeof(real)) + 15) / 16 * 16;
     r2 *stage = reinterpret_cast<r2 *>(smem_raw + acc_bytes);          // [2][nt + nj][BLOCK]
     const int stage_stride = (C.tmax + C.nj) * BLOCK;
@@ -165,9 +314,10 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
         cp_async_commit();
     };
 
+    cp_async_wait<0>();                 // the direction table; published by the first barrier below
     for (int kc0 = 0; kc0 < a.K; kc0 += kchunk) {
         const int kc1 = min(a.K, kc0 + kchunk);
-        for (int i = tid; i < (kc1 - kc0) * pvs * BLOCK; i += BLOCK) sacc[i] = real(0);
+        for (int i = tid; i < (kc1 - kc0) * pva * BLOCK; i += BLOCK) sacc[i] = real(0);
         __syncthreads();
 
         int buf = 0;
@@ -207,116 +357,46 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
 #pragma unroll kP1Unroll
             for (int k = kc0; k < kc1; ++k) {
                 real eps[S::MAXC];
-                column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key,
+                column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, strig,
                                                  a.sup, c, cpad, C.tmax, C.nj);
-                real *acc = sacc + (size_t)(k - kc0) * pvs * BLOCK + tid;
-                real z[S::MAXT];
+                real zth[S::MAXE];
+                if constexpr (HIER) {
+                    if (!seg.neutral) {
 #pragma unroll
-                for (int t = 0; t < S::MAXT; ++t) {
-                    if (t >= nt) break;
-                    z[t] = fma(sg[t], eps[t], mu[t]);
-                    acc[t * BLOCK] += bb_exp(z[t]);
-                }
-                if (seg.neutral) {
-#pragma unroll
-                    for (int t = 0; t < S::MAXT - 1; ++t) {
-                        if (t >= nt - 1) break;
-                        const real d = z[t + 1] - z[t];
-                        acc[(nt + t) * BLOCK] += d;
-                        acc[(2 * nt - 1 + t) * BLOCK] += d * d;
-                    }
-                } else {
-                    real zs[S::MAXE], w[S::MAXE];
-#pragma unroll
-                    for (int e = 0; e < S::MAXE; ++e) {
-                        if (e >= ne) break;
-                        if constexpr (HIER) {
-                            const real zth = a.hy_zeps[(size_t)k * a.H + hbase + e].x;
-                            const real ztt = fma(sgb[3 * e], eps[nt + 3 * e], mub[3 * e]);
-                            const real ztau = fma(sgb[3 * e + 1], eps[nt + 3 * e + 1], mub[3 * e + 1]);
-                            zs[e] = fma(bb_exp(ztau), ztt, zth);
-                            w[e] = bb_exp(real(-2) * fma(sgb[3 * e + 2], eps[nt + 3 * e + 2], mub[3 * e + 2]));
-                        } else {
-                            zs[e] = fma(sgb[2 * e], eps[nt + 2 * e], mub[2 * e]);
-                            w[e] = bb_exp(real(-2) * fma(sgb[2 * e + 1], eps[nt + 2 * e + 1], mub[2 * e + 1]));
+                        for (int e = 0; e < S::MAXE; ++e) {
+                            if (e >= ne) break;
+                            zth[e] = a.hy_zeps[(size_t)k * a.H + hbase + e].x;
                         }
                     }
-#pragma unroll
-                    for (int t = 0; t < S::MAXT - 1; ++t) {
-                        if (t >= nt - 1) break;
-                        const int e = NE == 1 ? 0 : a.env_of_t[t + 1];
-                        acc[(nt + t) * BLOCK] += w[e] * (z[t + 1] - z[t] - zs[e]);
-                        if (NE != 1) acc[(2 * nt - 1 + t) * BLOCK] += w[e];
-                    }
-                    if (NE == 1) acc[(2 * nt - 1) * BLOCK] += w[0];
                 }
+                pass1_sample<real, NT, NE, HIER>(eps, mu, sg, mub, sgb, zth, seg.neutral, nt, ne, a.env_of_t,
+                                                 sacc + (size_t)(k - kc0) * pva * BLOCK + (PAIRS ? 2 * tid : tid));
             }
         }
         cp_async_wait<0>();
         __syncthreads();
         // block reduction of the private columns, in double, fixed order
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int row = warp; row < (kc1 - kc0) * pvs; row += BLOCK / 32) {
-            double s = 0.0;
-#pragma unroll
-            for (int j = 0; j < BLOCK / 32; ++j) s += (double)sacc[(size_t)row * BLOCK + j * 32 + lane];
-            s = warp_sum<double>(s);
-            if (lane == 0) {
-                const int kl = row / pvs, v = row % pvs;
-                // [k][v][block]: the reducer reads consecutive blocks (coalesced)
-                a.part[((size_t)(kc0 + kl) * pv + v) * gridDim.x + blockIdx.x] = s;
-            }
-        }
+        flush_rows<real, PAIRS>(sacc, kc1 - kc0, pvs, pva, kc0, pv, a.part);
         __syncthreads();
     }
 }
 
-// Pass-1 accumulation of all K samples of one non-hierarchical column into the thread-private slots
-// `acc0[(k * pvs + slot) * BLOCK]` (same slot layout as pass1_kernel).  Used by the fused step kernel.
+// Pass-1 accumulation of samples [k0, k1) of one non-hierarchical column into the thread-private
+// accumulators `acc0` (offset to this thread, sample k0; same layout as pass1_kernel).  Used by the fused step kernel.
 template <typename real, int NT, int NE>
 __device__ __forceinline__ void pass1_column_direct(const real *mu, const real *sg, const real *mub, const real *sgb,
                                                     bool neutral, int nt, int ne, int k0, int k1, uint32_t colid,
-                                                    uint32_t step, const PhiloxKey &key, const int *env_of_t,
-                                                    real *acc0, int pvs) {
+                                                    uint32_t step, const PhiloxKey &key, const float2 *tab,
+                                                    const int *env_of_t, real *acc0, int pva) {
     using S = Shape<NT, NE, false>;
     const int nclass = neutral ? nt : nt + 2 * ne;
     const SupArgs<real> nosup{};
+#pragma unroll kFuseUnroll
     for (int k = k0; k < k1; ++k) {
         real eps[S::MAXC];
-        column_noise<real, S::MAXC, false>(eps, nclass, nt, colid, (uint32_t)k, step, key, nosup, 0, 0, 0, 0);
-        real *acc = acc0 + (size_t)(k - k0) * pvs * BLOCK;
-        real z[S::MAXT];
-#pragma unroll
-        for (int t = 0; t < S::MAXT; ++t) {
-            if (t >= nt) break;
-            z[t] = fma(sg[t], eps[t], mu[t]);
-            acc[t * BLOCK] += bb_exp(z[t]);
-        }
-        if (neutral) {
-#pragma unroll
-            for (int t = 0; t < S::MAXT - 1; ++t) {
-                if (t >= nt - 1) break;
-                const real d = z[t + 1] - z[t];
-                acc[(nt + t) * BLOCK] += d;
-                acc[(2 * nt - 1 + t) * BLOCK] += d * d;
-            }
-        } else {
-            real zs[S::MAXE], w[S::MAXE];
-#pragma unroll
-            for (int e = 0; e < S::MAXE; ++e) {
-                if (e >= ne) break;
-                zs[e] = fma(sgb[2 * e], eps[nt + 2 * e], mub[2 * e]);
-                w[e] = bb_exp(real(-2) * fma(sgb[2 * e + 1], eps[nt + 2 * e + 1], mub[2 * e + 1]));
-            }
-#pragma unroll
-            for (int t = 0; t < S::MAXT - 1; ++t) {
-                if (t >= nt - 1) break;
-                const int e = NE == 1 ? 0 : env_of_t[t + 1];
-                acc[(nt + t) * BLOCK] += w[e] * (z[t + 1] - z[t] - zs[e]);
-                if (NE != 1) acc[(2 * nt - 1 + t) * BLOCK] += w[e];
-            }
-            if (NE == 1) acc[(2 * nt - 1) * BLOCK] += w[0];
-        }
+        column_noise<real, S::MAXC, false>(eps, nclass, nt, colid, (uint32_t)k, step, key, tab, nosup, 0, 0, 0, 0);
+        pass1_sample<real, NT, NE, false>(eps, mu, sg, mub, sgb, nullptr, neutral, nt, ne, env_of_t,
+                                          acc0 + (size_t)(k - k0) * pva * BLOCK);
     }
 }
 
@@ -379,6 +459,75 @@ __device__ __forceinline__ void finish_latent_mode(const OptArgsT<real> &o, real
     }
 }
 
+// The same update for the `n` (<= N) latents of one class of a column, stage by stage over all of them: the
+// latents are independent, so their MUFU chains (ex2, rcp | sqrt x2 | rcp x2 | softplus of the new omega)
+// overlap instead of running one latent after the other.  Rows are strided: smem rows by BLOCK, global
+// rows by `cpad`; all pointers are already offset to this thread's column.  FUSE: returns the updated
+// mu / sigma in place for the next step's pass 1.
+template <typename real, int MODE, int N, bool FUSE>
+__device__ __forceinline__ void finish_batch(const OptArgsT<real> &o, real invK, int n, const real *sgrad,
+                                             const real *sgrade, real *mu, real *sigma, const vec2<real> *sth,
+                                             const vec2<real> *sac, const vec2<real> *srg, vec2<real> *g_th,
+                                             vec2<real> *g_acc, vec2<real> *g_ring, vec2<real> *g_out, size_t cpad) {
+    using r2 = vec2<real>;
+    if constexpr (MODE == 3) return;
+    r2 th[N], ac[N];
+    real g0[N], g1[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (i >= n) break;
+        th[i] = sth[i * BLOCK];
+        if constexpr (MODE < 2) ac[i] = sac ? sac[i * BLOCK] : g_acc[(size_t)i * cpad];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (i >= n) break;
+        // d ELBO / d mu = mean_k g ; d ELBO / d omega = (mean_k g eps + 1/sigma) sigmoid(omega), and
+        // sigmoid(w) = exp(w - softplus(w)): sigma is already at hand from the prologue
+        const real sgm = bb_exp(th[i].y - sigma[i]);
+        const real gm = sgrad[i] * invK;
+        const real go = (sgrade[i] * invK + bb_rcp(sigma[i])) * sgm;
+        g0[i] = -gm; g1[i] = -go;                       // the engine minimises -ELBO
+        if constexpr (MODE == 2) g_out[(size_t)i * cpad] = mk2<real>(gm, go);
+    }
+    if constexpr (MODE < 2) {
+        real d0[N], d1[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (i >= n) break;
+            const real q0 = g0[i] * g0[i], q1 = g1[i] * g1[i];
+            if constexpr (MODE == 0) {
+                ac[i].x = fma(o.post, ac[i].x, o.tau * q0);
+                ac[i].y = fma(o.post, ac[i].y, o.tau * q1);
+                d0[i] = bb_sqrt(ac[i].x) + real(1e-8);
+                d1[i] = bb_sqrt(ac[i].y) + real(1e-8);
+            } else {
+                const r2 rg = srg ? srg[i * BLOCK] : g_ring[(size_t)i * cpad];   // the ring slot evicted this step
+                ac[i].x = fmax(ac[i].x - rg.x + q0, real(0));
+                ac[i].y = fmax(ac[i].y - rg.y + q1, real(0));
+                g_ring[(size_t)i * cpad] = mk2<real>(q0, q1);
+                d0[i] = o.tau + bb_sqrt(ac[i].x) + real(1e-8);
+                d1[i] = o.tau + bb_sqrt(ac[i].y) + real(1e-8);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (i >= n) break;
+            th[i].x -= o.eta * g0[i] * bb_rcp(d0[i]);
+            th[i].y -= o.eta * g1[i] * bb_rcp(d1[i]);
+            g_th[(size_t)i * cpad] = th[i];
+            g_acc[(size_t)i * cpad] = ac[i];
+        }
+        if constexpr (FUSE) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                if (i >= n) break;
+                mu[i] = th[i].x; sigma[i] = softplus_only<real>(th[i].y);
+            }
+        }
+    }
+}
+
 template <typename real>
 __device__ __forceinline__ void finish_latent(const OptArgsT<real> &o, real invK, real sgrad, real sgrade,
                                               vec2<real> th, vec2<real> ac, vec2<real> *th_ptr,
@@ -402,13 +551,20 @@ __device__ __forceinline__ void finish_latent(const OptArgsT<real> &o, real invK
 // written exactly once per ADVI step (non-hierarchical models; the hyper latents of the hierarchical
 // ones are only known after every member column has been processed).
 template <typename real, int NT, int NE, bool HIER, bool SUP, bool ELBO, bool FUSE = false>
-__global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kernel(const P2Args<real> a) {
+__global__ void __launch_bounds__(BLOCK, FUSE ? BB_FUSE_MIN_BLOCKS : BB_P2_MIN_BLOCKS) pass2_kernel(const P2Args<real> a) {
     using S = Shape<NT, NE, HIER>;
     using r2 = vec2<real>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_all2[];
+    const float2 *strig = TrigTab<real>::template stage<!SUP>(smem_all2, a.key);   // published by the barrier after the ctx load
+    unsigned char *smem_raw = smem_all2 + TrigTab<real>::BYTES;
     real *sctx = reinterpret_cast<real *>(smem_raw);
-    const int ctx_n = a.K * 3 * a.tmax_ctx;
-    const size_t ctx_bytes = ((ctx_n * sizeof(real) + 15) / 16) * 16;
+    // per-sample context rows {c_t - sbar_t | (U_{t-1} - U_t) / Lambda_t | exp(-2 logsigma-bar_t)}: staged as
+    // [K][CS] with 16-byte rows so a sample's context is a few vector loads (compile-time T), not 3 T - 2 scalars
+    constexpr int VW = 16 / (int)sizeof(real);
+    const int TT = NT > 0 ? NT : a.tmax_ctx;
+    const int CS = ((3 * TT + VW - 1) / VW) * VW;
+    constexpr int CSC = NT > 0 ? ((3 * NT + VW - 1) / VW) * VW : VW;
+    const size_t ctx_bytes = (size_t)a.K * (((3 * a.tmax_ctx + VW - 1) / VW) * VW) * sizeof(real);
     double *sel = reinterpret_cast<double *>(smem_raw + ctx_bytes);
     const size_t sel_bytes = ELBO ? (size_t)(a.K + 1) * BLOCK * sizeof(double) : 0;
 
@@ -431,51 +587,100 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
     const size_t th_bytes = (size_t)rows * BLOCK * sizeof(r2);
     const size_t cn_bytes = (size_t)C.tmax * BLOCK * sizeof(int);
     // what is staged (host decides by the shared-memory budget): theta + counts always; accumulators,
-    // matrix priors and the evicted TruncatedADAGrad ring slot when they fit; one or two buffers
+    // matrix priors and the evicted TruncatedADAGrad ring slot when they fit.  What the sample loop reads
+    // (theta, priors, counts) is prefetched one tile ahead into one of `nbuf` buffers; what only the
+    // update epilogue reads (accumulators, ring slot) has ONE buffer, filled while the samples run.
     const int nac = a.stage_acc ? 1 : 0;
     const int npr = (a.stage_acc && a.stage_pr) ? 1 : 0;
     const int nrg = (a.stage_acc && a.stage_ring) ? 1 : 0;
-    const size_t buf_bytes = (1 + nac + npr + nrg) * th_bytes + cn_bytes;   // theta, [acc], [priors], [ring], counts
+    const size_t buf_bytes = (1 + npr) * th_bytes + cn_bytes;            // theta, [priors], counts
     const int nbuf = a.nbuf;
     unsigned char *stage0 = smem_raw + ctx_bytes + sel_bytes;
+    unsigned char *epi0 = stage0 + (size_t)nbuf * buf_bytes;             // [acc], [ring]
     // fused step: thread-private pass-1 accumulators behind the staging buffers, a.acc_slots rows of
     // BLOCK reals sized for the mutant population ([K][pvs]); mutant blocks accumulate inline right
     // after updating a column, the few neutral blocks (3 nt - 2 slots per sample) sweep their own
     // columns again in sample chunks once their updates are written
     const int pvs = seg.neutral ? 3 * nt - 2 : (NE == 1 ? 2 * nt : 3 * nt - 2);
-    real *facc = reinterpret_cast<real *>(stage0 + (size_t)nbuf * buf_bytes);
+    constexpr bool PAIRS = AccLayout<NT, NE>::PAIRS;
+    const int pva = AccLayout<NT, NE>::rows(pvs);
+    real *facc = reinterpret_cast<real *>(epi0 + (size_t)(nac + nrg) * th_bytes);
     if constexpr (FUSE)
         for (int i = tid; i < a.acc_slots * BLOCK; i += BLOCK) facc[i] = real(0);
 
+    // element offsets are 32-bit (t * cpad + c < 2^31: checked by the host), one IMAD.WIDE per address; the
+    // optional sets (matrix priors, ring slot) sit in their own uniformly-branched loops, not predicated
     auto prefetch = [&](int tile, int buf) {
         const int i = tile * BLOCK + tid;
         if (tile < ntile && i < seg.ncol) {
-            const int c = seg.col0 + i;
+            const uint32_t c = (uint32_t)(seg.col0 + i);
             unsigned char *base = stage0 + (size_t)buf * buf_bytes;
             r2 *sth = reinterpret_cast<r2 *>(base) + tid;
-            r2 *sac = reinterpret_cast<r2 *>(base + th_bytes) + tid;
-            r2 *spr = reinterpret_cast<r2 *>(base + (1 + nac) * th_bytes) + tid;
-            r2 *srg = reinterpret_cast<r2 *>(base + (1 + nac + npr) * th_bytes) + tid;
-            int *scn = reinterpret_cast<int *>(base + (1 + nac + npr + nrg) * th_bytes) + tid;
+            r2 *spr = reinterpret_cast<r2 *>(base + th_bytes) + tid;
+            int *scn = reinterpret_cast<int *>(base + (1 + npr) * th_bytes) + tid;
 #pragma unroll
             for (int t = 0; t < S::MAXT; ++t) {
                 if (t >= nt) break;
-                const size_t o = (size_t)t * cpad + c;
+                const uint32_t o = (uint32_t)t * (uint32_t)cpad + c;
                 cp_async<sizeof(r2)>(sth + t * BLOCK, C.lam_th + o);
-                if (nac) cp_async<sizeof(r2)>(sac + t * BLOCK, C.lam_acc + o);
                 cp_async<4>(scn + t * BLOCK, C.cnt + o);
-                if (lam_mat && npr) cp_async<sizeof(r2)>(spr + t * BLOCK, C.lam_pr + o);
-                if (nrg) cp_async<sizeof(r2)>(srg + t * BLOCK, C.lam_ring + o);
             }
             if (!seg.neutral) {
 #pragma unroll
                 for (int j = 0; j < S::MAXJ; ++j) {
                     if (j >= nj) break;
-                    const size_t o = (size_t)j * cpad + c;
-                    cp_async<sizeof(r2)>(sth + (nt + j) * BLOCK, C.bc_th + o);
-                    if (nac) cp_async<sizeof(r2)>(sac + (nt + j) * BLOCK, C.bc_acc + o);
-                    if (bc_mat && npr) cp_async<sizeof(r2)>(spr + (nt + j) * BLOCK, C.bc_pr + o);
-                    if (nrg) cp_async<sizeof(r2)>(srg + (nt + j) * BLOCK, C.bc_ring + o);
+                    cp_async<sizeof(r2)>(sth + (nt + j) * BLOCK, C.bc_th + ((uint32_t)j * (uint32_t)cpad + c));
+                }
+            }
+            if (npr) {
+                if (lam_mat) {
+#pragma unroll
+                    for (int t = 0; t < S::MAXT; ++t) {
+                        if (t >= nt) break;
+                        cp_async<sizeof(r2)>(spr + t * BLOCK, C.lam_pr + ((uint32_t)t * (uint32_t)cpad + c));
+                    }
+                }
+                if (bc_mat && !seg.neutral) {
+#pragma unroll
+                    for (int j = 0; j < S::MAXJ; ++j) {
+                        if (j >= nj) break;
+                        cp_async<sizeof(r2)>(spr + (nt + j) * BLOCK, C.bc_pr + ((uint32_t)j * (uint32_t)cpad + c));
+                    }
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    auto prefetch_epi = [&](int tile) {          // always commits a (possibly empty) group
+        const int i = tile * BLOCK + tid;
+        if (nac && i < seg.ncol) {
+            const uint32_t c = (uint32_t)(seg.col0 + i);
+            r2 *sac = reinterpret_cast<r2 *>(epi0) + tid;
+            r2 *srg = reinterpret_cast<r2 *>(epi0 + th_bytes) + tid;
+#pragma unroll
+            for (int t = 0; t < S::MAXT; ++t) {
+                if (t >= nt) break;
+                cp_async<sizeof(r2)>(sac + t * BLOCK, C.lam_acc + ((uint32_t)t * (uint32_t)cpad + c));
+            }
+            if (!seg.neutral) {
+#pragma unroll
+                for (int j = 0; j < S::MAXJ; ++j) {
+                    if (j >= nj) break;
+                    cp_async<sizeof(r2)>(sac + (nt + j) * BLOCK, C.bc_acc + ((uint32_t)j * (uint32_t)cpad + c));
+                }
+            }
+            if (nrg) {
+#pragma unroll
+                for (int t = 0; t < S::MAXT; ++t) {
+                    if (t >= nt) break;
+                    cp_async<sizeof(r2)>(srg + t * BLOCK, C.lam_ring + ((uint32_t)t * (uint32_t)cpad + c));
+                }
+                if (!seg.neutral) {
+#pragma unroll
+                    for (int j = 0; j < S::MAXJ; ++j) {
+                        if (j >= nj) break;
+                        cp_async<sizeof(r2)>(srg + (nt + j) * BLOCK, C.bc_ring + ((uint32_t)j * (uint32_t)cpad + c));
+                    }
                 }
             }
         }
@@ -483,9 +688,13 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
     };
 
     prefetch(blockIdx.x - seg.blk0, 0);
-    for (int i = tid; i < ctx_n; i += BLOCK) sctx[i] = a.ctx[(size_t)seg.rep * ctx_n + i];
+    for (int i = tid; i < a.K * 3 * TT; i += BLOCK) {
+        const int k = i / (3 * TT), r = i - k * 3 * TT, j = r / TT, t = r - j * TT;
+        sctx[k * CS + j * TT + t] = a.ctx[(((size_t)seg.rep * a.K + k) * 3 + j) * a.tmax_ctx + t];
+    }
     if (want_elbo)
         for (int k = 0; k <= a.K; ++k) sel[k * BLOCK + tid] = 0.0;
+    cp_async_wait<1>();                 // the direction table (the first tile may still be in flight)
     __syncthreads();
 
     // ratio terms per environment (the "-1" of d/dlog-sigma and the -log-sigma of the density)
@@ -497,18 +706,19 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
 
     int buf = 0;
     for (int tile = blockIdx.x - seg.blk0; tile < ntile; tile += nblk, buf ^= (nbuf - 1)) {
-        if (nbuf == 2) { prefetch(tile + nblk, buf ^ 1); cp_async_wait<1>(); }
-        else { if (tile != (int)blockIdx.x - seg.blk0) prefetch(tile, 0); cp_async_wait<0>(); }
+        // in flight, oldest first: {theta(tile)} -> + {acc(tile)} + {theta(next tile)}
+        if (nbuf == 2) { prefetch_epi(tile); prefetch(tile + nblk, buf ^ 1); cp_async_wait<2>(); }
+        else { if (tile != (int)blockIdx.x - seg.blk0) prefetch(tile, 0); prefetch_epi(tile); cp_async_wait<0>(); }
         const int i = tile * BLOCK + tid;
         if (i >= seg.ncol) continue;
         const int c = seg.col0 + i;
         const uint32_t colid = C.col_id ? C.col_id[c] : seg.colid0 + (uint32_t)i;
         unsigned char *base = stage0 + (size_t)buf * buf_bytes;
         const r2 *sth = reinterpret_cast<const r2 *>(base) + tid;
-        const r2 *sac = reinterpret_cast<const r2 *>(base + th_bytes) + tid;
-        const r2 *spr = reinterpret_cast<const r2 *>(base + (1 + nac) * th_bytes) + tid;
-        const r2 *srg = reinterpret_cast<const r2 *>(base + (1 + nac + npr) * th_bytes) + tid;
-        const int *scn = reinterpret_cast<const int *>(base + (1 + nac + npr + nrg) * th_bytes) + tid;
+        const r2 *spr = reinterpret_cast<const r2 *>(base + th_bytes) + tid;
+        const int *scn = reinterpret_cast<const int *>(base + (1 + npr) * th_bytes) + tid;
+        const r2 *sac = reinterpret_cast<const r2 *>(epi0) + tid;
+        const r2 *srg = reinterpret_cast<const r2 *>(epi0 + th_bytes) + tid;
 
         real mu[S::MAXT], sg[S::MAXT], sgr[S::MAXT], sge[S::MAXT], cnt[S::MAXT];
         double lsig_sum = 0.0;
@@ -546,14 +756,25 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
         // the K samples; instantiated twice so the common vector-prior case carries no per-latent prior loads
         auto sample_loop = [&](auto matpr_tag) {
         constexpr bool MATPR = decltype(matpr_tag)::value;
-#pragma unroll kP2Unroll
+#pragma unroll(FUSE ? kFuseUnroll : kP2Unroll)
         for (int k = 0; k < a.K; ++k) {
             real eps[S::MAXC];
-            column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, a.sup,
+            column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, strig, a.sup,
                                              c, cpad, C.tmax, C.nj);
-            const real *cE = sctx + (size_t)(k * 3 + 0) * a.tmax_ctx;   // c_t - sbar_t
-            const real *cG = sctx + (size_t)(k * 3 + 1) * a.tmax_ctx;   // (U_{t-1} - U_t) / Lambda_t
-            const real *cW = sctx + (size_t)(k * 3 + 2) * a.tmax_ctx;   // exp(-2 logsigma-bar_t)
+            const real *crow = sctx + (size_t)k * CS;
+            real cv[CSC];
+            if constexpr (NT > 0) {
+                using vw = typename std::conditional<std::is_same<real, float>::value, float4, double2>::type;
+#pragma unroll
+                for (int q = 0; q < CSC / VW; ++q) {
+                    const vw v = reinterpret_cast<const vw *>(crow)[q];
+                    if constexpr (VW == 4) { cv[4 * q] = v.x; cv[4 * q + 1] = v.y; cv[4 * q + 2] = v.z; cv[4 * q + 3] = v.w; }
+                    else { cv[2 * q] = v.x; cv[2 * q + 1] = v.y; }
+                }
+            }
+            auto cE = [&](int t) -> real { if constexpr (NT > 0) return cv[t]; else return crow[t]; };            // c_t - sbar_t
+            auto cG = [&](int t) -> real { if constexpr (NT > 0) return cv[NT + t]; else return crow[TT + t]; };  // (U_{t-1} - U_t) / Lambda_t
+            auto cW = [&](int t) -> real { if constexpr (NT > 0) return cv[2 * NT + t]; else return crow[2 * TT + t]; };   // exp(-2 logsigma-bar_t)
             real z[S::MAXT], g[S::MAXT];
             real lp = real(0);
 #pragma unroll
@@ -565,7 +786,7 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
                 if constexpr (MATPR) if (lam_mat) p = npr ? spr[t * BLOCK] : C.lam_pr[(size_t)t * cpad + c];
                 const real dz = z[t] - p.x;
                 // Poisson (collapsed Poisson x Multinomial) + logLambda coupling + Normal prior
-                g[t] = (cnt[t] - lam) + lam * cG[t] - dz * p.y;
+                g[t] = (cnt[t] - lam) + lam * cG(t) - dz * p.y;
                 if (want_elbo) lp += cnt[t] * z[t] - lam - real(0.5) * dz * dz * p.y;
             }
             if (seg.neutral) {
@@ -573,8 +794,8 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
 #pragma unroll
                 for (int t = 0; t < S::MAXT - 1; ++t) {
                     if (t >= nt - 1) break;
-                    const real res = z[t + 1] - z[t] - cE[t];
-                    const real u = cW[t] * res;
+                    const real res = z[t + 1] - z[t] - cE(t);
+                    const real u = cW(t) * res;
                     g[t] += u - uprev;
                     uprev = u;
                 }
@@ -608,7 +829,7 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
                 for (int t = 0; t < S::MAXT - 1; ++t) {
                     if (t >= nt - 1) break;
                     const int e = NE == 1 ? 0 : a.env_of_t[t + 1];
-                    const real res = z[t + 1] - z[t] - zs[e] - cE[t];
+                    const real res = z[t + 1] - z[t] - zs[e] - cE(t);
                     const real u = w[e] * res;
                     gs[e] += u;
                     gq[e] += u * res;
@@ -661,35 +882,20 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
         if (lam_mat || bc_mat) sample_loop(std::true_type{});
         else sample_loop(std::false_type{});
         if (want_elbo) sel[a.K * BLOCK + tid] += lsig_sum;
+        if (nbuf == 2) cp_async_wait<1>();      // this tile's accumulators (the next tile's theta may still fly)
 
         // fused optimiser update of every latent of the column (theta / accumulators re-read from the
         // stage); the mode is kernel-uniform, so branch once around straight-line per-latent code
         auto finish_all = [&](auto mode_tag) {
             constexpr int MODE = decltype(mode_tag)::value;
-#pragma unroll
-            for (int t = 0; t < S::MAXT; ++t) {
-                if (t >= nt) break;
-                const size_t o = (size_t)t * cpad + c;
-                const r2 ac = MODE >= 2 ? mk2<real>(0, 0) : (nac ? sac[t * BLOCK] : C.lam_acc[o]);
-                const r2 rg = MODE != 1 ? mk2<real>(0, 0) : (nrg ? srg[t * BLOCK] : C.lam_ring[o]);
-                r2 th = sth[t * BLOCK];
-                finish_latent_mode<real, MODE>(a.opt, invK, sgr[t], sge[t], sg[t], th, ac, rg, C.lam_th + o,
-                                               C.lam_acc + o, C.lam_ring + o, a.gout_lam + o);
-                if constexpr (FUSE) { mu[t] = th.x; sg[t] = softplus_only<real>(th.y); }
-            }
-            if (!seg.neutral) {
-#pragma unroll
-                for (int j = 0; j < S::MAXJ; ++j) {
-                    if (j >= nj) break;
-                    const size_t o = (size_t)j * cpad + c;
-                    const r2 ac = MODE >= 2 ? mk2<real>(0, 0) : (nac ? sac[(nt + j) * BLOCK] : C.bc_acc[o]);
-                    const r2 rg = MODE != 1 ? mk2<real>(0, 0) : (nrg ? srg[(nt + j) * BLOCK] : C.bc_ring[o]);
-                    r2 th = sth[(nt + j) * BLOCK];
-                    finish_latent_mode<real, MODE>(a.opt, invK, sgrb[j], sgeb[j], sgb[j], th, ac, rg,
-                                                   C.bc_th + o, C.bc_acc + o, C.bc_ring + o, a.gout_bc + o);
-                    if constexpr (FUSE) { mub[j] = th.x; sgb[j] = softplus_only<real>(th.y); }
-                }
-            }
+            finish_batch<real, MODE, S::MAXT, FUSE>(a.opt, invK, nt, sgr, sge, mu, sg, sth, nac ? sac : nullptr,
+                                                    nrg ? srg : nullptr, C.lam_th + c, C.lam_acc + c,
+                                                    C.lam_ring + c, a.gout_lam + c, (size_t)cpad);
+            if (!seg.neutral)
+                finish_batch<real, MODE, S::MAXJ, FUSE>(a.opt, invK, nj, sgrb, sgeb, mub, sgb, sth + nt * BLOCK,
+                                                        nac ? sac + nt * BLOCK : nullptr,
+                                                        nrg ? srg + nt * BLOCK : nullptr, C.bc_th + c, C.bc_acc + c,
+                                                        C.bc_ring + c, a.gout_bc + c, (size_t)cpad);
         };
         if (a.opt.update) {
             if (a.opt.kind == 1) finish_all(std::integral_constant<int, 0>{});
@@ -709,31 +915,23 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
         if constexpr (FUSE && !HIER)
             if (!seg.neutral)
                 pass1_column_direct<real, NT, NE>(mu, sg, mub, sgb, false, nt, ne, 0, a.K, colid, a.step + 1, a.key,
-                                                  a.env_of_t, facc + tid, pvs);
+                                                  strig, a.env_of_t, facc + (PAIRS ? 2 * tid : tid), pva);
     }
     cp_async_wait<0>();
     if constexpr (FUSE && !HIER) {
-        const int warp = tid >> 5, lane = tid & 31;
         auto flush = [&](int k0, int k1) {          // block reduction of the private columns -> part
             __syncthreads();
-            for (int row = warp; row < (k1 - k0) * pvs; row += BLOCK / 32) {
-                double s = 0.0;
-#pragma unroll
-                for (int j = 0; j < BLOCK / 32; ++j) s += (double)facc[(size_t)row * BLOCK + j * 32 + lane];
-                s = warp_sum<double>(s);
-                if (lane == 0)
-                    a.part[((size_t)(k0 + row / pvs) * a.pv + row % pvs) * gridDim.x + blockIdx.x] = s;
-            }
+            flush_rows<real, PAIRS>(facc, k1 - k0, pvs, pva, k0, a.pv, a.part);
             __syncthreads();
         };
         if (!seg.neutral) {
             flush(0, a.K);
         } else {
-            const int kchunk = max(1, min(a.K, a.acc_slots / pvs));
+            const int kchunk = max(1, min(a.K, a.acc_slots / pva));
             for (int kc0 = 0; kc0 < a.K; kc0 += kchunk) {
                 const int kc1 = min(a.K, kc0 + kchunk);
                 if (kc0 > 0) {
-                    for (int i = tid; i < (kc1 - kc0) * pvs * BLOCK; i += BLOCK) facc[i] = real(0);
+                    for (int i = tid; i < (kc1 - kc0) * pva * BLOCK; i += BLOCK) facc[i] = real(0);
                     __syncthreads();
                 }
                 for (int tile = blockIdx.x - seg.blk0; tile < ntile; tile += nblk) {
@@ -749,7 +947,7 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? 4 : BB_P2_MIN_BLOCKS) pass2_kern
                         mu[t] = th.x; sg[t] = softplus_only<real>(th.y);
                     }
                     pass1_column_direct<real, NT, NE>(mu, sg, mu, sg, true, nt, ne, kc0, kc1, colid, a.step + 1,
-                                                      a.key, a.env_of_t, facc + tid, pvs);
+                                                      a.key, strig, a.env_of_t, facc + (PAIRS ? 2 * tid : tid), pva);
                 }
                 flush(kc0, kc1);
             }

@@ -199,6 +199,9 @@ void build_layout(const bb_desc &d, Layout &L) {
             col += (n + 31) / 32 * 32;
         }
     L.cpad = std::max(col, 32);
+    // the kernels address latents with 32-bit element offsets (row * cpad + column)
+    if ((long long)std::max(L.tmax, L.nj) * L.cpad >= (1LL << 31))
+        throw std::runtime_error("problem too large for one device: (time points x columns) must stay below 2^31 per shard");
 
     // ---- maps, counts, ids
     L.map_lam.assign((size_t)L.tmax * L.cpad, -1);
