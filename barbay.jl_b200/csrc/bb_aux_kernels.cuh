@@ -21,7 +21,7 @@ struct ReduceArgs {
 };
 
 // one warp per output (r, k, q, t): fixed-order sum over the CTAs of the matching segments
-static __global__ void __launch_bounds__(128) reduce_kernel(const ReduceArgs a, int R) {
+__device__ __forceinline__ void reduce_rows(const ReduceArgs &a, int R) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nout = R * a.K * NQ * a.tmax;
     if (warp >= nout) return;
@@ -44,6 +44,7 @@ static __global__ void __launch_bounds__(128) reduce_kernel(const ReduceArgs a, 
     s = warp_sum<double>(s);
     if (lane == 0) a.sums[((size_t)(r * a.K + k) * NQ + q) * a.tmax + t] = s;
 }
+static __global__ void __launch_bounds__(128) reduce_kernel(const ReduceArgs a, int R) { reduce_rows(a, R); }
 
 // ------------------------------------------------------------------ peer-memory exchange of the step's sums
 // One-shot all-reduce over NVLink peer memory (one process per GPU, buffers shared through CUDA IPC):
@@ -137,16 +138,18 @@ __device__ __forceinline__ double softplus_d(double w) { return fmax(w, 0.0) + l
 //   phase 1  (r, k, t<T-1) c_t, residual sums u_t, per-sample gradients, ctx -> scratch
 //   phase 2  (r, k, t<T)   G_Lambda_t = (u_{t-1} - u_t) / Lambda_t           -> ctx
 //   phase 3  (i)           mean over samples, optimiser update (or emit)
+// `sums`: where the (all-reduced) totals are / will be; `scratch`: working arrays (global, or shared memory
+// in the merged tail kernel)
 template <typename real>
-__global__ void __launch_bounds__(256) shared_kernel(const SharedArgs<real> a) {
+__device__ __forceinline__ void shared_body(const SharedArgs<real> &a, double *sums, double *scratch) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int n2 = 2 * a.nst;
-    double *eps_t = a.scratch + (size_t)a.K * n2;            // [K][n2] eps
+    double *eps_t = scratch + (size_t)a.K * n2;              // [K][n2] eps
     double *z_t = eps_t + (size_t)a.K * n2;                  // [K][n2] z
     double *u_t = z_t + (size_t)a.K * n2;                    // [R][K][tmax] sum_all w res
     double *lp_t = u_t + (size_t)a.R * a.K * a.tmax;         // [R][K][tmax] log-density pieces
     double *lsig_t = lp_t + (size_t)a.R * a.K * a.tmax;      // [n2] log sigma before the update
-    xchg_wait_and_sum(a.xchg, a.sums);                       // multi-GPU: complete the sums over NVLink peer memory
+    xchg_wait_and_sum(a.xchg, sums);                       // multi-GPU: complete the sums over NVLink peer memory
     // ---- phase 0
     for (int j = tid; j < a.K * n2; j += nthr) {
         const int k = j / n2, i = j % n2;
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(256) shared_kernel(const SharedArgs<real> a) {
         u_t[j] = 0.0; lp_t[j] = 0.0;
         if (t >= nt - 1) continue;
         const int is = a.sh0[r] + t, il = a.nst + a.sh0[r] + t;
-        const double *S = a.sums + (size_t)(r * a.K + k) * NQ * a.tmax;
+        const double *S = sums + (size_t)(r * a.K + k) * NQ * a.tmax;
         real *ctx = a.ctx + (size_t)(r * a.K + k) * 3 * a.tmax;
         const double zs = z_t[(size_t)k * n2 + is], zl = z_t[(size_t)k * n2 + il];   // s-bar_t, log-sigma-bar_t
         const double c = log(S[Q_LAM * a.tmax + t + 1]) - log(S[Q_LAM * a.tmax + t]);
@@ -177,8 +180,8 @@ __global__ void __launch_bounds__(256) shared_kernel(const SharedArgs<real> a) {
         const double qn = d2n + 2.0 * av * dn + a.n_neutral * av * av;   // sum_neutral res^2
         const double u = wbar * (dn + a.n_neutral * av) + (am + av * wm);   // sum_all w res
         const double2 ps = a.sh_pr[is], pl = a.sh_pr[il];
-        a.scratch[(size_t)k * n2 + is] = -u - (zs - ps.x) * ps.y;
-        a.scratch[(size_t)k * n2 + il] = wbar * qn - a.n_neutral - (zl - pl.x) * pl.y;
+        scratch[(size_t)k * n2 + is] = -u - (zs - ps.x) * ps.y;
+        scratch[(size_t)k * n2 + il] = wbar * qn - a.n_neutral - (zl - pl.x) * pl.y;
         u_t[j] = u;
         lp_t[j] = -a.n_neutral * zl - 0.5 * wbar * qn - 0.5 * (zs - ps.x) * (zs - ps.x) * ps.y -
                   0.5 * (zl - pl.x) * (zl - pl.x) * pl.y;
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(256) shared_kernel(const SharedArgs<real> a) {
     for (int j = tid; j < a.R * a.K * a.tmax; j += nthr) {
         const int t = j % a.tmax, k = (j / a.tmax) % a.K, r = j / (a.tmax * a.K);
         if (t >= a.nt[r]) continue;
-        const double *S = a.sums + (size_t)(r * a.K + k) * NQ * a.tmax;
+        const double *S = sums + (size_t)(r * a.K + k) * NQ * a.tmax;
         const double uprev = t > 0 ? u_t[j - 1] : 0.0;
         a.ctx[(size_t)(r * a.K + k) * 3 * a.tmax + 1 * a.tmax + t] = (real)((uprev - u_t[j]) / S[Q_LAM * a.tmax + t]);
     }
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(256) shared_kernel(const SharedArgs<real> a) {
         const double sigma = softplus_d(th.y);
         double sg = 0.0, sge = 0.0;
         for (int k = 0; k < a.K; ++k) {
-            const double g = a.scratch[(size_t)k * n2 + i];
+            const double g = scratch[(size_t)k * n2 + i];
             sg += g; sge += g * eps_t[(size_t)k * n2 + i];
             if (a.dump) a.dump[(size_t)k * n2 + i] = g;
         }
@@ -233,6 +236,54 @@ __global__ void __launch_bounds__(256) shared_kernel(const SharedArgs<real> a) {
             a.elbo_sh[k] = a.leader ? s : 0.0;
         }
     }
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256) shared_kernel(const SharedArgs<real> a) {
+    shared_body<real>(a, a.sums, a.scratch);
+}
+
+// ------------------------------------------------------------------ merged step tail
+// reduce (+ peer post) + shared latents in ONE launch: every CTA reduces its share of the partial sums;
+// the CTA that finishes last (ticket) posts them to the peers (multi-GPU) and runs the shared-latent
+// phases with its working arrays in shared memory.  Saves two launch boundaries per step and the
+// global-memory round trips between the phases; the arithmetic and its order are those of
+// reduce_kernel / xchg_post_kernel / shared_kernel, so the results are bitwise the same.
+template <typename real>
+__global__ void __launch_bounds__(256) tail_kernel(const ReduceArgs ra, int R, const XchgPostArgs xp,
+                                                   const SharedArgs<real> sa, unsigned *ticket, int nsums) {
+    extern __shared__ double tail_smem[];        // [nsums] totals | scratch
+    __shared__ int is_last;
+    asm volatile("griddepcontrol.launch_dependents;");      // let the next column kernel start its prologue
+    reduce_rows(ra, R);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        is_last = t == gridDim.x - 1 ? 1 : 0;
+        if (is_last) *ticket = 0u;               // ready for the next launch (stream order)
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double *tot = tail_smem, *scratch = tail_smem + nsums;
+    if (sa.xchg.buf) {
+        // multi-GPU: this rank's sums go to every peer, the totals come back inside shared_body
+        for (int r = 0; r < xp.world; ++r) {
+            double *dst = xp.peer_buf[r] + (size_t)(xp.parity * xp.world + xp.rank) * xp.P;
+            for (int i = threadIdx.x; i < xp.P; i += blockDim.x) dst[i] = __ldcg(ra.sums + i);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < xp.world) {
+            volatile unsigned long long *f = xp.peer_flag[threadIdx.x] + (xp.parity * xp.world + xp.rank);
+            *f = xp.seq;
+        }
+    } else {
+        for (int i = threadIdx.x; i < nsums; i += blockDim.x) tot[i] = __ldcg(ra.sums + i);
+        __syncthreads();
+    }
+    shared_body<real>(sa, tot, scratch);
 }
 
 // ------------------------------------------------------------------ hyper latents (theta of the hierarchical models)

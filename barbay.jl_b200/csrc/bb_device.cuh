@@ -63,14 +63,14 @@ __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ft
 // angle, so the pair is exactly uncorrelated with exact second and fourth moments; one Philox4x32-10
 // call therefore yields eight standard normals.  Identical definition in fp32 and fp64.
 // fp32: the 2048 directions (cos, sin)(2 pi (a + 0.5) / 2048) come from a table instead of two MUFU ops
-// (the XU pipe is the scarce one in the column kernels): TRIG_N = 1024 correctly rounded entries cover
-// the half turn a & 1023, bit 10 of the word flips the sign of the radius.  `tab` is the table -- the
+// (the XU pipe is the scarce one in the column kernels): TRIG_N = 1024 entries sqrt(2 ln 2) (cos, sin),
+// rounded once from double, cover the half turn a & 1023; bit 10 of the word flips the sign of the radius.  `tab` is the table -- the
 // column kernels pass their shared-memory copy, everything else the global one of the key.
 constexpr int TRIG_N = 1024;
 __device__ __forceinline__ void box_muller(uint32_t x, float &n0, float &n1, const float2 *tab) {
     // j = x >> 11 dropped into the mantissa of 4.0f by one funnel shift: 4 + j 2^-21, minus (4 - 2^-22) -> (j + 0.5) / 2^21, exact
     const float u = __uint_as_float(__funnelshift_r(x, 0x204u, 11)) - 3.9999997615814208984375f;
-    const float radius = fast_sqrt(-1.3862943611198906f * fast_lg2(u));   // sqrt(-2 ln u)
+    const float radius = fast_sqrt(-fast_lg2(u));   // sqrt(-2 ln u) / sqrt(2 ln 2): the table carries the factor
     const float rs = __uint_as_float(__float_as_uint(radius) | ((x << 21) & 0x80000000u));
     const float2 d = tab[x & (TRIG_N - 1)];
     n0 = rs * d.x; n1 = rs * d.y;
@@ -100,12 +100,14 @@ __device__ __forceinline__ void normals8(uint32_t c0, uint32_t c1, uint32_t c2, 
 template <typename real>
 __device__ __forceinline__ real stream_normal(uint32_t stream, uint32_t i, uint32_t k, uint32_t step,
                                               const PhiloxKey &key) {
-    real n[8];
-    normals8<real>(i >> 3, stream << 24, k, step, key, key.trig, n);
-    real r = n[0];
-#pragma unroll
-    for (int l = 1; l < 8; ++l) r = (i & 7u) == (uint32_t)l ? n[l] : r;
-    return r;
+    // lane i & 7 of normals8(i >> 3, ...): only its own word goes through Box-Muller
+    uint32_t x[4];
+    philox4x32_10(i >> 3, stream << 24, k, step, key, x);
+    const uint32_t w = (i >> 1) & 3u;
+    const uint32_t xw = w == 0 ? x[0] : w == 1 ? x[1] : w == 2 ? x[2] : x[3];
+    real n0, n1;
+    box_muller(xw, n0, n1, key.trig);
+    return (i & 1u) ? n1 : n0;
 }
 
 // ---------------------------------------------------------------- scalar math

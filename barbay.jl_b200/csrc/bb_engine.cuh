@@ -202,6 +202,7 @@ template <typename real> class Engine : public EngineBase {
     DBuf<double2> sh_th_, sh_acc_, sh_ring_, sh_pr_, sh_gout_;
     DBuf<r2> lam_pr_, bc_pr_, hy_pr_;
     DBuf<int> cnt_, map_lam_, map_bc_, map_hy_, map_sh_, hgroup_, csr_off_, csr_mem_;
+    DBuf<unsigned> ticket_;    // arrival counter of the merged tail kernel (zero between launches)
     DBuf<float2> trig_;        // Box-Muller direction table of the fp32 noise lattice (bb_device.cuh)
     PhiloxKey philox_key(uint64_t seed) const { PhiloxKey k = make_philox_key(seed); k.trig = trig_.p; return k; }
     DBuf<uint32_t> col_id_;
@@ -246,13 +247,16 @@ template <typename real> Engine<real>::Engine(const bb_desc &d) {
     for (auto &e : ev_) BB_CUDA(cudaEventCreate(&e));
 
     {
-        // directions (cos, sin)(2 pi (a + 0.5) / 2048), a < TRIG_N, correctly rounded to fp32
+        // directions sqrt(2 ln 2) (cos, sin)(2 pi (a + 0.5) / 2048), a < TRIG_N, rounded once to fp32
+        // (the kernel's radius is sqrt(-log2 u); the factor turns it into sqrt(-2 ln u))
         std::vector<float2> t(TRIG_N);
+        const double scale = std::sqrt(2.0 * std::log(2.0));
         for (int a = 0; a < TRIG_N; ++a) {
             const double ang = 6.283185307179586476925286766559 * ((double)a + 0.5) / 2048.0;
-            t[a] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+            t[a] = make_float2((float)(scale * std::cos(ang)), (float)(scale * std::sin(ang)));
         }
         trig_.upload(t);
+        ticket_.alloc(1);
     }
     const size_t nlam = (size_t)L.tmax * L.cpad, nbc = (size_t)L.nj * L.cpad;
     lam_th_.alloc(nlam); lam_acc_.alloc(nlam);
@@ -648,6 +652,12 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
     }
     // ---- pass 1
     if (tev_pos_ >= 0) BB_CUDA(cudaEventRecord(tev_[tev_pos_++], stream_));
+    // one launch group and no NCCL collective in between: reduce + peer post + shared latents run as ONE
+    // kernel with its working arrays in shared memory (tail_kernel); otherwise the separate kernels
+    const int nwarps = L.R * L.K * NQ * L.tmax;
+    const size_t tail_smem = (sums_.n + sh_scratch_.n) * sizeof(double);
+    const bool use_tail = groups_.size() == 1 && !(comm_ && !xchg_on_) && tail_smem <= 40 * 1024 && !getenv("BB_NO_TAIL");
+    ReduceArgs ra{};
     for (Group &g : groups_) {
         // partial sums of this step: from the previous fused kernel (its grid / segment split), or pass 1 now
         double *gpart = part_.p + (size_t)(m.have_part ? g.epart_off : g.part_off) * L.K * (3 * L.tmax);
@@ -663,27 +673,30 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
             ++launches;
         }
         if (tev_pos_ >= 0 && &g == &groups_.back()) BB_CUDA(cudaEventRecord(tev_[tev_pos_++], stream_));
-        ReduceArgs ra{};
+        ra = ReduceArgs{};
         ra.segs = m.have_part ? g.p2segs : g.p1segs; ra.K = L.K; ra.tmax = L.tmax; ra.pv = g.pv; ra.nt = g.nt;
         ra.w_single = L.E == 1 ? 1 : 0; ra.rep_mask = g.rep_mask; ra.nblk = m.have_part ? g.p2blocks : g.p1blocks;
         ra.part = gpart; ra.sums = sums_.p;
-        const int nwarps = L.R * L.K * NQ * L.tmax;
-        reduce_kernel<<<cdiv((long long)nwarps * 32, 128), 128, 0, stream_>>>(ra, L.R);
-        ++launches;
+        if (!use_tail) {
+            reduce_kernel<<<cdiv((long long)nwarps * 32, 128), 128, 0, stream_>>>(ra, L.R);
+            ++launches;
+        }
     }
     XchgWaitArgs xw{};
+    XchgPostArgs xp{};
     if (comm_ && xchg_on_) {
         // one-shot all-reduce over NVLink peer memory, completed inside shared_kernel
         ++xchg_seq_;
-        XchgPostArgs xp{};
         xp.sums = sums_.p; xp.P = (int)sums_.n; xp.world = L.world; xp.rank = L.rank;
         xp.parity = (int)(xchg_seq_ & 1ull); xp.seq = xchg_seq_;
         for (int r = 0; r < L.world; ++r) {
             xp.peer_buf[r] = reinterpret_cast<double *>(xchg_peer_mem_[r]);
             xp.peer_flag[r] = reinterpret_cast<unsigned long long *>(static_cast<char *>(xchg_peer_mem_[r]) + xchg_flag_off_);
         }
-        xchg_post_kernel<<<1, 256, 0, stream_>>>(xp);
-        ++launches;
+        if (!use_tail) {
+            xchg_post_kernel<<<1, 256, 0, stream_>>>(xp);
+            ++launches;
+        }
         xw.buf = reinterpret_cast<const double *>(xchg_mem_);
         xw.flag = reinterpret_cast<const unsigned long long *>(static_cast<char *>(xchg_mem_) + xchg_flag_off_);
         xw.P = (int)sums_.n; xw.world = L.world; xw.parity = xp.parity; xw.seq = xchg_seq_; xw.err = xchg_err_.p;
@@ -707,7 +720,11 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         sa.elbo_sh = m.want_elbo ? elbo_sh_.p : nullptr;
         sa.opt = opt_args<double>(m.update);
         sa.leader = L.rank == 0 ? 1 : 0;
-        shared_kernel<real><<<1, 256, 0, stream_>>>(sa);
+        if (use_tail)
+            tail_kernel<real><<<cdiv((long long)nwarps * 32, 256), 256, tail_smem, stream_>>>(ra, L.R, xp, sa, ticket_.p,
+                                                                                             (int)sums_.n);
+        else
+            shared_kernel<real><<<1, 256, 0, stream_>>>(sa);
         ++launches;
     }
     // ---- pass 2
@@ -734,7 +751,16 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
             // the reducer has consumed this step's partials (stream order): the fused kernel overwrites them
             a.part = part_.p + (size_t)g.epart_off * L.K * (3 * L.tmax);
             a.pv = g.pv; a.acc_slots = g.facc_slots;
-            g.ks.pass2_fused<<<g.p2blocks, BLOCK, g.fsmem, stream_>>>(a);
+            // programmatic dependent launch: the CTAs become resident while the tail kernel is still running and
+            // do everything that does not need its output (direction table, accumulator zeroing, first tile)
+            // before griddepcontrol.wait
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(g.p2blocks); cfg.blockDim = dim3(BLOCK); cfg.dynamicSmemBytes = g.fsmem; cfg.stream = stream_;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = getenv("BB_NO_PDL") ? 0 : 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            BB_CUDA(cudaLaunchKernelEx(&cfg, g.ks.pass2_fused, a));
         } else {
             const KernelSet<real> &ks = m.sup ? g.ks_sup : g.ks;
             if (elbo) ks.pass2_elbo<<<g.p2blocks, BLOCK, g.p2smem_elbo, stream_>>>(a);

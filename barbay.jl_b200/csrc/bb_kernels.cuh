@@ -156,36 +156,55 @@ template <int NT, int NE> struct AccLayout {
 };
 
 // Block reduction of the thread-private accumulators -> part[(k0 + k) * pv + v][block], in double and in a
-// fixed order (thread j*32 + lane ascending in j, then the lane butterfly).  Four rows per warp and
-// iteration keep four independent chains in flight: the kernel tail is pure latency.
+// fixed order.  A warp owns whole samples (k = warp, warp + 4, ...) and reduces four slots at a time with
+// a transposed butterfly: after the xor-16 and xor-8 exchanges every lane carries ONE of the four rows
+// (row = lane >> 3 of its octet class), so the four 32-lane sums cost 6 double shuffles instead of 20.
+// The kernel tail is pure latency: no divisions, few instructions.
 template <typename real, bool PAIRS>
 __device__ __forceinline__ void flush_rows(const real *sacc, int nk, int pvs, int pva, int k0, int pv, double *part) {
-    constexpr int NW = BLOCK / 32, U = 4;
+    using r2 = vec2<real>;
+    constexpr int NW = BLOCK / 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nrow = nk * pvs;
-    for (int r0 = warp * U; r0 < nrow; r0 += NW * U) {
-        double s[U];
+    const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+    for (int k = warp; k < nk; k += NW) {
+        const real *base = sacc + (size_t)k * pva * BLOCK;
+        for (int v0 = 0; v0 < pvs; v0 += 4) {
+            double s[4] = {0.0, 0.0, 0.0, 0.0};
+            if constexpr (PAIRS) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            s[u] = 0.0;
-            if (r0 + u < nrow) {
-                const int k = (r0 + u) / pvs, v = (r0 + u) - k * pvs;
-                const real *rp = sacc + (size_t)k * pva * BLOCK + (PAIRS ? (v >> 1) * 2 * BLOCK + (v & 1) : v * BLOCK);
+                for (int q = 0; q < 2; ++q) {
+                    if (v0 + 2 * q < pvs) {
+                        const r2 *rp = reinterpret_cast<const r2 *>(base) + (size_t)((v0 >> 1) + q) * BLOCK;
 #pragma unroll
-                for (int j = 0; j < NW; ++j) s[u] += (double)rp[(j * 32 + lane) * (PAIRS ? 2 : 1)];
+                        for (int j = 0; j < NW; ++j) {
+                            const r2 t = rp[j * 32 + lane];
+                            s[2 * q] += (double)t.x; s[2 * q + 1] += (double)t.y;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (v0 + u < pvs) {
+                        const real *rp = base + (size_t)(v0 + u) * BLOCK;
+#pragma unroll
+                        for (int j = 0; j < NW; ++j) s[u] += (double)rp[j * 32 + lane];
+                    }
+                }
             }
+            // rows {0,1} stay in lanes 0-15, rows {2,3} in lanes 16-31; then row parity by bit 3
+            double ka = hi16 ? s[2] : s[0], kb = hi16 ? s[3] : s[1];
+            ka += __shfl_xor_sync(0xffffffffu, hi16 ? s[0] : s[2], 16);
+            kb += __shfl_xor_sync(0xffffffffu, hi16 ? s[1] : s[3], 16);
+            double kk = hi8 ? kb : ka;
+            kk += __shfl_xor_sync(0xffffffffu, hi8 ? ka : kb, 8);
+            kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+            kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+            kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+            const int v = v0 + (lane >> 3);
+            if ((lane & 7) == 0 && v < pvs)
+                part[((size_t)(k0 + k) * pv + v) * gridDim.x + blockIdx.x] = kk;   // [k][v][block]: coalesced for the reducer
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
-        }
-        double val = s[0];
-#pragma unroll
-        for (int u = 1; u < U; ++u) val = lane == u ? s[u] : val;
-        const int row = r0 + lane;
-        if (lane < U && row < nrow)
-            part[((size_t)(k0 + row / pvs) * pv + row % pvs) * gridDim.x + blockIdx.x] = val;   // [k][v][block]: coalesced for the reducer
     }
 }
 
@@ -688,6 +707,9 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? BB_FUSE_MIN_BLOCKS : BB_P2_MIN_B
     };
 
     prefetch(blockIdx.x - seg.blk0, 0);
+    // launched as a programmatic dependent of the tail kernel (fused step): everything above ran beside it,
+    // its output (the context) is needed from here on.  A no-op for ordinary launches.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int i = tid; i < a.K * 3 * TT; i += BLOCK) {
         const int k = i / (3 * TT), r = i - k * 3 * TT, j = r / TT, t = r - j * TT;
         sctx[k * CS + j * TT + t] = a.ctx[(((size_t)seg.rep * a.K + k) * 3 + j) * a.tmax_ctx + t];

@@ -266,8 +266,9 @@ def main():
     value = units_step * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel, live CUDA-event brackets on the launching stream.
-    # For non-hierarchical models the step runs one fused kernel (pass 2 of step i + pass 1 of step i+1:
-    # theta, accumulators and counts cross HBM exactly once per step) plus two small kernels.
+    # For non-hierarchical models the step is two launches: the fused step kernel (pass 2 of step i + pass 1
+    # of step i+1: theta, accumulators and counts cross HBM exactly once per step) and the merged tail kernel
+    # (partial-sum reduction + shared latents), see DESIGN.md section 4.
     n_prof = min(200, max(10, args.steps))
     ms_tot, ms_p1, ms_p2 = eng.time_steps(n_prof)
     barrier()
@@ -283,14 +284,15 @@ def main():
                   else "pass2_kernel (gradient + fused optimiser update)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
-        # (profiles/r1_ncu_fused_kernel.csv; cfg2 fp32 K=8 DecayedADAGrad, 1 GPU) -- null for other configurations
-        "traffic": 186.7e6 if (world == 1 and args.dtype == "f32" and args.opt == "decayed" and K == 8) else None,
+        # (profiles/r1_final_ncu_fused_kernel.csv; cfg2 fp32 K=8 DecayedADAGrad, 1 GPU) -- null for other configurations
+        "traffic": 186.9e6 if (world == 1 and args.dtype == "f32" and args.opt == "decayed" and K == 8) else None,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
         "kernel_us": t_p2 * 1e6, "pass1_us": t_p1 * 1e6, "step_us": ms / args.steps * 1e3,
         "kernel_share_of_step": t_p2 / (ms_tot / n_prof * 1e-3),
         "step_achieved": step_achieved, "step_frac": step_achieved / peak,
-        "note": "K=8: issue/MUFU-bound (noise generated in both passes), see profiles/; roofline_k1 shows the "
-                "bandwidth-bound regime of the reference's default samples_per_step=1",
+        "note": "K=8: issue-bound (two passes regenerate the Philox/Box-Muller noise: 323 instructions per "
+                "column*sample), DRAM ~15% busy, see profiles/r1_final.md; roofline_k1 is the same measurement at the "
+                "reference's default samples_per_step=1",
     }
     # the same measurement at the reference's default samples_per_step = 1 (src/vi.jl:98), for context
     roofline_k1 = None

@@ -36,6 +36,7 @@ def main():
         eng.init_params(5)
         eng.set_optimizer("truncated", n=4)
         trace = eng.step(steps, elbo_trace=True)
+        eng.step(steps)            # production path: fused step kernel + merged tail kernel (peer exchange inside)
         m, s = eng.get_posterior()
         eng.close()
         return trace, m, s
