@@ -138,19 +138,15 @@ __device__ __forceinline__ double softplus_d(double w) { return fmax(w, 0.0) + l
 //   phase 1  (r, k, t<T-1) c_t, residual sums u_t, per-sample gradients, ctx -> scratch
 //   phase 2  (r, k, t<T)   G_Lambda_t = (u_{t-1} - u_t) / Lambda_t           -> ctx
 //   phase 3  (i)           mean over samples, optimiser update (or emit)
-// `sums`: where the (all-reduced) totals are / will be; `scratch`: working arrays (global, or shared memory
-// in the merged tail kernel)
+// phase 0 of the shared-latent kernel: noise and z of the shared latents -> scratch (eps, z, log sigma).
+// Independent of the step's sums: the merged tail kernel runs it on its own CTA beside the reduction.
 template <typename real>
-__device__ __forceinline__ void shared_body(const SharedArgs<real> &a, double *sums, double *scratch) {
+__device__ __forceinline__ void shared_phase0(const SharedArgs<real> &a, double *scratch) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int n2 = 2 * a.nst;
-    double *eps_t = scratch + (size_t)a.K * n2;              // [K][n2] eps
-    double *z_t = eps_t + (size_t)a.K * n2;                  // [K][n2] z
-    double *u_t = z_t + (size_t)a.K * n2;                    // [R][K][tmax] sum_all w res
-    double *lp_t = u_t + (size_t)a.R * a.K * a.tmax;         // [R][K][tmax] log-density pieces
-    double *lsig_t = lp_t + (size_t)a.R * a.K * a.tmax;      // [n2] log sigma before the update
-    xchg_wait_and_sum(a.xchg, sums);                       // multi-GPU: complete the sums over NVLink peer memory
-    // ---- phase 0
+    double *eps_t = scratch + (size_t)a.K * n2;
+    double *z_t = eps_t + (size_t)a.K * n2;
+    double *lsig_t = z_t + (size_t)a.K * n2 + (size_t)2 * a.R * a.K * a.tmax;
     for (int j = tid; j < a.K * n2; j += nthr) {
         const int k = j / n2, i = j % n2;
         const double e = a.eps_sh ? a.eps_sh[j]
@@ -161,6 +157,21 @@ __device__ __forceinline__ void shared_body(const SharedArgs<real> &a, double *s
         z_t[j] = a.z_direct ? e : th.x + sigma * e;
         if (k == 0) lsig_t[i] = log(sigma);
     }
+}
+
+// `sums`: where the (all-reduced) totals are / will be; `scratch`: working arrays (global, or shared memory
+// in the merged tail kernel); do_phase0 = false: eps / z / log sigma are already in `scratch`
+template <typename real>
+__device__ __forceinline__ void shared_body(const SharedArgs<real> &a, double *sums, double *scratch, bool do_phase0) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int n2 = 2 * a.nst;
+    double *eps_t = scratch + (size_t)a.K * n2;              // [K][n2] eps
+    double *z_t = eps_t + (size_t)a.K * n2;                  // [K][n2] z
+    double *u_t = z_t + (size_t)a.K * n2;                    // [R][K][tmax] sum_all w res
+    double *lp_t = u_t + (size_t)a.R * a.K * a.tmax;         // [R][K][tmax] log-density pieces
+    double *lsig_t = lp_t + (size_t)a.R * a.K * a.tmax;      // [n2] log sigma before the update
+    if (do_phase0) shared_phase0<real>(a, scratch);
+    xchg_wait_and_sum(a.xchg, sums);                         // multi-GPU: complete the sums over NVLink peer memory
     __syncthreads();
     // ---- phase 1
     for (int j = tid; j < a.R * a.K * a.tmax; j += nthr) {
@@ -240,7 +251,7 @@ __device__ __forceinline__ void shared_body(const SharedArgs<real> &a, double *s
 
 template <typename real>
 __global__ void __launch_bounds__(256) shared_kernel(const SharedArgs<real> a) {
-    shared_body<real>(a, a.sums, a.scratch);
+    shared_body<real>(a, a.sums, a.scratch, true);
 }
 
 // ------------------------------------------------------------------ merged step tail
@@ -255,7 +266,9 @@ __global__ void __launch_bounds__(256) tail_kernel(const ReduceArgs ra, int R, c
     extern __shared__ double tail_smem[];        // [nsums] totals | scratch
     __shared__ int is_last;
     asm volatile("griddepcontrol.launch_dependents;");      // let the next column kernel start its prologue
-    reduce_rows(ra, R);
+    // the extra CTA (index gridDim.x - 1, no reduction rows) draws the shared latents' noise beside the reduction
+    if (blockIdx.x == gridDim.x - 1) shared_phase0<real>(sa, sa.scratch);
+    else reduce_rows(ra, R);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -283,7 +296,14 @@ __global__ void __launch_bounds__(256) tail_kernel(const ReduceArgs ra, int R, c
         for (int i = threadIdx.x; i < nsums; i += blockDim.x) tot[i] = __ldcg(ra.sums + i);
         __syncthreads();
     }
-    shared_body<real>(sa, tot, scratch);
+    {
+        // eps, z (contiguous) and log sigma of phase 0: global scratch -> shared-memory scratch
+        const int n2 = 2 * sa.nst, kn = sa.K * n2;
+        const size_t ls = (size_t)3 * kn + (size_t)2 * sa.R * sa.K * sa.tmax;
+        for (int i = threadIdx.x; i < 2 * kn; i += blockDim.x) scratch[kn + i] = __ldcg(sa.scratch + kn + i);
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) scratch[ls + i] = __ldcg(sa.scratch + ls + i);
+    }
+    shared_body<real>(sa, tot, scratch, false);
 }
 
 // ------------------------------------------------------------------ hyper latents (theta of the hierarchical models)

@@ -721,7 +721,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         sa.opt = opt_args<double>(m.update);
         sa.leader = L.rank == 0 ? 1 : 0;
         if (use_tail)
-            tail_kernel<real><<<cdiv((long long)nwarps * 32, 256), 256, tail_smem, stream_>>>(ra, L.R, xp, sa, ticket_.p,
+            tail_kernel<real><<<cdiv((long long)nwarps * 32, 256) + 1, 256, tail_smem, stream_>>>(ra, L.R, xp, sa, ticket_.p,
                                                                                              (int)sums_.n);
         else
             shared_kernel<real><<<1, 256, 0, stream_>>>(sa);

@@ -1,6 +1,7 @@
-"""Naive priors: host-side mirror of ``BarBay.stats.naive_prior`` / ``naive_fitness``
+"""Host-side mirror of ``BarBay.stats``: the naive priors ``naive_prior`` / ``naive_fitness``
 (src/stats.jl:1175-1359, 1040-1106) -- the empirical priors every documented workflow feeds into the
-models (docs/src/examples.md:121-140).  O(rows) numpy on top of ``utils.data_to_arrays``; the values
+models (docs/src/examples.md:121-140) -- and, at the end of the file, the posterior predictive checks
+on a DataFrame of posterior draws (src/stats.jl:35-996).  O(rows) numpy on top of ``utils.data_to_arrays``; the values
 go to the kernels as matrix priors.  SURVEY.md §8f rank 3 ("next" row): host arithmetic only, it is
 not on the per-step path.
 
@@ -92,3 +93,129 @@ def naive_fitness(data: pd.DataFrame, *, id_col="barcode", time_col="time", coun
     pos = {b: i for i, b in enumerate(da.bc_ids)}
     idx = [pos[b] for b in order]
     return pd.DataFrame({id_col: list(order), "fitness": fitness[idx]})
+
+
+# ------------------------------------------------------------------------------------------------------
+# Posterior predictive checks: host mirrors of the DataFrame methods of
+# src/stats.jl:35-996.  `df` holds one posterior draw per row (e.g. draws of the fitted mean-field
+# Gaussian); the draws of the predictive Normal / LogNormal use numpy's Generator, so -- exactly like
+# the reference with Julia's global RNG -- results are reproducible only for a caller-supplied `rng`.
+def _sorted_vars(df: pd.DataFrame, pattern: str) -> list:
+    """``sort(names(df)[occursin.(pattern, names(df))])`` (stats.jl:165-169): code-point order."""
+    return sorted(c for c in df.columns if pattern in str(c))
+
+
+def _flatten(ppc: np.ndarray, flatten: bool) -> np.ndarray:
+    """``vcat(collect(eachslice(ppc, dims=3))...)`` (stats.jl:208-212): the n_ppc slices stacked by rows."""
+    if not flatten:
+        return ppc
+    return np.concatenate([ppc[:, :, k] for k in range(ppc.shape[2])], axis=0)
+
+
+def matrix_quantile_range(quantile, matrix, dims: int = 2) -> np.ndarray:
+    """Symmetric quantile ranges of ``matrix`` along ``dims`` (1-based, as in the reference,
+    stats.jl:55-88): ``out[:, i, 0/1]`` = the ``(1-q)/2`` and ``1-(1-q)/2`` quantiles (StatsBase
+    default = linear interpolation = numpy default)."""
+    q = np.asarray(quantile, dtype=np.float64)
+    if ((q < 0.0) | (q > 1.0)).any():
+        raise _err("All quantiles must be between zero and one")
+    if dims not in (1, 2):
+        raise _err("Dimensions should match a Matrix dimensiosn, i.e., 1 or 2")
+    m = np.asarray(matrix)
+    # eachslice(matrix, dims=dims): one slice per index of `dims` (dims = 2: the columns), one quantile pair
+    # per slice; the output has size(matrix, dims) rows (stats.jl:69-72: `op_dims` evaluates to `dims`)
+    axis = 0 if dims == 2 else 1
+    n_out = m.shape[1] if dims == 2 else m.shape[0]
+    out = np.empty((n_out, q.size, 2), dtype=np.result_type(m.dtype, np.float64))
+    for i, qi in enumerate(q):
+        out[:, i, 0] = np.quantile(m, (1.0 - qi) / 2.0, axis=axis)
+        out[:, i, 1] = np.quantile(m, 1.0 - (1.0 - qi) / 2.0, axis=axis)
+    return out
+
+
+def _err(msg: str):
+    from ._lib import BarBayError
+    return BarBayError(msg)
+
+
+def logfreq_ratio_bc_ppc(df: pd.DataFrame, n_ppc: int, *, param: dict | None = None, flatten: bool = True,
+                         rng: np.random.Generator | None = None) -> np.ndarray:
+    """``log(f_{t+1}/f_t) ~ N(s⁽ᵐ⁾ - s̄_t, exp(σ⁽ᵐ⁾))`` for every posterior draw (stats.jl:377-418).
+    Returns ``(n_draws * n_ppc) x n_times`` (flattened) or ``n_draws x n_times x n_ppc``."""
+    p = {"bc_mean_fitness": "s⁽ᵐ⁾", "bc_std_fitness": "σ⁽ᵐ⁾", "population_mean_fitness": "s̲ₜ"}
+    p.update(param or {})
+    rng = rng or np.random.default_rng()
+    mean_vars = _sorted_vars(df, p["population_mean_fitness"])
+    s = df[p["bc_mean_fitness"]].to_numpy(np.float64)
+    sd = np.exp(df[p["bc_std_fitness"]].to_numpy(np.float64))
+    ppc = np.empty((len(df), len(mean_vars), n_ppc))
+    for i, var in enumerate(mean_vars):
+        mu = s - df[var].to_numpy(np.float64)
+        ppc[:, i, :] = mu[:, None] + sd[:, None] * rng.standard_normal((len(df), n_ppc))
+    return _flatten(ppc, flatten)
+
+
+def logfreq_ratio_popmean_ppc(df: pd.DataFrame, n_ppc: int, *, param: dict | None = None, flatten: bool = True,
+                              rng: np.random.Generator | None = None) -> np.ndarray:
+    """Neutral lineages: ``log(f_{t+1}/f_t) ~ N(-s̄_t, exp(σ_t))`` (stats.jl:571-621)."""
+    p = {"population_mean_fitness": "sₜ", "population_std_fitness": "σₜ"}
+    p.update(param or {})
+    rng = rng or np.random.default_rng()
+    mean_vars = _sorted_vars(df, p["population_mean_fitness"])
+    std_vars = _sorted_vars(df, p["population_std_fitness"])
+    if len(mean_vars) != len(std_vars):
+        raise _err("The number of mean and standard deviation variables does not match")
+    ppc = np.empty((len(df), len(mean_vars), n_ppc))
+    for i, (mv, sv) in enumerate(zip(mean_vars, std_vars)):
+        mu = -df[mv].to_numpy(np.float64)
+        sd = np.exp(df[sv].to_numpy(np.float64))
+        ppc[:, i, :] = mu[:, None] + sd[:, None] * rng.standard_normal((len(df), n_ppc))
+    return _flatten(ppc, flatten)
+
+
+def logfreq_ratio_multienv_ppc(df: pd.DataFrame, n_ppc: int, envs, *, param: dict | None = None,
+                               flatten: bool = True, rng: np.random.Generator | None = None) -> np.ndarray:
+    """Multi-environment version: the ratio ``t -> t+1`` uses the fitness of the environment of time
+    ``t+1`` (stats.jl:789-864); ``envs`` lists the environment of every time point."""
+    p = {"bc_mean_fitness": "s̲⁽ᵐ⁾", "bc_std_fitness": "σ̲⁽ᵐ⁾", "population_mean_fitness": "s̲ₜ"}
+    p.update(param or {})
+    rng = rng or np.random.default_rng()
+    env_unique = list(dict.fromkeys(envs))                                  # unique(): first appearance
+    env_idx = [env_unique.index(e) for e in envs]                           # indexin (0-based here)
+    mean_vars = _sorted_vars(df, p["population_mean_fitness"])
+    s_vars = _sorted_vars(df, p["bc_mean_fitness"])
+    sd_vars = _sorted_vars(df, p["bc_std_fitness"])
+    if len(s_vars) != len(env_unique) or len(sd_vars) != len(env_unique):
+        raise _err("# of mutant-related variables does not match # of environments")
+    if len(envs) != len(mean_vars) + 1:
+        raise _err("Number of given environments does not match time points in chain")
+    ppc = np.empty((len(df), len(mean_vars), n_ppc))
+    for i, var in enumerate(mean_vars):
+        e = env_idx[i + 1]
+        mu = df[s_vars[e]].to_numpy(np.float64) - df[var].to_numpy(np.float64)
+        sd = np.exp(df[sd_vars[e]].to_numpy(np.float64))
+        ppc[:, i, :] = mu[:, None] + sd[:, None] * rng.standard_normal((len(df), n_ppc))
+    return _flatten(ppc, flatten)
+
+
+def freq_bc_ppc(df: pd.DataFrame, n_ppc: int, *, param: dict | None = None, model: str = "lognormal",
+                flatten: bool = True, rng: np.random.Generator | None = None) -> np.ndarray:
+    """Barcode frequency trajectories ``f_{t+1} = f_t * LogNormal(s⁽ᵐ⁾ - s̄_t, σ)`` from the initial
+    frequency column (stats.jl:152-213); ``model="normal"`` exponentiates the std column first."""
+    p = {"bc_mean_fitness": "s⁽ᵐ⁾", "bc_std_fitness": "σ⁽ᵐ⁾", "bc_freq": "f̲⁽ᵐ⁾[1]",
+         "population_mean_fitness": "s̲ₜ"}
+    p.update(param or {})
+    if model not in ("lognormal", "normal"):
+        raise _err("model must be :normal or :lognormal")
+    rng = rng or np.random.default_rng()
+    mean_vars = _sorted_vars(df, p["population_mean_fitness"])
+    s = df[p["bc_mean_fitness"]].to_numpy(np.float64)
+    sd = df[p["bc_std_fitness"]].to_numpy(np.float64)
+    if model == "normal":
+        sd = np.exp(sd)
+    ppc = np.empty((len(df), len(mean_vars) + 1, n_ppc))
+    ppc[:, 0, :] = df[p["bc_freq"]].to_numpy(np.float64)[:, None]
+    for i, var in enumerate(mean_vars):
+        mu = s - df[var].to_numpy(np.float64)
+        ppc[:, i + 1, :] = ppc[:, i, :] * np.exp(mu[:, None] + sd[:, None] * rng.standard_normal((len(df), n_ppc)))
+    return _flatten(ppc, flatten)

@@ -56,3 +56,61 @@ def test_prior_matrices_feed_the_engine_layout(bb):
     size = {g.name: g.length for g in lay.groups}
     assert pri["s_pop_prior"].shape == (size[bb.model.V_S_POP], 2)
     assert pri["logλ_prior"].shape == (size[bb.model.V_LOGLAM], 2)
+
+
+# ------------------------------------------------------------------ posterior predictive checks (stats.jl:35-996)
+def _draws(n=4000, seed=0):
+    import pandas as pd
+    r = np.random.default_rng(seed)
+    return pd.DataFrame({"s̲ₜ[1]": 0.3 + 0.01 * r.standard_normal(n), "s̲ₜ[2]": 0.5 + 0.01 * r.standard_normal(n),
+                         "s⁽ᵐ⁾": 1.0 + 0.01 * r.standard_normal(n), "σ⁽ᵐ⁾": np.full(n, np.log(0.2)),
+                         "f̲⁽ᵐ⁾[1]": np.full(n, 1e-3)})
+
+
+def test_logfreq_ratio_bc_ppc_shapes_and_moments(bb):
+    df = _draws()
+    flat = bb.stats.logfreq_ratio_bc_ppc(df, 3, rng=np.random.default_rng(1))
+    raw = bb.stats.logfreq_ratio_bc_ppc(df, 3, flatten=False, rng=np.random.default_rng(1))
+    assert flat.shape == (3 * len(df), 2) and raw.shape == (len(df), 2, 3)
+    assert np.array_equal(flat[len(df):2 * len(df)], raw[:, :, 1])           # vcat of the n_ppc slices
+    # N(s - sbar_t, exp(sigma)): mean 0.7 / 0.5, sd 0.2 (+ the 0.014 spread of the draws)
+    assert np.allclose(flat.mean(axis=0), [0.7, 0.5], atol=0.01) and np.allclose(flat.std(axis=0), 0.2, atol=0.01)
+
+
+def test_popmean_and_multienv_ppc(bb):
+    import pandas as pd
+    n = 3000
+    df = pd.DataFrame({"sₜ[1]": np.full(n, 0.4), "sₜ[2]": np.full(n, 0.1), "σₜ[1]": np.full(n, np.log(0.1)),
+                       "σₜ[2]": np.full(n, np.log(0.3))})
+    pm = bb.stats.logfreq_ratio_popmean_ppc(df, 2, rng=np.random.default_rng(2))
+    assert pm.shape == (2 * n, 2)
+    assert np.allclose(pm.mean(axis=0), [-0.4, -0.1], atol=0.02) and np.allclose(pm.std(axis=0), [0.1, 0.3], atol=0.02)
+    with pytest.raises(bb.BarBayError, match="does not match"):
+        bb.stats.logfreq_ratio_popmean_ppc(df.drop(columns=["σₜ[2]"]), 2)
+    me = pd.DataFrame({"s̲ₜ[1]": np.zeros(n), "s̲ₜ[2]": np.zeros(n), "s̲⁽ᵐ⁾[1]": np.full(n, 1.0), "s̲⁽ᵐ⁾[2]": np.full(n, -1.0),
+                       "σ̲⁽ᵐ⁾[1]": np.full(n, np.log(0.05)), "σ̲⁽ᵐ⁾[2]": np.full(n, np.log(0.05))})
+    out = bb.stats.logfreq_ratio_multienv_ppc(me, 1, ["a", "a", "b"], rng=np.random.default_rng(3))
+    assert np.allclose(out.mean(axis=0), [1.0, -1.0], atol=0.01)             # ratio t -> t+1 uses the env of t+1
+    with pytest.raises(bb.BarBayError, match="environments"):
+        bb.stats.logfreq_ratio_multienv_ppc(me, 1, ["a", "b"])
+    with pytest.raises(bb.BarBayError, match="# of mutant-related"):
+        bb.stats.logfreq_ratio_multienv_ppc(me, 1, ["a", "b", "c"])
+
+
+def test_freq_bc_ppc_and_quantile_range(bb):
+    df = _draws(2000)
+    df["σ⁽ᵐ⁾"] = 0.2                                                         # :lognormal takes sigma as is
+    f = bb.stats.freq_bc_ppc(df, 2, flatten=False, rng=np.random.default_rng(4))
+    assert f.shape == (len(df), 3, 2) and np.all(f[:, 0, :] == 1e-3)
+    assert np.allclose(np.log(f[:, 1, :] / f[:, 0, :]).mean(), 0.7, atol=0.02)
+    fn = bb.stats.freq_bc_ppc(df.assign(**{"σ⁽ᵐ⁾": np.log(0.2)}), 2, model="normal", flatten=False,
+                              rng=np.random.default_rng(4))
+    assert np.allclose(fn, f)                                                # exp(log 0.2) == 0.2: same draws
+    with pytest.raises(bb.BarBayError, match="model must be"):
+        bb.stats.freq_bc_ppc(df, 1, model="poisson")
+    m = np.random.default_rng(5).standard_normal((500, 4))
+    q = bb.stats.matrix_quantile_range([0.95, 0.5], m, dims=2)
+    assert q.shape == (4, 2, 2)
+    assert np.allclose(q[:, 0, 0], np.quantile(m, 0.025, axis=0)) and np.allclose(q[:, 1, 1], np.quantile(m, 0.75, axis=0))
+    with pytest.raises(bb.BarBayError, match="between zero and one"):
+        bb.stats.matrix_quantile_range([1.5], m)
