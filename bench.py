@@ -156,7 +156,7 @@ def run_reference(args):
     N, M = da.n_neutral, da.n_bc
     K = args.mc_samples
     # probe the rate on a small sample, then size the per-step sample
-    probe_rate, _, cores = cpu_port_rate(da, 1.0, K, max_barcodes=50_000)
+    probe_rate, cores, _ = cpu_port_rate(da, 1.0, K, max_barcodes=50_000)
     budget = 120.0 / max(1, args.steps + args.warmup)
     nb = int(min(M, max(2_000, probe_rate * budget / (K * T) - N)))
     sub = np.ascontiguousarray(R[:, :N + nb])
@@ -285,12 +285,12 @@ def main():
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
         # (profiles/r1_final_ncu_fused_kernel.csv; cfg2 fp32 K=8 DecayedADAGrad, 1 GPU) -- null for other configurations
-        "traffic": 186.9e6 if (world == 1 and args.dtype == "f32" and args.opt == "decayed" and K == 8) else None,
+        "traffic": 188.0e6 if (world == 1 and args.dtype == "f32" and args.opt == "decayed" and K == 8) else None,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
         "kernel_us": t_p2 * 1e6, "pass1_us": t_p1 * 1e6, "step_us": ms / args.steps * 1e3,
         "kernel_share_of_step": t_p2 / (ms_tot / n_prof * 1e-3),
         "step_achieved": step_achieved, "step_frac": step_achieved / peak,
-        "note": "K=8: issue-bound (two passes regenerate the Philox/Box-Muller noise: 323 instructions per "
+        "note": "K=8: issue-bound (two passes regenerate the Philox/Box-Muller noise: 416 warp instructions per "
                 "column*sample), DRAM ~15% busy, see profiles/r1_final.md; roofline_k1 is the same measurement at the "
                 "reference's default samples_per_step=1",
     }

@@ -188,3 +188,31 @@ def test_fused_pipelined_steps_match_oracle_and_unfused(bb, model, opt, monkeypa
         assert rel_err(mu_g, tr.mu) < 1e-8 and rel_err(om_g, tr.omega) < 1e-8, mode
     assert np.array_equal(results["fused"][0], results["fused_split"][0])
     assert rel_err(results["fused"][0], results["unfused"][0]) < 1e-10
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("model", ["fitness_normal", "replicate_fitness_normal"])
+def test_merged_tail_kernel_equals_separate_kernels(bb, model, dtype, monkeypatch):
+    """The production step uses the merged tail kernel (reduction + shared latents, working set in shared
+    memory, noise of the shared latents drawn on its own CTA) and launches the fused column kernel as a
+    programmatic dependent.  Same arithmetic in the same order as reduce_kernel -> shared_kernel with plain
+    launches: the trajectories must be bitwise identical."""
+    res = {}
+    for mode in ("default", "no_tail", "no_pdl"):
+        monkeypatch.delenv("BB_NO_TAIL", raising=False)
+        monkeypatch.delenv("BB_NO_PDL", raising=False)
+        if mode == "no_tail":
+            monkeypatch.setenv("BB_NO_TAIL", "1")
+        if mode == "no_pdl":
+            monkeypatch.setenv("BB_NO_PDL", "1")
+        da, eng = _setup(bb, model, 3, dtype)
+        eng.init_params(9)
+        eng.set_optimizer("decayed")
+        eng.step(6)
+        trace = eng.step(2, elbo_trace=True)
+        res[mode] = (eng.get_params(), trace)
+        eng.close()
+    for mode in ("no_tail", "no_pdl"):
+        assert np.array_equal(res["default"][0][0], res[mode][0][0]), mode
+        assert np.array_equal(res["default"][0][1], res[mode][0][1]), mode
+        assert np.array_equal(res["default"][1], res[mode][1]), mode
