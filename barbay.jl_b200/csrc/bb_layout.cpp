@@ -5,6 +5,7 @@
 #include <cmath>
 #include <numeric>
 #include <stdexcept>
+#include <thread>
 
 namespace bb {
 
@@ -311,8 +312,41 @@ void build_layout(const bb_desc &d, Layout &L) {
         cst += prior_norm_const(d.s_bc_prior, L.bc_block) + prior_norm_const(d.logsig_bc_prior, L.bc_block);
     }
     cst += prior_norm_const(d.loglam_prior, ncount);
+    // sum of lgamma(r + 1) over every count: 64 fixed chunks (so the rounding does not depend on the machine),
+    // spread over the host threads -- at 5 * 10^6 counts this loop was the largest part of bb_create
     double lg = 0.0;
-    for (long long i = 0; i < ncount; ++i) lg += std::lgamma((double)d.bc_count[i] + 1.0);
+    {
+        constexpr int kChunks = 64;
+        double partial[kChunks] = {0.0};
+        const int nthr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        // read counts are small integers: lgamma(r + 1) of r < 4096 comes from a table of the same libm values
+        constexpr int kTab = 4096;
+        std::vector<double> tab(kTab);
+        {
+            int sign = 0;
+            for (int r = 0; r < kTab; ++r) tab[r] = lgamma_r((double)r + 1.0, &sign);
+        }
+        auto work = [&](int w) {
+            int sign = 0;
+            for (int ch = w; ch < kChunks; ch += nthr) {
+                const long long i0 = ncount * ch / kChunks, i1 = ncount * (ch + 1) / kChunks;
+                double acc = 0.0;
+                for (long long i = i0; i < i1; ++i) {
+                    const int64_t r = d.bc_count[i];
+                    acc += (r >= 0 && r < kTab) ? tab[r] : lgamma_r((double)r + 1.0, &sign);
+                }
+                partial[ch] = acc;
+            }
+        };
+        if (ncount < 100000 || nthr == 1) {
+            for (int w = 0; w < nthr; ++w) work(w);
+        } else {
+            std::vector<std::thread> pool;
+            for (int w = 0; w < nthr; ++w) pool.emplace_back(work, w);
+            for (auto &t : pool) t.join();
+        }
+        for (int ch = 0; ch < kChunks; ++ch) lg += partial[ch];
+    }
     cst -= lg;
     long long nratio = 0;
     for (int r = 0; r < L.R; ++r) nratio += (long long)(L.nt[r] - 1) * L.B;

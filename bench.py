@@ -199,7 +199,8 @@ def main():
     ap.add_argument("--opt", default="decayed", choices=["decayed", "truncated"])
     ap.add_argument("--mc-samples", type=int, default=K_MC)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=2000)
+    # the end-to-end call runs the reference's default number of iterations (ADVI(1, 10_000), src/vi.jl:98)
+    ap.add_argument("--e2e-steps", type=int, default=10000)
     args = ap.parse_args()
     # exactly ONE line on stdout: libraries (NCCL prints its version banner there) write to fd 1 too, so fd 1
     # is pointed at stderr for the whole run and the JSON line goes to the saved descriptor
