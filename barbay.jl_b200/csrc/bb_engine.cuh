@@ -151,7 +151,7 @@ template <typename real> class Engine : public EngineBase {
         KernelSet<real> ks, ks_sup;
         int pv = 0, kchunk = 0;
         size_t p1smem = 0, p2smem = 0, p2smem_elbo = 0;
-        int p1nbuf = 2, p2nbuf = 2, p2stage_acc = 1;
+        int p1nbuf = 2, p2nbuf = 2, p2stage_acc = 1, p2stage_ring = 1;
         size_t fsmem = 0;          // fused step kernel: pass-2 staging + pass-1 accumulators
         int facc_slots = 0;        // 0: the fused kernel is not available for this group
         size_t part_off = 0, epart_off = 0;     // block offsets into part_ / epart_
@@ -406,31 +406,40 @@ template <typename real> void Engine<real>::size_pass2() {
         // (1 buffer, theta + counts only; accumulators / priors / ring read from global)
         const size_t cn_b = (size_t)L.tmax * BLOCK * sizeof(int);
         const size_t sel_b = (size_t)(L.K + 1) * BLOCK * sizeof(double);
-        // prefetched set (theta, priors, counts: one or two buffers) + epilogue set (accumulators, ring: one)
-        const size_t pre_b = (1 + npr) * th_b + cn_b, epi_b = (1 + nrg) * th_b;
-        g.p2nbuf = 2; g.p2stage_acc = 1;
-        size_t stage_b = 2 * pre_b + epi_b;
-        if (ctx_b + sel_b + stage_b > kMaxSmem) { g.p2nbuf = 1; stage_b = pre_b + epi_b; }
-        if (ctx_b + sel_b + stage_b > kMaxSmem) { g.p2stage_acc = 0; stage_b = th_b + cn_b; }
-        if (ctx_b + sel_b + stage_b > kMaxSmem)
-            throw std::runtime_error("T x E too large for the column kernels' shared memory");
-        g.p2smem = ctx_b + stage_b;                                               // ELBO = false kernels
-        g.p2smem_elbo = g.p2smem + sel_b;
-        // fused step kernel (non-hierarchical, all K samples in one sweep of the mutant accumulators)
-        g.facc_slots = 0;
-        if (g.ks.pass2_fused && !getenv("BB_NO_FUSE")) {
-            const int pv_m = L.E == 1 ? 2 * g.nt : g.pv;
-            const int slots = std::max(L.K * pv_m, (g.pv + 1) & ~1);
-            const size_t fs = g.p2smem + (size_t)slots * BLOCK * sizeof(real);
-            if (fs <= kMaxSmem && (size_t)slots * BLOCK * sizeof(real) <= 64 * 1024) {
-                BB_CUDA(cudaFuncSetAttribute((const void *)g.ks.pass2_fused,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
-                int occf = 0;
-                BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occf, g.ks.pass2_fused, BLOCK, fs));
-                // measured (B200, cfg2): the fused kernel wins at >= 3 resident CTAs per SM; with 2 (large K plus
-                // the TruncatedADAGrad ring stage) the two-kernel step is faster
-                if (occf >= 3) { g.facc_slots = slots; g.fsmem = fs; }
+        // prefetched set (theta, priors, counts: one or two buffers) + epilogue set (accumulators, ring: one).
+        // TruncatedADAGrad: the evicted ring slot is staged too unless that costs the fused step kernel its third
+        // resident CTA per SM (cfg2, K = 8) -- then the epilogue reads the slot straight from global memory.
+        auto plan = [&](int stage_ring) {
+            const size_t pre_b = (1 + npr) * th_b + cn_b, epi_b = (1 + stage_ring) * th_b;
+            g.p2nbuf = 2; g.p2stage_acc = 1; g.p2stage_ring = stage_ring;
+            size_t stage_b = 2 * pre_b + epi_b;
+            if (ctx_b + sel_b + stage_b > kMaxSmem) { g.p2nbuf = 1; stage_b = pre_b + epi_b; }
+            if (ctx_b + sel_b + stage_b > kMaxSmem) { g.p2stage_acc = 0; stage_b = th_b + cn_b; }
+            if (ctx_b + sel_b + stage_b > kMaxSmem)
+                throw std::runtime_error("T x E too large for the column kernels' shared memory");
+            g.p2smem = ctx_b + stage_b;                                               // ELBO = false kernels
+            g.p2smem_elbo = g.p2smem + sel_b;
+            // fused step kernel (non-hierarchical, all K samples in one sweep of the mutant accumulators)
+            g.facc_slots = 0;
+            if (g.ks.pass2_fused && !getenv("BB_NO_FUSE")) {
+                const int pv_m = L.E == 1 ? 2 * g.nt : g.pv;
+                const int slots = std::max(L.K * pv_m, (g.pv + 1) & ~1);
+                const size_t fs = g.p2smem + (size_t)slots * BLOCK * sizeof(real);
+                if (fs <= kMaxSmem && (size_t)slots * BLOCK * sizeof(real) <= 64 * 1024) {
+                    BB_CUDA(cudaFuncSetAttribute((const void *)g.ks.pass2_fused,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs));
+                    int occf = 0;
+                    BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occf, g.ks.pass2_fused, BLOCK, fs));
+                    // measured (B200, cfg2): the fused kernel wins at >= 3 resident CTAs per SM; with 2 the
+                    // two-kernel step is faster
+                    if (occf >= 3) { g.facc_slots = slots; g.fsmem = fs; }
+                }
             }
+        };
+        plan(nrg);
+        if (nrg && !g.facc_slots && g.ks.pass2_fused && !L.hier) {
+            plan(0);
+            if (!g.facc_slots) plan(nrg);          // no fused kernel either way: keep the ring staged
         }
         BB_CUDA(cudaFuncSetAttribute((const void *)g.ks.pass2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)g.p2smem));
@@ -745,7 +754,8 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         a.sup = sup;
         a.stage_pr = (L.lam_pr_matrix || L.bc_pr_matrix) ? 1 : 0;
         // smem is sized for the ring by size_pass2(); stage it only when the ring exists and is updated
-        a.stage_ring = (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p && m.update) ? 1 : 0;
+        a.stage_ring = (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p && m.update && g.p2stage_ring) ? 1 : 0;
+        a.l2_ring = (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p && m.update && !(a.stage_ring && g.p2stage_acc)) ? 1 : 0;
         a.stage_acc = g.p2stage_acc; a.nbuf = g.p2nbuf;
         if (m.fuse) {
             // the reducer has consumed this step's partials (stream order): the fused kernel overwrites them

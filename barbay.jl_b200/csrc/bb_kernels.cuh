@@ -490,13 +490,16 @@ __device__ __forceinline__ void finish_batch(const OptArgsT<real> &o, real invK,
                                              vec2<real> *g_acc, vec2<real> *g_ring, vec2<real> *g_out, size_t cpad) {
     using r2 = vec2<real>;
     if constexpr (MODE == 3) return;
-    r2 th[N], ac[N];
+    r2 th[N], ac[N], rg[MODE == 1 ? N : 1];
     real g0[N], g1[N];
+    // every load of the batch is issued before its first store: unstaged accumulators / ring slots come from
+    // global memory, and a load behind a (possibly aliasing) store would pay its DRAM latency alone
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         if (i >= n) break;
         th[i] = sth[i * BLOCK];
         if constexpr (MODE < 2) ac[i] = sac ? sac[i * BLOCK] : g_acc[(size_t)i * cpad];
+        if constexpr (MODE == 1) rg[i] = srg ? srg[i * BLOCK] : g_ring[(size_t)i * cpad];   // the ring slot evicted this step
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -521,9 +524,8 @@ __device__ __forceinline__ void finish_batch(const OptArgsT<real> &o, real invK,
                 d0[i] = bb_sqrt(ac[i].x) + real(1e-8);
                 d1[i] = bb_sqrt(ac[i].y) + real(1e-8);
             } else {
-                const r2 rg = srg ? srg[i * BLOCK] : g_ring[(size_t)i * cpad];   // the ring slot evicted this step
-                ac[i].x = fmax(ac[i].x - rg.x + q0, real(0));
-                ac[i].y = fmax(ac[i].y - rg.y + q1, real(0));
+                ac[i].x = fmax(ac[i].x - rg[i].x + q0, real(0));
+                ac[i].y = fmax(ac[i].y - rg[i].y + q1, real(0));
                 g_ring[(size_t)i * cpad] = mk2<real>(q0, q1);
                 d0[i] = o.tau + bb_sqrt(ac[i].x) + real(1e-8);
                 d1[i] = o.tau + bb_sqrt(ac[i].y) + real(1e-8);
@@ -672,6 +674,23 @@ __global__ void __launch_bounds__(BLOCK, FUSE ? BB_FUSE_MIN_BLOCKS : BB_P2_MIN_B
     };
     auto prefetch_epi = [&](int tile) {          // always commits a (possibly empty) group
         const int i = tile * BLOCK + tid;
+        if (a.l2_ring && i < seg.ncol) {
+            // TruncatedADAGrad with the ring slot not staged (shared-memory budget): pull it into L2 now, the
+            // update epilogue reads it after the K samples
+            const uint32_t c = (uint32_t)(seg.col0 + i);
+#pragma unroll
+            for (int t = 0; t < S::MAXT; ++t) {
+                if (t >= nt) break;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(C.lam_ring + ((uint32_t)t * (uint32_t)cpad + c)));
+            }
+            if (!seg.neutral) {
+#pragma unroll
+                for (int j = 0; j < S::MAXJ; ++j) {
+                    if (j >= nj) break;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(C.bc_ring + ((uint32_t)j * (uint32_t)cpad + c)));
+                }
+            }
+        }
         if (nac && i < seg.ncol) {
             const uint32_t c = (uint32_t)(seg.col0 + i);
             r2 *sac = reinterpret_cast<r2 *>(epi0) + tid;

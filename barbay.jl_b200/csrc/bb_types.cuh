@@ -101,6 +101,7 @@ template <typename real> struct P2Args {
     int stage_pr;          // 1: per-latent (matrix) priors are staged through shared memory
     int stage_ring;        // 1: TruncatedADAGrad update -> the evicted ring slot is staged too
     int stage_acc;         // 1: accumulators (and priors / ring) go through the stage; 0: read from global
+    int l2_ring;           // 1: the evicted ring slot is NOT staged: prefetch it into L2 at tile start
     int nbuf;              // staging buffers: 2 = prefetch the next tile, 1 = no overlap (large T x E)
     double *part;          // fused step: block partial sums of the next step's pass 1, [K][pv][gridDim.x]
     int pv;                // row stride of part (3 nt - 2)

@@ -216,3 +216,28 @@ def test_merged_tail_kernel_equals_separate_kernels(bb, model, dtype, monkeypatc
         assert np.array_equal(res["default"][0][0], res[mode][0][0]), mode
         assert np.array_equal(res["default"][0][1], res[mode][0][1]), mode
         assert np.array_equal(res["default"][1], res[mode][1]), mode
+
+
+def test_truncated_adagrad_unstaged_ring_fp32_k8(bb, monkeypatch):
+    """fp32, K = 8, TruncatedADAGrad: the ring slot no longer fits the fused step kernel's shared-memory stage
+    (three CTAs per SM), so the update epilogue reads it from global memory (L2-prefetched at tile start).
+    Must agree with the two-kernel path (ring staged) up to fp32 reduction order, and follow the oracle."""
+    from oracle import advi_ref
+    model, K, n_steps = "fitness_normal", 8, 6
+    res = {}
+    for mode in ("fused", "unfused"):
+        if mode == "unfused":
+            monkeypatch.setenv("BB_NO_FUSE", "1")
+        else:
+            monkeypatch.delenv("BB_NO_FUSE", raising=False)
+        da, eng = _setup(bb, model, K, "f32")
+        eng.init_params(5)
+        mu0, om0 = eng.get_params()
+        eng.set_optimizer("truncated", eta=0.1, tau=1.0, n=3)
+        eng.step(n_steps)
+        res[mode] = eng.get_params()
+        eng.close()
+    assert rel_err(res["fused"][0], res["unfused"][0]) < 2e-4 and rel_err(res["fused"][1], res["unfused"][1]) < 2e-4
+    tr = advi_ref.advi_run(model, oracle_problem(da, model), n_steps, K, advi_ref.TruncatedADAGrad(0.1, 1.0, 3),
+                           mu0, om0, seed=1234)
+    assert rel_err(res["fused"][0], tr.mu) < 2e-3 and rel_err(res["fused"][1], tr.omega) < 2e-3
