@@ -321,6 +321,7 @@ template <typename real> struct HyperArgs {
     const int *csr_off;          // [H+1]
     const int *csr_mem;          // contribution slots (e * cpad + c)
     const vec2<real> *hcontrib;  // [E][cpad]
+    vec2<real> *hsum;            // [H] member sums from hyper_gather_kernel, or nullptr (hyper_update gathers itself)
     const real *dump_hcontrib;   // [K][E * cpad] per-sample contributions or nullptr
     long long dump_stride;       // E * cpad
     real *dump;                  // [K][H] per-sample d log pi / d theta or nullptr
@@ -344,6 +345,25 @@ __global__ void __launch_bounds__(BLOCK) hyper_prep_kernel(const HyperArgs<real>
     }
 }
 
+// Genotype-style hierarchies (few hyper latents, ~100 member columns each): one WARP per hyper latent gathers
+// the member contributions -- lane l takes members l, l + 32, ... in order, then a fixed butterfly -- instead of
+// one thread walking ~100 dependent (index, value) load pairs.  Deterministic; used when the mean member count
+// is >= 8 (the replicate models, 2-3 members each, keep the in-thread loop of hyper_update_kernel).
+template <typename real>
+__global__ void __launch_bounds__(BLOCK) hyper_gather_kernel(const HyperArgs<real> a) {
+    const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (h >= a.H) return;
+    const int m0 = a.csr_off[h], m1 = a.csr_off[h + 1];
+    real sg = real(0), sge = real(0);
+    for (int m = m0 + lane; m < m1; m += 32) {
+        const vec2<real> cb = a.hcontrib[a.csr_mem[m]];
+        sg += cb.x; sge += cb.y;
+    }
+    sg = warp_sum<real>(sg);
+    sge = warp_sum<real>(sge);
+    if (lane == 0) a.hsum[h] = mk2<real>(sg, sge);
+}
+
 template <typename real>
 __global__ void __launch_bounds__(BLOCK) hyper_update_kernel(const HyperArgs<real> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -359,9 +379,14 @@ __global__ void __launch_bounds__(BLOCK) hyper_update_kernel(const HyperArgs<rea
         const vec2<real> pr = a.hy_pr[h];
         real sg = real(0), sge = real(0);
         const int m0 = a.csr_off[h], m1 = a.csr_off[h + 1];
-        for (int m = m0; m < m1; ++m) {                       // fixed member order -> deterministic
-            const vec2<real> cb = a.hcontrib[a.csr_mem[m]];
-            sg += cb.x; sge += cb.y;
+        if (a.hsum) {                                         // gathered by hyper_gather_kernel (many members)
+            const vec2<real> hs = a.hsum[h];
+            sg = hs.x; sge = hs.y;
+        } else {
+            for (int m = m0; m < m1; ++m) {                   // fixed member order -> deterministic
+                const vec2<real> cb = a.hcontrib[a.csr_mem[m]];
+                sg += cb.x; sge += cb.y;
+            }
         }
         for (int k = 0; k < a.K; ++k) {
             const vec2<real> ze = a.zeps[(size_t)k * a.H + h];

@@ -208,7 +208,7 @@ template <typename real> class Engine : public EngineBase {
     DBuf<uint32_t> col_id_;
     DBuf<double> part_, sums_, epart_, hy_epart_, elbo_sh_, elbo_out_, sh_scratch_;
     DBuf<real> ctx_;
-    DBuf<r2> zeps_, hcontrib_;
+    DBuf<r2> zeps_, hcontrib_, hsum_;
     // parity / gradient outputs
     DBuf<real> sup_lam_, sup_bc_, sup_hy_, dump_lam_, dump_bc_, dump_hy_, dump_hc_;
     DBuf<double> sup_sh_, dump_sh_, hostvec_a_, hostvec_b_;
@@ -780,6 +780,13 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
     }
     if (tev_pos_ >= 0) BB_CUDA(cudaEventRecord(tev_[tev_pos_++], stream_));
     if (L.hier && L.H > 0) {
+        // many members per hyper latent (genotypes): warp-per-latent gather first
+        if (!m.dump && csr_mem_.n >= (size_t)8 * L.H) {
+            hsum_.ensure((size_t)L.H);
+            ha.hsum = hsum_.p;
+            hyper_gather_kernel<real><<<cdiv((long long)L.H * 32, BLOCK), BLOCK, 0, stream_>>>(ha);
+            ++launches;
+        }
         hyper_update_kernel<real><<<hyblocks_, BLOCK, (size_t)(L.K + 1) * BLOCK * sizeof(double), stream_>>>(ha);
         ++launches;
     }

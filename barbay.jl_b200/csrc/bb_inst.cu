@@ -19,6 +19,11 @@ namespace bb {
 namespace {
 struct Registrar {
     Registrar() {
+#if BB_NE_SEL > 1
+        // multi-environment production kernels with a compile-time number of environments (no caller-supplied
+        // noise, no hierarchy): the runtime-E kernels size their per-environment state for 8 environments and spill
+        register_kernels<BB_REAL>(BB_NT, BB_NE_SEL, false, false, make_kernel_set<BB_REAL, BB_NT, BB_NE_SEL, false, false>());
+#else
 #if BB_NE_SEL != 0
         register_kernels<BB_REAL>(BB_NT, 1, false, false, make_kernel_set<BB_REAL, BB_NT, 1, false, false>());
         register_kernels<BB_REAL>(BB_NT, 1, false, true, make_kernel_set<BB_REAL, BB_NT, 1, false, true>());
@@ -30,6 +35,7 @@ struct Registrar {
         register_kernels<BB_REAL>(BB_NT, 0, false, true, make_kernel_set<BB_REAL, BB_NT, 0, false, true>());
         register_kernels<BB_REAL>(BB_NT, 0, true, false, make_kernel_set<BB_REAL, BB_NT, 0, true, false>());
         register_kernels<BB_REAL>(BB_NT, 0, true, true, make_kernel_set<BB_REAL, BB_NT, 0, true, true>());
+#endif
 #endif
     }
 } registrar_instance;

@@ -572,7 +572,10 @@ __device__ __forceinline__ void finish_latent(const OptArgsT<real> &o, real invK
 // written exactly once per ADVI step (non-hierarchical models; the hyper latents of the hierarchical
 // ones are only known after every member column has been processed).
 template <typename real, int NT, int NE, bool HIER, bool SUP, bool ELBO, bool FUSE = false>
-__global__ void __launch_bounds__(BLOCK, FUSE ? BB_FUSE_MIN_BLOCKS : BB_P2_MIN_BLOCKS) pass2_kernel(const P2Args<real> a) {
+// register budget: 6 CTAs per SM (80 registers) for the one-environment kernels; the runtime-environment
+// kernels carry up to 8 x (s, log sigma[, log tau]) per column and would spill kilobytes at 80 -> 3 CTAs (168)
+__global__ void __launch_bounds__(BLOCK, FUSE ? BB_FUSE_MIN_BLOCKS : (NE == 1 ? BB_P2_MIN_BLOCKS : 3))
+pass2_kernel(const P2Args<real> a) {
     using S = Shape<NT, NE, HIER>;
     using r2 = vec2<real>;
     extern __shared__ __align__(16) unsigned char smem_all2[];

@@ -22,7 +22,7 @@ template <typename real> void register_kernels(int nt, int ne, bool hier, bool s
 
 template <typename real> bool lookup_kernels(int nt, int ne, bool hier, bool sup, KernelSet<real> *out) {
     const int try_nt[2] = {nt, 0};
-    const int try_ne[2] = {ne == 1 ? 1 : 0, 0};
+    const int try_ne[2] = {ne, 0};        // exact environment count if compiled, else the runtime-E kernels
     for (int a : try_nt)
         for (int b : try_ne)
             for (const auto &e : Registry<real>::entries())
