@@ -373,21 +373,32 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
             }
             const int nclass = seg.neutral ? nt : nt + nj;
 
-#pragma unroll kP1Unroll
-            for (int k = kc0; k < kc1; ++k) {
-                real eps[S::MAXC];
-                column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, strig,
-                                                 a.sup, c, cpad, C.tmax, C.nj);
-                real zth[S::MAXE];
+            // hierarchical models: the hyper latent's draw of sample k + 1 is loaded while sample k is computed
+            // (an L2 round trip per sample otherwise sits on the critical path of every warp)
+            real zth_nxt[S::MAXE];
+            auto load_zth = [&](int k) {
                 if constexpr (HIER) {
                     if (!seg.neutral) {
 #pragma unroll
                         for (int e = 0; e < S::MAXE; ++e) {
                             if (e >= ne) break;
-                            zth[e] = a.hy_zeps[(size_t)k * a.H + hbase + e].x;
+                            zth_nxt[e] = a.hy_zeps[(size_t)k * a.H + hbase + e].x;
                         }
                     }
                 }
+            };
+            load_zth(kc0);
+#pragma unroll kP1Unroll
+            for (int k = kc0; k < kc1; ++k) {
+                real zth[S::MAXE];
+                if constexpr (HIER) {
+#pragma unroll
+                    for (int e = 0; e < S::MAXE; ++e) zth[e] = zth_nxt[e];
+                    if (k + 1 < kc1) load_zth(k + 1);
+                }
+                real eps[S::MAXC];
+                column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, strig,
+                                                 a.sup, c, cpad, C.tmax, C.nj);
                 pass1_sample<real, NT, NE, HIER>(eps, mu, sg, mub, sgb, zth, seg.neutral, nt, ne, a.env_of_t,
                                                  sacc + (size_t)(k - kc0) * pva * BLOCK + (PAIRS ? 2 * tid : tid));
             }
@@ -800,8 +811,28 @@ pass2_kernel(const P2Args<real> a) {
         // the K samples; instantiated twice so the common vector-prior case carries no per-latent prior loads
         auto sample_loop = [&](auto matpr_tag) {
         constexpr bool MATPR = decltype(matpr_tag)::value;
+        // hierarchical models: (z, eps) of the hyper latent for sample k + 1 is loaded while sample k is computed
+        r2 hz_nxt[S::MAXE];
+        auto load_hz = [&](int k) {
+            if constexpr (HIER) {
+                if (!seg.neutral) {
+#pragma unroll
+                    for (int e = 0; e < S::MAXE; ++e) {
+                        if (e >= ne) break;
+                        hz_nxt[e] = a.hy_zeps[(size_t)k * a.H + hbase + e];
+                    }
+                }
+            }
+        };
+        load_hz(0);
 #pragma unroll(FUSE ? kFuseUnroll : kP2Unroll)
         for (int k = 0; k < a.K; ++k) {
+            r2 hz_cur[S::MAXE];
+            if constexpr (HIER) {
+#pragma unroll
+                for (int e = 0; e < S::MAXE; ++e) hz_cur[e] = hz_nxt[e];
+                if (k + 1 < a.K) load_hz(k + 1);
+            }
             real eps[S::MAXC];
             column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, strig, a.sup,
                                              c, cpad, C.tmax, C.nj);
@@ -856,7 +887,7 @@ pass2_kernel(const P2Args<real> a) {
                 for (int e = 0; e < S::MAXE; ++e) {
                     if (e >= ne) break;
                     if constexpr (HIER) {
-                        const r2 hz = a.hy_zeps[(size_t)k * a.H + hbase + e];
+                        const r2 hz = hz_cur[e];
                         extau[e] = bb_exp(zb[3 * e + 1]);
                         zs[e] = fma(extau[e], zb[3 * e], hz.x);
                         epsth[e] = hz.y;
