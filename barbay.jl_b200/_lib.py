@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # BB_LIB_PATH: tuning builds of the same library (development only)
 LIB_PATH = os.environ.get("BB_LIB_PATH") or os.path.join(_HERE, "libbarbay_b200.so")
@@ -46,7 +46,7 @@ class bb_desc(C.Structure):
         ("s_pop_prior", bb_prior), ("logsig_pop_prior", bb_prior), ("s_bc_prior", bb_prior),
         ("logsig_bc_prior", bb_prior), ("loglam_prior", bb_prior), ("logtau_prior", bb_prior),
         ("ragged_as_written", C.c_int32), ("n_samples", C.c_int32), ("seed", C.c_uint64),
-        ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+        ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("n_devices", C.c_int32),
     ]
 
 
@@ -78,6 +78,8 @@ SYMBOLS = [
     ("bb_launch_count", C.c_int64, [_P]),
     ("bb_algorithmic_bytes_per_step", C.c_double, [_P]),
     ("bb_time_steps", C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    ("bb_persist_stats", C.c_int, [_P, _D]),
+    ("bb_data_plane", C.c_int, [_P, C.POINTER(C.c_int32)]),
     ("bb_comm_unique_id", C.c_int, [C.c_char * 128]),
     ("bb_comm_init", C.c_int, [_P, C.c_char * 128]),
 ]

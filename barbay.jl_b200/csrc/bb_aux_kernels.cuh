@@ -17,6 +17,7 @@ struct ReduceArgs {
     int w_single;            // E == 1: mutant W stored once (slot 2nt-1)
     unsigned rep_mask;       // replicates belonging to this launch group (bit r)
     const double *part;      // [K][pv][nblk]
+    const double *xpart;     // step kernel (bb_step_kernel.cuh): [nblk][K * NQ * tmax] in output space, or nullptr
     double *sums;
 };
 
@@ -31,6 +32,14 @@ __device__ __forceinline__ void reduce_rows(const ReduceArgs &a, int R) {
     if (t >= (q == Q_LAM ? nt : nt - 1)) return;
     if (!((a.rep_mask >> r) & 1u)) return;      // replicate handled by another launch group (ragged T)
     double s = 0.0;
+    if (a.xpart) {
+        // the step kernel's blocks write output-space vectors (R == 1): plain fixed-order sum over the blocks
+        const int P = a.K * NQ * a.tmax;
+        for (int b = lane; b < a.nblk; b += 32) s += a.xpart[(size_t)b * P + warp];
+        s = warp_sum<double>(s);
+        if (lane == 0) a.sums[warp] = s;
+        return;
+    }
     for (int si = 0; si < a.segs.nseg; ++si) {
         const Seg &sg = a.segs.seg[si];
         if (sg.rep != r) continue;
@@ -116,7 +125,13 @@ template <typename real> struct SharedArgs {
     double n_neutral;             // N over all shards
     double *sums;                 // all-reduced (NCCL), or this rank's partials to be completed by `xchg`
     XchgWaitArgs xchg;
-    double2 *sh_th, *sh_acc, *sh_ring;   // [2 nst] (s-bar block, then log-sigma-bar block); ring [n][2 nst]
+    double2 *sh_th, *sh_acc;      // [2 nst] (s-bar block, then log-sigma-bar block)
+    // TruncatedADAGrad ring of the shared latents, n + 1 slots of [2 nst]: step s evicts slot (s + 1) % (n + 1)
+    // (= the g^2 of step s - n) and writes slot s % (n + 1).  Read and write never share a slot, so the CTAs of
+    // the persistent step kernel can all read while one of them (ring_writer) writes.
+    const double2 *sh_ring_rd;
+    double2 *sh_ring_wr;
+    int ring_writer;
     const double2 *sh_pr;         // (mean, 1/var)
     PhiloxKey key;
     uint32_t step;
@@ -224,12 +239,12 @@ __device__ __forceinline__ void shared_body(const SharedArgs<real> &a, double *s
         if (a.opt.update) {
             double2 ac = a.sh_acc[i];
             double2 rg = make_double2(0.0, 0.0);
-            double2 *rp = a.opt.kind == 0 ? a.sh_ring + i : nullptr;   // sh_ring: this step's slot
-            if (rp) rg = *rp;
+            const bool trunc = a.opt.kind == 0;
+            if (trunc) rg = __ldcg(a.sh_ring_rd + i);                  // the slot evicted this step
             opt_apply<double>(a.opt, -gm, th.x, ac.x, rg.x);
             opt_apply<double>(a.opt, -go, th.y, ac.y, rg.y);
             a.sh_th[i] = th; a.sh_acc[i] = ac;
-            if (rp) *rp = rg;
+            if (trunc && a.ring_writer) a.sh_ring_wr[i] = rg;
         } else if (a.gout) {
             a.gout[i] = make_double2(gm, go);
         }
@@ -252,6 +267,16 @@ __device__ __forceinline__ void shared_body(const SharedArgs<real> &a, double *s
 template <typename real>
 __global__ void __launch_bounds__(256) shared_kernel(const SharedArgs<real> a) {
     shared_body<real>(a, a.sums, a.scratch, true);
+}
+
+// noise of the shared latents for `nsteps` consecutive steps (what shared_phase0 would draw at each of them):
+// out[(j * K + k) * n2 + i] for step step0 + j.  The persistent step kernel reads it instead of running the fp64
+// Box-Muller on every CTA's critical path.
+static __global__ void shared_noise_steps_kernel(const PhiloxKey key, uint32_t step0, int nsteps, int K, int n2, double *out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nsteps * K * n2) return;
+    const int i = idx % n2, k = (idx / n2) % K, j = idx / (n2 * K);
+    out[idx] = stream_normal<double>(STREAM_SHARED, (uint32_t)i, (uint32_t)k, step0 + (uint32_t)j, key);
 }
 
 // ------------------------------------------------------------------ merged step tail

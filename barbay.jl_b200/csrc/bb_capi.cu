@@ -2,10 +2,11 @@
 // records the message for bb_last_error() and returns a non-zero code: there is no
 // CPU fallback -- without a B200 and this library the path fails loudly.
 #include <cstring>
+#include <memory>
 #include <string>
 
 #include "../../include/barbay_b200.h"
-#include "bb_engine.cuh"
+#include "bb_multi.cuh"
 
 struct bb_handle {
     bb::EngineBase *eng = nullptr;
@@ -15,9 +16,21 @@ struct bb_handle {
 namespace {
 thread_local std::string g_create_error;
 
+// the caller's current device is left as it was found: a handle runs on ITS device whatever is current
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (dev < 0) return;
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 template <typename F> int guarded(bb_handle *h, F &&f) {
     if (!h || !h->eng) return 2;
     try {
+        DeviceGuard g(h->eng->home_device);
         f(*h->eng);
         h->err.clear();
         return 0;
@@ -42,9 +55,18 @@ int bb_create(const bb_desc *desc, bb_handle **out) {
         if (ce != cudaSuccess || ndev == 0)
             throw std::runtime_error(std::string("no CUDA device available (") + cudaGetErrorString(ce) +
                                      "); barbay_b200 has no CPU fallback");
-        bb_handle *h = new bb_handle;
-        h->eng = desc->dtype == BB_F64 ? bb::make_engine_f64(*desc) : bb::make_engine_f32(*desc);
-        *out = h;
+        int prev_dev = -1;
+        cudaGetDevice(&prev_dev);
+        struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
+        std::unique_ptr<bb_handle> h(new bb_handle);
+        if (desc->n_devices > 1) {
+            if (desc->rank != 0 || desc->world != 1)
+                throw std::runtime_error("n_devices > 1 shards inside the library: rank / world must be 0 / 1");
+            h->eng = desc->dtype == BB_F64 ? bb::make_multi_engine_f64(*desc) : bb::make_multi_engine_f32(*desc);
+        } else {
+            h->eng = desc->dtype == BB_F64 ? bb::make_engine_f64(*desc) : bb::make_engine_f32(*desc);
+        }
+        *out = h.release();
         g_create_error.clear();
         return 0;
     } catch (const std::exception &e) {
@@ -56,6 +78,7 @@ int bb_create(const bb_desc *desc, bb_handle **out) {
 
 void bb_destroy(bb_handle *h) {
     if (!h) return;
+    DeviceGuard g(h->eng ? h->eng->home_device : -1);
     delete h->eng;
     delete h;
 }
@@ -130,6 +153,18 @@ int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_pass
     return guarded(h, [&](bb::EngineBase &e) {
         if (n_steps < 1 || !ms_total) throw std::runtime_error("bb_time_steps: bad arguments");
         e.time_steps(n_steps, ms_total, ms_pass1, ms_pass2);
+    });
+}
+int bb_persist_stats(bb_handle *h, double out[5]) {
+    return guarded(h, [&](bb::EngineBase &e) {
+        if (!out) throw std::runtime_error("bb_persist_stats: NULL argument");
+        e.persist_stats(out);
+    });
+}
+int bb_data_plane(bb_handle *h, int32_t out[4]) {
+    return guarded(h, [&](bb::EngineBase &e) {
+        if (!out) throw std::runtime_error("bb_data_plane: NULL argument");
+        e.data_plane(out);
     });
 }
 int bb_comm_unique_id(char id[128]) {

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,7 +15,7 @@
 #include <string>
 #include <vector>
 
-#include "bb_aux_kernels.cuh"
+#include "bb_kernel_set.cuh"
 #include "bb_layout.h"
 
 namespace bb {
@@ -110,6 +111,12 @@ class EngineBase {
     virtual void sync() = 0;
     virtual void time_steps(int n, float *ms_total, float *ms_pass1, float *ms_pass2) = 0;
     virtual void comm_init(const char id[128]) = 0;
+    // persistent step kernel: cycles of CTA 0 in {column phase, arrive -> sums, sums -> context} and the number of
+    // in-kernel tails, summed since the last call (then reset); out[4] = SM clock in kHz
+    virtual void persist_stats(double out[5]) = 0;
+    // out = {packed step kernel in use, steps per persistent launch (0: off), peer-memory exchange on, NCCL communicator present}
+    virtual void data_plane(int32_t out[4]) = 0;
+    int home_device = -1;      // CUDA ordinal every call of a single-GPU handle runs on (-1: the handle sets devices itself)
     long long launches = 0;
     long long step_count = 0;
     double alg_bytes = 0.0;
@@ -117,6 +124,8 @@ class EngineBase {
 
 EngineBase *make_engine_f32(const bb_desc &d);
 EngineBase *make_engine_f64(const bb_desc &d);
+EngineBase *make_multi_engine_f32(const bb_desc &d);      // bb_multi.cuh: one handle, n_devices GPUs
+EngineBase *make_multi_engine_f64(const bb_desc &d);
 
 // =====================================================================================
 template <typename real> class Engine : public EngineBase {
@@ -141,6 +150,20 @@ template <typename real> class Engine : public EngineBase {
     void sync() override { BB_CUDA(cudaStreamSynchronize(stream_)); }
     void time_steps(int n, float *ms_total, float *ms_pass1, float *ms_pass2) override;
     void comm_init(const char id[128]) override;
+    void persist_stats(double out[5]) override;
+    void data_plane(int32_t out[4]) override {
+        out[0] = stepk_ok_ ? 1 : 0;
+        out[1] = (stepk_ok_ && persist_chunk_ > 1 && !(comm_ && !xchg_on_)) ? persist_chunk_ : 0;
+        out[2] = xchg_on_ ? 1 : 0;
+        out[3] = comm_ ? 1 : 0;
+    }
+    // single-process multi-GPU (bb_multi.cuh): exchange buffers of all devices of the handle, peer access enabled
+    void *xchg_local() const { return xchg_mem_; }
+    void attach_peers(const std::vector<void *> &bufs);
+    void finish_elbo_partial(double *out);          // [K + 1] this shard's ELBO partial sums (no collective)
+    int device() const { return device_; }
+    void set_raw_elbo(bool on) { raw_elbo_ = on; }
+    void alloc_exchange() { alloc_xchg(); }
 
   private:
     struct Group {                 // replicates sharing one T: one launch of each column kernel
@@ -154,6 +177,13 @@ template <typename real> class Engine : public EngineBase {
         int p1nbuf = 2, p2nbuf = 2, p2stage_acc = 1, p2stage_ring = 1;
         size_t fsmem = 0;          // fused step kernel: pass-2 staging + pass-1 accumulators
         int facc_slots = 0;        // 0: the fused kernel is not available for this group
+        // packed / persistent step kernel (bb_step_kernel.cuh); stepk == nullptr: not available for this shape
+        StepKernelFn<real> stepk = nullptr;
+        int step_w = 1, step_acc_rows = 0, step_stage_ring = 0, step_occ = 0;
+        size_t step_smem = 0;
+        SegList stsegs;
+        int stblocks = 0;
+        bool step_persist = false; // the in-kernel tail's scratch fits behind the flushed accumulators
         size_t part_off = 0, epart_off = 0;     // block offsets into part_ / epart_
     };
     struct RunMode {
@@ -166,6 +196,9 @@ template <typename real> class Engine : public EngineBase {
         uint32_t step = 0;
         bool fuse = false;         // pass 2 also accumulates the next step's pass-1 partials
         bool have_part = false;    // this step's partials were produced by the previous fused kernel
+        bool stepk = false;        // the fused kernel is the packed step kernel (partials in xpart_, output space)
+        bool have_xpart = false;   // this step's partials sit in xpart_
+        int nsteps = 1;            // > 1: persistent step kernel covering this many steps
     };
 
     void build_groups();
@@ -174,7 +207,7 @@ template <typename real> class Engine : public EngineBase {
     void run_pipeline(const RunMode &m);
     void upload_supplied(const double *x, int K);
     void ensure_supplied(bool dump);
-    ColArrays<real> col_arrays() const;
+    ColArrays<real> col_arrays(bool ring_base = false) const;
     template <typename T> OptArgsT<T> opt_args(bool update) const {
         OptArgsT<T> o;
         o.kind = opt_.kind; o.update = update ? 1 : 0;
@@ -193,7 +226,15 @@ template <typename real> class Engine : public EngineBase {
     bool opt_ready_ = false;
     int ring_slot_ = 0;
     bool fused_ok_ = false;        // every launch group has a fused step kernel that fits
-    long long part_step_ = -1;     // step whose pass-1 partials already sit in part_ (fused layout), or -1
+    long long part_step_ = -1;     // step whose pass-1 partials already sit in part_ (fused layout) / xpart_, or -1
+    bool part_is_x_ = false;       // ... in xpart_ (written by the step kernel)
+    bool stepk_ok_ = false;        // every launch group (there is one: R == 1) has a step kernel that fits
+    int persist_chunk_ = 0;        // steps per persistent launch (0: persistent mode off)
+    DBuf<double> xpart_, gpart_, eps_steps_;
+    DBuf<StepSync> step_sync_;
+    int step_gsize_ = 32;
+    void alloc_xchg();
+    void check_step_sync();
     std::vector<Group> groups_;
     int p1blocks_total_ = 0, p2blocks_total_ = 0, hyblocks_ = 0;
 
@@ -218,6 +259,8 @@ template <typename real> class Engine : public EngineBase {
     NcclApi::Comm comm_ = nullptr;
     // peer-memory exchange (see bb_aux_kernels.cuh): local buffer + IPC-mapped peer buffers
     bool xchg_on_ = false;
+    bool raw_elbo_ = false;        // ELBO / log-density values without their constants (summed by a multi-GPU owner)
+    bool peers_local_ = false;     // peer buffers are plain peer-access pointers of this process (not IPC mappings)
     unsigned long long xchg_seq_ = 0;
     void *xchg_mem_ = nullptr;
     std::vector<void *> xchg_peer_mem_;
@@ -236,6 +279,7 @@ template <typename real> Engine<real>::Engine(const bb_desc &d) {
     seed_ = d.seed;
     if (d.device >= 0) BB_CUDA(cudaSetDevice(d.device));
     BB_CUDA(cudaGetDevice(&device_));
+    home_device = device_;
     cudaDeviceProp prop;
     BB_CUDA(cudaGetDeviceProperties(&prop, device_));
     if (prop.major != 10)
@@ -311,7 +355,7 @@ template <typename real> Engine<real>::Engine(const bb_desc &d) {
 }
 
 template <typename real> Engine<real>::~Engine() {
-    for (size_t r = 0; r < xchg_peer_mem_.size(); ++r)
+    for (size_t r = 0; r < xchg_peer_mem_.size() && !peers_local_; ++r)
         if (xchg_peer_mem_[r] && (int)r != L.rank) cudaIpcCloseMemHandle(xchg_peer_mem_[r]);
     if (xchg_mem_) cudaFree(xchg_mem_);
     if (comm_) NcclApi::get().CommDestroy(comm_);
@@ -441,6 +485,44 @@ template <typename real> void Engine<real>::size_pass2() {
             plan(0);
             if (!g.facc_slots) plan(nrg);          // no fused kernel either way: keep the ring staged
         }
+        // ---- packed step kernel (bb_step_kernel.cuh): non-hierarchical models, compile-time T and E
+        g.stepk = nullptr;
+        if (!L.hier && L.R == 1 && !getenv("BB_NO_STEPK")) {
+            const int W = (L.K % 2 == 0) ? 2 : 1;
+            StepKernelFn<real> fn = W == 2 ? g.ks.step_w2 : g.ks.step_w1;
+            if (fn) {
+                auto r128 = [](size_t b) { return (b + 127) / 128 * 128; };
+                const int NJ = 2 * L.E, ROWS = g.nt + NJ, npack = L.K / W;
+                const size_t thb = (size_t)ROWS * BLOCK * sizeof(r2), cnb = (size_t)g.nt * BLOCK * sizeof(int);
+                const int pvs_m = L.E == 1 ? 2 * g.nt : 3 * g.nt - 2, pvs_n = 3 * g.nt - 2;
+                const int rows = std::max(npack * ((pvs_m + 1) / 2), (pvs_n + 1) / 2);
+                const size_t spb = (size_t)2 * W * sizeof(real);        // one SlotPair
+                const size_t head = 64 + r128((size_t)npack * 3 * g.nt * W * sizeof(real)) +
+                                    r128((size_t)L.K * 3 * g.nt * sizeof(real)) + r128((size_t)4 * (g.nt - 1) * sizeof(double2));
+                auto total = [&](int stage_ring) {
+                    return head + 2 * ((1 + npr) * thb + cnb) + (size_t)(1 + stage_ring) * thb + (size_t)rows * BLOCK * spb;
+                };
+                const int min_occ = getenv("BB_STEPK_MIN_OCC") ? atoi(getenv("BB_STEPK_MIN_OCC")) : 3;
+                for (int stage_ring = nrg; stage_ring >= 0; --stage_ring) {
+                    const size_t sm = total(stage_ring);
+                    if (sm > kMaxSmem) continue;
+                    BB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                    int occ = 0;
+                    BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, BLOCK, sm));
+                    if (occ >= min_occ) {
+                        g.stepk = fn; g.step_w = W; g.step_acc_rows = rows; g.step_stage_ring = stage_ring;
+                        g.step_occ = occ; g.step_smem = sm;
+                        break;
+                    }
+                }
+                if (g.stepk) {
+                    assign_blocks(g.stsegs, g.nt, nsm_ * g.step_occ, &g.stblocks);
+                    // scratch of the in-kernel tail (totals + shared_body's working arrays) aliases the accumulators
+                    const size_t tail_d = sums_.n + sh_scratch_.n;
+                    g.step_persist = tail_d * sizeof(double) <= (size_t)rows * BLOCK * spb && (int)sums_.n <= 4096;
+                }
+            }
+        }
         BB_CUDA(cudaFuncSetAttribute((const void *)g.ks.pass2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)g.p2smem));
         for (auto *fn : {(const void *)g.ks.pass2_elbo, (const void *)g.ks_sup.pass2_elbo})
@@ -459,10 +541,33 @@ template <typename real> void Engine<real>::size_pass2() {
     part_.alloc((size_t)std::max(p1blocks_total_, p2blocks_total_) * L.K * (3 * L.tmax));
     fused_ok_ = !L.hier;
     for (Group &g : groups_) fused_ok_ = fused_ok_ && g.facc_slots > 0;
+    stepk_ok_ = !L.hier && groups_.size() == 1 && groups_[0].stepk != nullptr;
+    persist_chunk_ = 0;
+    if (stepk_ok_) {
+        Group &g = groups_[0];
+        xpart_.alloc((size_t)g.stblocks * sums_.n);
+        // persistent mode: default on for multi-GPU shards (the small-shard / strong-scaling path); BB_PERSIST overrides
+        int coop = 0;
+        BB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
+        const char *pe = getenv("BB_PERSIST");
+        int want = pe ? atoi(pe) : 256;
+        if (!coop || !g.step_persist) want = 0;
+        if (L.world > 1 && !xchg_on_) want = 0;
+        if (want > 1) {
+            persist_chunk_ = want;
+            step_gsize_ = 32;
+            while (cdiv(g.stblocks, step_gsize_) > 64) step_gsize_ *= 2;
+            gpart_.alloc((size_t)cdiv(g.stblocks, step_gsize_) * sums_.n);
+            if (!step_sync_.p) step_sync_.alloc(1);
+            eps_steps_.alloc((size_t)persist_chunk_ * L.K * 2 * L.nst);
+            alloc_xchg();
+            if (xchg_peer_mem_.empty() && L.world == 1) xchg_peer_mem_.assign(1, xchg_mem_);
+        }
+    }
     part_step_ = -1;
 }
 
-template <typename real> ColArrays<real> Engine<real>::col_arrays() const {
+template <typename real> ColArrays<real> Engine<real>::col_arrays(bool ring_base) const {
     ColArrays<real> C;
     C.cpad = L.cpad; C.tmax = L.tmax; C.nj = L.nj;
     C.lam_th = lam_th_.p; C.lam_acc = lam_acc_.p; C.cnt = cnt_.p;
@@ -472,8 +577,9 @@ template <typename real> ColArrays<real> Engine<real>::col_arrays() const {
     for (int k = 0; k < 3; ++k) C.bc_pr_s[k] = r2{(real)L.pr_bc_s[k][0], (real)L.pr_bc_s[k][1]};
     C.hgroup = hgroup_.p; C.col_id = col_id_.p;
     // the rings are [n][...]: hand the kernels this step's slot
-    C.lam_ring = lam_ring_.p ? lam_ring_.p + (size_t)ring_slot_ * L.tmax * L.cpad : nullptr;
-    C.bc_ring = bc_ring_.p ? bc_ring_.p + (size_t)ring_slot_ * L.nj * L.cpad : nullptr;
+    const int slot = ring_base ? 0 : ring_slot_;
+    C.lam_ring = lam_ring_.p ? lam_ring_.p + (size_t)slot * L.tmax * L.cpad : nullptr;
+    C.bc_ring = bc_ring_.p ? bc_ring_.p + (size_t)slot * L.nj * L.cpad : nullptr;
     return C;
 }
 
@@ -572,7 +678,7 @@ template <typename real> void Engine<real>::set_optimizer(const bb_opt &o) {
     if (o.kind == BB_OPT_TRUNCATED_ADAGRAD) {
         lam_ring_.alloc(nlam * o.n); bc_ring_.alloc(nbc * o.n);
         if (L.hier) hy_ring_.alloc(nhy * o.n);
-        sh_ring_.alloc(nsh * o.n);
+        sh_ring_.alloc(nsh * ((size_t)o.n + 1));     // n + 1 slots: see SharedArgs (bb_aux_kernels.cuh)
         BB_CUDA(cudaMemsetAsync(lam_acc_.p, 0, sizeof(r2) * nlam, stream_));
         BB_CUDA(cudaMemsetAsync(bc_acc_.p, 0, sizeof(r2) * nbc, stream_));
         if (nhy) BB_CUDA(cudaMemsetAsync(hy_acc_.p, 0, sizeof(r2) * nhy, stream_));
@@ -665,12 +771,15 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
     // kernel with its working arrays in shared memory (tail_kernel); otherwise the separate kernels
     const int nwarps = L.R * L.K * NQ * L.tmax;
     const size_t tail_smem = (sums_.n + sh_scratch_.n) * sizeof(double);
+    if (L.world > 1 && !comm_ && !xchg_on_)
+        throw std::runtime_error("this handle is shard " + std::to_string(L.rank) + " of " + std::to_string(L.world) +
+                                 ": call bb_comm_init before any evaluation (the step's sums must be combined)");
     const bool use_tail = groups_.size() == 1 && !(comm_ && !xchg_on_) && tail_smem <= 40 * 1024 && !getenv("BB_NO_TAIL");
     ReduceArgs ra{};
     for (Group &g : groups_) {
         // partial sums of this step: from the previous fused kernel (its grid / segment split), or pass 1 now
         double *gpart = part_.p + (size_t)(m.have_part ? g.epart_off : g.part_off) * L.K * (3 * L.tmax);
-        if (!m.have_part) {
+        if (!m.have_part && !m.have_xpart) {
             P1Args<real> a{};
             a.segs = g.p1segs; a.cols = C; a.K = L.K; a.acc_slots = g.kchunk; a.ne = L.E;
             for (int t = 0; t < MAX_NT_DYN; ++t) a.env_of_t[t] = L.env_of_t[t];
@@ -686,6 +795,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         ra.segs = m.have_part ? g.p2segs : g.p1segs; ra.K = L.K; ra.tmax = L.tmax; ra.pv = g.pv; ra.nt = g.nt;
         ra.w_single = L.E == 1 ? 1 : 0; ra.rep_mask = g.rep_mask; ra.nblk = m.have_part ? g.p2blocks : g.p1blocks;
         ra.part = gpart; ra.sums = sums_.p;
+        if (m.have_xpart) { ra.xpart = xpart_.p; ra.nblk = g.stblocks; }
         if (!use_tail) {
             reduce_kernel<<<cdiv((long long)nwarps * 32, 128), 128, 0, stream_>>>(ra, L.R);
             ++launches;
@@ -693,7 +803,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
     }
     XchgWaitArgs xw{};
     XchgPostArgs xp{};
-    if (comm_ && xchg_on_) {
+    if (xchg_on_ && L.world > 1) {
         // one-shot all-reduce over NVLink peer memory, completed inside shared_kernel
         ++xchg_seq_;
         xp.sums = sums_.p; xp.P = (int)sums_.n; xp.world = L.world; xp.rank = L.rank;
@@ -714,13 +824,19 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         if (rc != 0) throw std::runtime_error(std::string("ncclAllReduce: ") + NcclApi::get().GetErrorString(rc));
     }
     // ---- shared latents
+    SharedArgs<real> sa{};
     {
-        SharedArgs<real> sa{};
         sa.R = L.R; sa.K = L.K; sa.tmax = L.tmax; sa.nst = L.nst;
         for (int r = 0; r < L.R; ++r) { sa.nt[r] = L.nt[r]; sa.sh0[r] = L.sh0[r]; }
         sa.n_neutral = (double)L.N;
         sa.sums = sums_.p; sa.xchg = xw; sa.sh_th = sh_th_.p; sa.sh_acc = sh_acc_.p;
-        sa.sh_ring = sh_ring_.p ? sh_ring_.p + (size_t)ring_slot_ * 2 * L.nst : nullptr; sa.sh_pr = sh_pr_.p;
+        if (sh_ring_.p) {               // n + 1 slots indexed by the step itself (bb_aux_kernels.cuh)
+            const uint32_t n1 = (uint32_t)opt_.n + 1u;
+            sa.sh_ring_rd = sh_ring_.p + (size_t)((m.step + 1u) % n1) * 2 * L.nst;
+            sa.sh_ring_wr = sh_ring_.p + (size_t)(m.step % n1) * 2 * L.nst;
+        }
+        sa.ring_writer = 1;
+        sa.sh_pr = sh_pr_.p;
         sa.key = pkey; sa.step = m.step;
         sa.eps_sh = m.sup ? sup_sh_.p : nullptr; sa.z_direct = m.z_direct ? 1 : 0;
         sa.ctx = ctx_.p; sa.scratch = sh_scratch_.p;
@@ -757,7 +873,54 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         a.stage_ring = (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p && m.update && g.p2stage_ring) ? 1 : 0;
         a.l2_ring = (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p && m.update && !(a.stage_ring && g.p2stage_acc)) ? 1 : 0;
         a.stage_acc = g.p2stage_acc; a.nbuf = g.p2nbuf;
-        if (m.fuse) {
+        if (m.stepk) {
+            // the packed step kernel: one step behind the tail (programmatic dependent launch), or -- persistent,
+            // cooperative -- m.nsteps steps with the tails of steps 2.. inside the kernel
+            StepArgs<real> sk{};
+            sk.segs = g.stsegs; sk.cols = col_arrays(true); sk.K = L.K; sk.P = (int)sums_.n;
+            for (int t = 0; t < MAX_NT_DYN; ++t) sk.env_of_t[t] = L.env_of_t[t];
+            sk.key = pkey; sk.step = m.step; sk.nsteps = m.nsteps;
+            sk.ctx = ctx_.p;
+            sk.opt = opt_args<real>(true);
+            sk.stage_pr = (L.lam_pr_matrix || L.bc_pr_matrix) ? 1 : 0;
+            const bool trunc = opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p;
+            sk.stage_ring = (trunc && g.step_stage_ring) ? 1 : 0;
+            sk.l2_ring = (trunc && !g.step_stage_ring) ? 1 : 0;
+            sk.acc_rows = g.step_acc_rows;
+            sk.xpart = xpart_.p;
+            sk.ring_n = trunc ? opt_.n : 0; sk.ring_slot = ring_slot_;
+            if (m.nsteps > 1) {
+                sk.sync = step_sync_.p; sk.gpart = gpart_.p; sk.gsize = step_gsize_;
+                sk.ngroups = cdiv(g.stblocks, step_gsize_);
+                sk.xp.P = (int)sums_.n; sk.xp.world = L.world; sk.xp.rank = L.rank;
+                sk.xp.seq = xchg_seq_ + 1; sk.xp.parity = 0; sk.xp.sums = nullptr;
+                for (int r = 0; r < L.world; ++r) {
+                    sk.xp.peer_buf[r] = reinterpret_cast<double *>(xchg_peer_mem_[r]);
+                    sk.xp.peer_flag[r] = reinterpret_cast<unsigned long long *>(static_cast<char *>(xchg_peer_mem_[r]) + xchg_flag_off_);
+                }
+                sk.xbuf = reinterpret_cast<const double *>(xchg_mem_);
+                sk.xflag = reinterpret_cast<const unsigned long long *>(static_cast<char *>(xchg_mem_) + xchg_flag_off_);
+                xchg_seq_ += (unsigned long long)(m.nsteps - 1);
+                sk.sa = sa;
+                sk.sa.xchg = XchgWaitArgs{};
+                sk.sa.sh_ring_rd = sh_ring_.p; sk.sa.sh_ring_wr = sh_ring_.p;      // ring base: the kernel picks the slots
+                sk.sa.eps_sh = eps_steps_.p; sk.sa.z_direct = 0;
+                sk.sa.gout = nullptr; sk.sa.dump = nullptr; sk.sa.elbo_sh = nullptr;
+                const int ne = m.nsteps * L.K * 2 * L.nst;
+                shared_noise_steps_kernel<<<cdiv(ne, 128), 128, 0, stream_>>>(pkey, m.step, m.nsteps, L.K, 2 * L.nst, eps_steps_.p);
+                ++launches;
+                void *kargs[] = {(void *)&sk};
+                BB_CUDA(cudaLaunchCooperativeKernel((const void *)g.stepk, dim3(g.stblocks), dim3(BLOCK), kargs, g.step_smem, stream_));
+            } else {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(g.stblocks); cfg.blockDim = dim3(BLOCK); cfg.dynamicSmemBytes = g.step_smem; cfg.stream = stream_;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = getenv("BB_NO_PDL") ? 0 : 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                BB_CUDA(cudaLaunchKernelEx(&cfg, g.stepk, sk));
+            }
+        } else if (m.fuse) {
             // the reducer has consumed this step's partials (stream order): the fused kernel overwrites them
             a.part = part_.p + (size_t)g.epart_off * L.K * (3 * L.tmax);
             a.pv = g.pv; a.acc_slots = g.facc_slots;
@@ -799,6 +962,11 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
 }
 
 // ELBO from elbo_out_ (device): (1/K) sum_k (logp_k) + sum log sigma + D (1 + log 2 pi) / 2
+template <typename real> void Engine<real>::finish_elbo_partial(double *out) {
+    BB_CUDA(cudaMemcpyAsync(out, elbo_out_.p, sizeof(double) * (L.K + 1), cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaStreamSynchronize(stream_));
+}
+
 template <typename real> double Engine<real>::finish_elbo(double *logp_k) {
     std::vector<double> out(L.K + 1);
     if (comm_) {
@@ -807,13 +975,15 @@ template <typename real> double Engine<real>::finish_elbo(double *logp_k) {
     }
     BB_CUDA(cudaMemcpyAsync(out.data(), elbo_out_.p, sizeof(double) * (L.K + 1), cudaMemcpyDeviceToHost, stream_));
     BB_CUDA(cudaStreamSynchronize(stream_));
+    // raw_elbo_ (one shard of a single-process multi-GPU handle): no constants, the owner adds them once after summing
+    const double cst = raw_elbo_ ? 0.0 : L.logp_const;
     double mean = 0.0;
     for (int k = 0; k < L.K; ++k) {
-        const double lp = out[k] + L.logp_const;
+        const double lp = out[k] + cst;
         if (logp_k) logp_k[k] = lp;
         mean += lp / L.K;
     }
-    return mean + out[L.K] + 0.5 * (double)L.D * (1.0 + std::log(2.0 * M_PI));
+    return mean + out[L.K] + (raw_elbo_ ? 0.0 : 0.5 * (double)L.D * (1.0 + std::log(2.0 * M_PI)));
 }
 
 template <typename real>
@@ -900,19 +1070,36 @@ template <typename real> void Engine<real>::get_noise(long long step, double *ep
 template <typename real> void Engine<real>::step(int n, double *trace) {
     if (!opt_ready_) set_optimizer(opt_);
     if (trace) trace_.ensure((size_t)n * (L.K + 1));
-    for (int i = 0; i < n; ++i) {
+    const bool use_stepk = stepk_ok_ && trace == nullptr;
+    // persistent launches need the merged tail kernel ahead of them and, multi-GPU, the peer-memory exchange
+    const bool can_persist = use_stepk && persist_chunk_ > 1 && !(comm_ && !xchg_on_) && !getenv("BB_NO_TAIL");
+    bool persisted = false;
+    for (int i = 0; i < n;) {
         RunMode m; m.update = true; m.want_elbo = trace != nullptr; m.step = (uint32_t)step_count;
-        // software-pipelined step: pass 2 of this step also produces the partial sums of the next one
-        m.fuse = fused_ok_ && trace == nullptr;
-        m.have_part = fused_ok_ && part_step_ == step_count;
+        if (use_stepk) {
+            m.fuse = true; m.stepk = true;
+            m.have_xpart = part_step_ == step_count && part_is_x_;
+            m.have_part = part_step_ == step_count && !part_is_x_;
+            m.nsteps = can_persist ? std::min(persist_chunk_, n - i) : 1;
+            persisted = persisted || m.nsteps > 1;
+        } else {
+            // software-pipelined step: pass 2 of this step also produces the partial sums of the next one
+            m.fuse = fused_ok_ && trace == nullptr;
+            m.have_part = fused_ok_ && part_step_ == step_count && !part_is_x_;
+            m.have_xpart = part_step_ == step_count && part_is_x_;
+        }
         run_pipeline(m);
-        part_step_ = m.fuse ? step_count + 1 : -1;
+        part_step_ = m.fuse ? step_count + m.nsteps : -1;
+        part_is_x_ = m.stepk;
         if (trace)
             BB_CUDA(cudaMemcpyAsync(trace_.p + (size_t)i * (L.K + 1), elbo_out_.p, sizeof(double) * (L.K + 1),
                                     cudaMemcpyDeviceToDevice, stream_));
-        ++step_count;
+        step_count += m.nsteps;
+        i += m.nsteps;
         if (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD) ring_slot_ = (int)(step_count % opt_.n);
     }
+    // the exchange inside a kernel cannot raise a host error by itself: surface it with the call that ran the steps
+    if (persisted || (xchg_on_ && L.world > 1)) check_step_sync();
     if (trace) {
         if (comm_) {
             int rc = NcclApi::get().AllReduce(trace_.p, trace_.p, (size_t)n * (L.K + 1), kNcclFloat64, kNcclSum, comm_, stream_);
@@ -923,8 +1110,8 @@ template <typename real> void Engine<real>::step(int n, double *trace) {
         BB_CUDA(cudaStreamSynchronize(stream_));
         for (int i = 0; i < n; ++i) {
             double mean = 0.0;
-            for (int k = 0; k < L.K; ++k) mean += (h[(size_t)i * (L.K + 1) + k] + L.logp_const) / L.K;
-            trace[i] = mean + h[(size_t)i * (L.K + 1) + L.K] + 0.5 * (double)L.D * (1.0 + std::log(2.0 * M_PI));
+            for (int k = 0; k < L.K; ++k) mean += (h[(size_t)i * (L.K + 1) + k] + (raw_elbo_ ? 0.0 : L.logp_const)) / L.K;
+            trace[i] = mean + h[(size_t)i * (L.K + 1) + L.K] + (raw_elbo_ ? 0.0 : 0.5 * (double)L.D * (1.0 + std::log(2.0 * M_PI)));
         }
     }
 }
@@ -944,7 +1131,7 @@ template <typename real> void Engine<real>::time_steps(int n, float *ms_total, f
     // CUDA-event timing on the launching stream: whole region, plus per-step brackets around the
     // pass-1 and pass-2 column kernels (with ragged T the bracket spans the group launches).
     if (!opt_ready_) set_optimizer(opt_);
-    while ((int)tev_.size() < 4 * n) {
+    while ((int)tev_.size() < 4 * n + 4) {
         cudaEvent_t e;
         BB_CUDA(cudaEventCreate(&e));
         tev_.push_back(e);
@@ -954,10 +1141,11 @@ template <typename real> void Engine<real>::time_steps(int n, float *ms_total, f
     try { step(n, nullptr); } catch (...) { tev_pos_ = -1; throw; }
     BB_CUDA(cudaEventRecord(ev_[1], stream_));
     BB_CUDA(cudaEventSynchronize(ev_[1]));
-    tev_pos_ = -1;
     BB_CUDA(cudaEventElapsedTime(ms_total, ev_[0], ev_[1]));
     float p1 = 0.f, p2 = 0.f;
-    for (int i = 0; i < n; ++i) {
+    const int nbr = tev_pos_ / 4;         // one bracket set per launch sequence (a persistent launch covers many steps)
+    tev_pos_ = -1;
+    for (int i = 0; i < nbr; ++i) {
         float a = 0.f, b = 0.f;
         BB_CUDA(cudaEventElapsedTime(&a, tev_[4 * i + 0], tev_[4 * i + 1]));
         BB_CUDA(cudaEventElapsedTime(&b, tev_[4 * i + 2], tev_[4 * i + 3]));
@@ -1016,6 +1204,7 @@ template <typename real> void Engine<real>::comm_init(const char id[128]) {
     int rc = api.CommInitRank(&comm_, L.world, uid, L.rank);
     if (rc != 0) throw std::runtime_error(std::string("ncclCommInitRank: ") + api.GetErrorString(rc));
     if (!getenv("BB_NO_P2P")) setup_peer_exchange();
+    size_pass2();          // the persistent step kernel needs the peer-memory exchange
 }
 
 // Exchange buffer [2][world][P] doubles + flags [2][world], shared with every peer through CUDA IPC
@@ -1024,12 +1213,7 @@ template <typename real> void Engine<real>::comm_init(const char id[128]) {
 template <typename real> void Engine<real>::setup_peer_exchange() {
     if (L.world > MAX_WORLD) return;
     NcclApi &api = NcclApi::get();
-    const size_t P = sums_.n;
-    xchg_flag_off_ = ((size_t)2 * L.world * P * sizeof(double) + 255) / 256 * 256;
-    const size_t bytes = xchg_flag_off_ + (size_t)2 * L.world * sizeof(unsigned long long);
-    BB_CUDA(cudaMalloc(&xchg_mem_, bytes));
-    BB_CUDA(cudaMemset(xchg_mem_, 0, bytes));
-    xchg_err_.alloc(1);
+    alloc_xchg();
     cudaIpcMemHandle_t mine;
     const bool dbg = getenv("BB_DEBUG") != nullptr;
     cudaError_t ge = cudaIpcGetMemHandle(&mine, xchg_mem_);
@@ -1071,6 +1255,56 @@ template <typename real> void Engine<real>::setup_peer_exchange() {
     BB_CUDA(cudaStreamSynchronize(stream_));
     xchg_on_ = ok != 0;
     if (dbg) fprintf(stderr, "[bb rank %d] peer-memory exchange %s\n", L.rank, xchg_on_ ? "enabled" : "disabled (NCCL all-reduce)");
+}
+
+// exchange buffer [2][world][P] doubles + flags [2][world] (bb_aux_kernels.cuh "peer-memory exchange")
+template <typename real> void Engine<real>::alloc_xchg() {
+    if (xchg_mem_) return;
+    const size_t P = sums_.n;
+    xchg_flag_off_ = ((size_t)2 * L.world * P * sizeof(double) + 255) / 256 * 256;
+    const size_t bytes = xchg_flag_off_ + (size_t)2 * L.world * sizeof(unsigned long long);
+    BB_CUDA(cudaMalloc(&xchg_mem_, bytes));
+    BB_CUDA(cudaMemset(xchg_mem_, 0, bytes));
+    if (!xchg_err_.p) xchg_err_.alloc(1);
+}
+
+// single-process multi-GPU: every device's exchange buffer, mapped by peer access (no IPC, no NCCL)
+template <typename real> void Engine<real>::attach_peers(const std::vector<void *> &bufs) {
+    xchg_peer_mem_ = bufs;
+    xchg_on_ = true;
+    peers_local_ = true;
+    size_pass2();
+}
+
+// after the steps of one call: did an exchange (tail kernel or persistent step kernel) give up waiting for a peer?
+template <typename real> void Engine<real>::check_step_sync() {
+    int err = 0, serr = 0;
+    if (xchg_err_.p) BB_CUDA(cudaMemcpyAsync(&err, xchg_err_.p, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    if (step_sync_.p)
+        BB_CUDA(cudaMemcpyAsync(&serr, reinterpret_cast<char *>(step_sync_.p) + offsetof(StepSync, err), sizeof(int),
+                                cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaStreamSynchronize(stream_));
+    BB_CUDA(cudaGetLastError());
+    if (err || serr) {
+        // the tickets of an aborted persistent launch are mid-cycle: reset the control block, drop the pipelined sums
+        if (step_sync_.p) BB_CUDA(cudaMemset(step_sync_.p, 0, sizeof(StepSync)));
+        if (xchg_err_.p) BB_CUDA(cudaMemset(xchg_err_.p, 0, sizeof(int)));
+        part_step_ = -1;
+        throw std::runtime_error("peer-memory exchange timed out: a rank did not post its partial sums; the steps of "
+                                 "this call are incomplete");
+    }
+}
+
+template <typename real> void Engine<real>::persist_stats(double out[5]) {
+    for (int i = 0; i < 5; ++i) out[i] = 0.0;
+    if (!step_sync_.p) return;
+    StepSync h;
+    BB_CUDA(cudaMemcpy(&h, step_sync_.p, sizeof(StepSync), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) out[i] = (double)h.stat[i];
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_);
+    out[4] = (double)khz;
+    BB_CUDA(cudaMemset(reinterpret_cast<char *>(step_sync_.p) + offsetof(StepSync, stat), 0, sizeof(h.stat)));
 }
 
 template <typename real> void Engine<real>::check_peer_exchange() {

@@ -2,7 +2,7 @@
 // by the Makefile (BB_NT = 0 -> runtime number of time points).  BB_NE_SEL (optional) restricts the unit
 // to the one-environment (1) or runtime-environment (0) kernels: the runtime-T units are the slowest to
 // compile and are split in two so the build parallelises.
-#include "bb_kernels.cuh"
+#include "bb_kernel_set.cuh"
 #include "bb_registry.h"
 
 #ifndef BB_REAL

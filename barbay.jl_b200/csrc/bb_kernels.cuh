@@ -1041,27 +1041,4 @@ pass2_kernel(const P2Args<real> a) {
     }
 }
 
-// function-pointer bundle of one (real, NT, NE, HIER, SUP) instantiation
-template <typename real> struct KernelSet {
-    void (*pass1)(const P1Args<real>);
-    void (*pass2)(const P2Args<real>);        // no ELBO partial sums (the production step)
-    void (*pass2_elbo)(const P2Args<real>);   // also accumulates the log-density / entropy partials
-    void (*pass2_fused)(const P2Args<real>);  // pass 2 + pass 1 of the next step (non-hierarchical), or nullptr
-};
-
-template <typename real, int NT, int NE, bool HIER, bool SUP> KernelSet<real> make_kernel_set() {
-    KernelSet<real> ks;
-    ks.pass1 = pass1_kernel<real, NT, NE, HIER, SUP>;
-    ks.pass2_elbo = pass2_kernel<real, NT, NE, HIER, SUP, true>;
-    // the caller-supplied-noise kernels are the parity path: always with the ELBO terms
-    if constexpr (SUP) ks.pass2 = ks.pass2_elbo;
-    else ks.pass2 = pass2_kernel<real, NT, NE, HIER, SUP, false>;
-    ks.pass2_fused = nullptr;
-    if constexpr (!SUP && !HIER) ks.pass2_fused = pass2_kernel<real, NT, NE, HIER, SUP, false, true>;
-    return ks;
-}
-
-// lookup implemented by the instantiation units (bb_inst_*.cu); nt / ne of 0 select the runtime-size kernels
-template <typename real> bool lookup_kernels(int nt, int ne, bool hier, bool sup, KernelSet<real> *out);
-
 }  // namespace bb

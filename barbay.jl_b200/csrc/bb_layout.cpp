@@ -55,6 +55,7 @@ void build_layout(const bb_desc &d, Layout &L) {
     if (!d.bc_count) fail("bc_count is NULL");
     if (d.n_samples < 1 || d.n_samples > kMaxK) fail("samples_per_step must be in [1, 1024]");
     if (d.world < 1 || d.rank < 0 || d.rank >= d.world) fail("invalid (rank, world)");
+    if (d.n_devices < 0) fail("n_devices must be >= 0");
 
     L.model = d.model;
     L.R = d.n_rep;

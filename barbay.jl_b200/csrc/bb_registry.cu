@@ -3,7 +3,7 @@
 // specialised match and falls back to the runtime-size (NT = 0 / NE = 0) kernels.
 #include <vector>
 
-#include "bb_kernels.cuh"
+#include "bb_kernel_set.cuh"
 #include "bb_registry.h"
 
 namespace bb {

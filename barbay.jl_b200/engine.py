@@ -22,7 +22,8 @@ class Engine:
     """
 
     def __init__(self, data_arrays, model, model_kwargs=None, *, n_samples: int = 1, dtype: str = "f64",
-                 seed: int = 0, device: int = -1, rank: int = 0, world: int = 1, corrected_ragged: bool = True):
+                 seed: int = 0, device: int = -1, rank: int = 0, world: int = 1, corrected_ragged: bool = True,
+                 n_devices: int = 1):
         self._h = C.c_void_p()
         self._lib = _lib.load()
         self.model = _model.resolve(model)
@@ -112,6 +113,8 @@ class Engine:
         desc.n_samples = int(n_samples)
         desc.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         desc.device, desc.rank, desc.world = int(device), int(rank), int(world)
+        desc.n_devices = int(n_devices)
+        self.n_devices = int(n_devices)
 
         self.layout = _model.var_groups(self.model, n_time, n_rep, da.n_neutral, da.n_bc, n_env, n_geno)
         self.n_samples = int(n_samples)
@@ -250,6 +253,24 @@ class Engine:
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         self._check(self._lib.bb_time_steps(self._h, int(n_steps), C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def data_plane(self) -> dict:
+        """Which kernels / exchange this handle runs (for reporting)."""
+        out = (C.c_int32 * 4)()
+        self._check(self._lib.bb_data_plane(self._h, out))
+        return {"step_kernel": bool(out[0]), "persistent": out[1] > 1, "persist_chunk": int(out[1]),
+                "peer_exchange": bool(out[2]), "nccl": bool(out[3])}
+
+    def persist_stats(self) -> dict:
+        """Per-step breakdown of the persistent step kernel since the last call (microseconds, CTA 0's clock):
+        column phase, arrival -> all ranks' sums (grid reduction + NVLink exchange), sums -> next context."""
+        out = np.zeros(5)
+        self._check(self._lib.bb_persist_stats(self._h, _c_doubles(out)))
+        n, khz = out[3], out[4]
+        if n <= 0 or khz <= 0:
+            return {"tails": 0}
+        us = lambda cyc: cyc / n / khz * 1e3
+        return {"tails": int(n), "column_us": us(out[0]), "exchange_us": us(out[1]), "context_us": us(out[2])}
 
     def comm_init(self, unique_id: bytes):
         buf = (C.c_char * 128).from_buffer_copy(unique_id)

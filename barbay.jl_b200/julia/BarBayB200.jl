@@ -16,7 +16,7 @@ import DistributionsAD
 import Turing
 
 const LIB = get(ENV, "BARBAY_B200_LIB", "libbarbay_b200.so")
-const BB_ABI_VERSION = Int32(1)
+const BB_ABI_VERSION = Int32(2)
 
 struct BBPrior
     data::Ptr{Cdouble}
@@ -58,6 +58,7 @@ struct BBDesc
     device::Int32
     rank::Int32
     world::Int32
+    n_devices::Int32     # ABI 2: N > 1 = one handle drives N GPUs of this process (single blocking advi call)
 end
 
 # model function name -> bb_model (the reference dispatches on the name too, src/vi.jl:111-169)
@@ -87,7 +88,8 @@ Replacement for `Turing.vi(bayes_model, advi; optimizer=opt)` (src/vi.jl:201).  
 `utils.advi_to_df` (which reads `dist.dist.m`, `dist.dist.σ`, `dist.transform.ranges_out`,
 src/utils.jl:1049-1060, and is typed `::Distributions.Sampleable`, :1411) accepts it.
 """
-function vi(da, model::Function, model_kwargs::Dict, advi, opt; seed::Integer=0, dtype::Symbol=:f64)
+function vi(da, model::Function, model_kwargs::Dict, advi, opt; seed::Integer=0, dtype::Symbol=:f64,
+            device::Integer=-1, n_devices::Integer=1)
     keep = Any[]
     kw = Dict{Symbol,Any}(model_kwargs)
     counts = da.bc_count isa Vector ? reduce(vcat, vec.(da.bc_count)) : vec(da.bc_count)
@@ -104,7 +106,7 @@ function vi(da, model::Function, model_kwargs::Dict, advi, opt; seed::Integer=0,
         isempty(geno_idx) ? 0 : length(unique(geno_idx)), isempty(geno_idx) ? C_NULL : pointer(geno_idx),
         getp(:s_pop_prior, [0.0, 2.0]), getp(:logσ_pop_prior, [0.0, 1.0]), getp(:s_bc_prior, [0.0, 2.0]),
         getp(:logσ_bc_prior, [0.0, 1.0]), getp(:logλ_prior, [3.0, 3.0]), getp(:logτ_prior, [-2.0, 1.0]),
-        0, advi.samples_per_step, UInt64(seed), -1, 0, 1)
+        1, advi.samples_per_step, UInt64(seed), Int32(device), 0, 1, Int32(n_devices))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep begin
         rc = ccall((:bb_create, LIB), Cint, (Ref{BBDesc}, Ref{Ptr{Cvoid}}), desc, h)

@@ -56,11 +56,14 @@ def advi(*, data, model, outputname=None, model_kwargs=None, id_col="barcode", t
          count_col="count", neutral_col="neutral", rep_col=None, env_col=None, genotype_col=None,
          advi=None, opt=None, verbose=True,
          # backend extras (not part of the reference signature; defaults keep its behaviour)
-         seed=0, dtype="f64", device=-1, n_posterior_samples=10_000, return_engine=False):
+         seed=0, dtype="f64", device=-1, n_devices=1, n_posterior_samples=10_000, return_engine=False):
     """Fit the mean-field Gaussian posterior of a BarBay model with ADVI on a B200.
 
     Returns the tidy posterior ``DataFrame`` (columns ``mean, std, varname, vartype[, rep][, env], id``)
     or, when ``outputname`` is given, writes ``<outputname>.csv`` and returns ``None``.
+
+    ``n_devices`` > 1 shards the barcodes over that many GPUs of this process inside the library (one handle, one
+    blocking call per step batch, per-step exchange over NVLink peer memory): same posterior as one GPU.
     """
     mdl = _model.resolve(model)
     advi_cfg = advi if advi is not None else ADVI(1, 10_000)
@@ -88,7 +91,7 @@ def advi(*, data, model, outputname=None, model_kwargs=None, id_col="barcode", t
         model_kwargs = {"genotypes": data_arrays.genotypes, **model_kwargs}
 
     eng = Engine(data_arrays, mdl, model_kwargs, n_samples=advi_cfg.samples_per_step, dtype=dtype, seed=seed,
-                 device=device)
+                 device=device, n_devices=n_devices)
     var_names = eng.layout.var_names                                                      # vi.jl:184-198
     eng.init_params(seed)                                                                 # Turing meanfield()
     _apply_optimizer(eng, opt)

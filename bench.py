@@ -7,8 +7,12 @@
 One "step" = one full ADVI step (K_mc reparameterised draws, log-joint, analytic gradient, fused
 optimiser update of all 2D variational parameters) over BASELINE.json configs[1]:
 fitness_normal, 10^6 barcodes x 5 time points, 8 MC samples, synthetic counts.  Inputs are
-resident in HBM when the timed region starts; the per-step working set (244 MB fp32) exceeds the
-126 MB L2, so no explicit flush is needed between iterations.
+resident in HBM when the timed region starts.
+
+Multi-GPU (torchrun, one rank per GPU): the headline is STRONG scaling -- the same 10^6 barcodes sharded
+over the N GPUs (north_star: "10^6 barcodes ... scales >= 6x at 8 GPUs"); the weak-scaling figure
+(10^6 barcodes per GPU) is reported inside the line as `scaling_weak`.  Before timing, a sharded run is
+checked against an unsharded one on rank 0 (`parity`).
 """
 from __future__ import annotations
 
@@ -29,6 +33,8 @@ METRIC = "ADVI ELBO-gradient evals/s (barcode*timepoint*sample/s)"
 UNIT = "barcode*timepoint*sample/s"
 K_MC = 8
 CFG = 2
+SEED = 20261018
+L2_BYTES = 126e6
 
 
 def measured_peak_gbs():
@@ -39,6 +45,18 @@ def measured_peak_gbs():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    machine-readable extract of the ncu --set full capture (profiles/ncu_traffic.json: {key: {bytes, source}});
+    None when no capture of this build's kernel / configuration is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        ent = json.load(open(p)).get(kernel_key)
+        return (float(ent["bytes"]), ent.get("source")) if ent else (None, None)
+    except Exception:
+        return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -93,23 +111,31 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def make_workload(world: int, scaling: str):
-    """BASELINE configs[1]; weak scaling keeps 10^6 barcodes per GPU (global = world x 10^6)."""
+def make_workload(cfg: int, mult: int = 1, scale: float = 1.0):
+    """BASELINE configs[cfg - 1]; mult > 1 multiplies the barcode axis (weak scaling: 10^6 barcodes per GPU)."""
     import barbay_b200 as bb
-    spec = dict(bb.synth.CONFIGS[CFG])
+    spec = dict(bb.synth.CONFIGS[cfg])
     model = spec.pop("model")
-    if scaling == "weak" and world > 1:
-        spec["n_neutral"] *= world
-        spec["n_bc"] *= world
-    da, _ = bb.synth.simulate(model, seed=bb.synth.BASE_SEED + CFG, **spec)
+    for key in ("n_neutral", "n_bc"):
+        spec[key] = max(8, int(round(spec[key] * mult * scale)))
+    if "n_geno" in spec and scale != 1.0:
+        spec["n_geno"] = max(2, int(round(spec["n_geno"] * scale)))
+    da, _ = bb.synth.simulate(model, seed=bb.synth.BASE_SEED + cfg, **spec)
     return model, da
 
 
+def count_shape(da):
+    R = np.asarray(da.bc_count)
+    return R.shape, int(R.size)          # (T, B[, R]), T * B * R
+
+
+# ------------------------------------------------------------------------------------------ reference arm
 def cpu_port_rate(da, budget_s: float, K: int, max_barcodes: int | None = None):
     """Oracle C port (analytic gradient, fp64, OpenMP on all host cores) on a bounded sample of the
     same workload: the first `nb` mutant columns plus all neutrals.  Returns (units/s, cores, sample)."""
     from oracle import cport
     cport.build()
+    cores = cport.set_threads()                     # every host core, whatever OMP_NUM_THREADS says (torchrun sets 1)
     R = np.asarray(da.bc_count)
     N, M = da.n_neutral, da.n_bc
     nb = M if max_barcodes is None else min(M, max_barcodes)
@@ -126,37 +152,40 @@ def cpu_port_rate(da, budget_s: float, K: int, max_barcodes: int | None = None):
         t = time.perf_counter()
         pp.advi_steps(theta, acc, steps, K, first_step=1)
         dt = time.perf_counter() - t
-        return steps * K * T * (N + nb_) / dt, dt, pp.threads
+        return steps * K * T * (N + nb_) / dt, dt
 
     probe_nb = min(nb, 100_000)
-    rate, dt, cores = run(probe_nb, 1)
+    rate, dt = run(probe_nb, 1)
     per_step_full = K * T * (N + nb) / rate
     steps = int(max(1, min(50, budget_s / max(per_step_full, 1e-6))))
     if per_step_full > budget_s:                             # shrink the sample instead
         nb = max(probe_nb, int(nb * budget_s / per_step_full))
         steps = 1
-    rate, dt, cores = run(nb, steps)
-    sample = f"{steps} ADVI step(s) on {N} neutral + {nb} of {M} mutant barcodes x {T} time points, K={K}, fp64, {dt:.1f} s"
+    rate, dt = run(nb, steps)
+    sample = (f"{steps} ADVI step(s) on {N} neutral + {nb} of {M} mutant barcodes x {T} time points, K={K}, fp64, "
+              f"{dt:.1f} s, OpenMP {cores} threads")
     return rate, cores, sample
 
 
 def run_reference(args, emit):
     """Reference arm (tier rules): the reference algorithm's CPU path on the box's host cores.  Julia is
-    absent, so it is the oracle's compiled C/OpenMP port (kind "port") with all host threads.  W warm-up
-    and exactly K timed ADVI steps run on a bounded sample of the workload (all neutrals + the first nb
-    mutant barcodes) sized so the whole run stays within ~2 minutes."""
+    absent, so it is the oracle's compiled C/OpenMP port (kind "port") with ALL host threads (set explicitly:
+    torchrun exports OMP_NUM_THREADS=1).  The workload is the repo arm's: BASELINE configs[1], 10^6 barcodes
+    (strong scaling: the same problem at every N).  W warm-up and exactly K timed ADVI steps run on a bounded
+    sample of it (all neutrals + the first nb mutant barcodes) sized so the whole run stays within ~2 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import cport
     cport.build()
-    model, da = make_workload(1, "strong")
+    cores = cport.set_threads()
+    mult = args.gpus if args.scaling == "weak" else 1
+    model, da = make_workload(CFG, mult)
     R = np.asarray(da.bc_count)
     T, B = R.shape
     N, M = da.n_neutral, da.n_bc
     K = args.mc_samples
-    # probe the rate on a small sample, then size the per-step sample
-    probe_rate, cores, _ = cpu_port_rate(da, 1.0, K, max_barcodes=50_000)
+    probe_rate, _, _ = cpu_port_rate(da, 1.0, K, max_barcodes=50_000)
     budget = 120.0 / max(1, args.steps + args.warmup)
     nb = int(min(M, max(2_000, probe_rate * budget / (K * T) - N)))
     sub = np.ascontiguousarray(R[:, :N + nb])
@@ -169,11 +198,10 @@ def run_reference(args, emit):
     t0 = time.perf_counter()
     pp.advi_steps(theta, acc, args.steps, K, first_step=args.warmup)
     dt = time.perf_counter() - t0
-    units_step = K * T * (N + nb)
-    rate = args.steps * units_step / dt
+    rate = args.steps * K * T * (N + nb) / dt
     sample = (f"{args.steps} ADVI steps on {N} neutral + {nb} of {M} mutant barcodes x {T} time points, K={K}, "
               f"fp64, {dt:.1f} s, OpenMP {cores} threads")
-    line = {
+    emit({
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -184,163 +212,226 @@ def run_reference(args, emit):
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }
-    emit(line)
+    })
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--opt", default="decayed", choices=["decayed", "truncated"])
-    ap.add_argument("--mc-samples", type=int, default=K_MC)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    # the end-to-end call runs the reference's default number of iterations (ADVI(1, 10_000), src/vi.jl:98)
-    ap.add_argument("--e2e-steps", type=int, default=10000)
-    args = ap.parse_args()
-    # exactly ONE line on stdout: libraries (NCCL prints its version banner there) write to fd 1 too, so fd 1
-    # is pointed at stderr for the whole run and the JSON line goes to the saved descriptor
-    sys.stdout.flush()
-    real_stdout = os.dup(1)
-    os.dup2(2, 1)
+# ------------------------------------------------------------------------------------------ our arm
+class Ctx:
+    """Process-wide state of one bench run (rank, device, stream, torch.distributed handle)."""
 
-    def emit(line: dict):
-        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a B200: no CUDA device visible (there is no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+        # a dedicated (non-default) stream: the engine launches on it and the CUDA events below time it
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        assert self.stream.cuda_stream != 0
 
-    if args.impl == "reference":
-        return run_reference(args, emit)
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    import torch
+    def max_over_ranks(self, *vals):
+        if self.dist is None:
+            return [float(v) for v in vals]
+        t = self.torch.tensor([float(v) for v in vals], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def engine(self, da, model, K, dtype, opt, sharded=True, seed=SEED):
+        import barbay_b200 as bb
+        rank, world = (self.rank, self.world) if sharded else (0, 1)
+        eng = bb.Engine(da, model, n_samples=K, dtype=dtype, seed=seed, device=self.local_rank, rank=rank, world=world)
+        if world > 1:
+            uid = [bb.comm_unique_id() if rank == 0 else None]
+            self.dist.broadcast_object_list(uid, src=0)
+            eng.comm_init(uid[0])
+        eng.set_stream(self.stream.cuda_stream)
+        eng.init_params(1)
+        eng.set_optimizer(opt)
+        return eng
+
+    def time_steps(self, eng, steps, warmup):
+        """(ms over `steps` steps, max over ranks; launches) -- CUDA events on the launching stream."""
+        torch = self.torch
+        eng.step(max(warmup, 3))
+        self.barrier()
+        l0 = eng.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(self.stream)
+        eng.step(steps)
+        ev1.record(self.stream)
+        self.barrier()
+        ms = ev0.elapsed_time(ev1)
+        (ms,) = self.max_over_ranks(ms)
+        return ms, eng.launch_count - l0
+
+
+def parity_check(cx: Ctx, K=2, n_barcodes=30_000, n_steps=4):
+    """Sharded (all ranks) vs unsharded (rank 0) run of the same problem, same seed: fp64, `n_steps` ADVI steps.
+    Returns {"mean_rel", "sd_rel", "elbo_rel", "ok"} on rank 0."""
+    torch = cx.torch
+    model, da = make_workload(CFG, 1, scale=n_barcodes / 1e6)
+    out = {}
+    eng = cx.engine(da, model, K, "f64", "decayed", sharded=True, seed=7)
+    eng.step(n_steps)
+    elbo = eng.step(1, elbo_trace=True)[0]
+    m, s = eng.get_posterior()
+    eng.close()
+    t = torch.from_numpy(np.stack([m, s])).cuda()
+    cx.dist.all_reduce(t)                       # every latent is owned (reported) by exactly one rank
+    m, s = t.cpu().numpy()
+    if cx.rank == 0:
+        ref = cx.engine(da, model, K, "f64", "decayed", sharded=False, seed=7)
+        ref.step(n_steps)
+        elbo1 = ref.step(1, elbo_trace=True)[0]
+        m1, s1 = ref.get_posterior()
+        ref.close()
+        out = {"mean_rel": float(np.max(np.abs(m - m1)) / np.max(np.abs(m1))),
+               "sd_rel": float(np.max(np.abs(s - s1) / s1)),
+               "elbo_rel": float(abs(elbo - elbo1) / abs(elbo1)),
+               "what": f"{cx.world}-GPU sharded vs 1-GPU run, fitness_normal {n_barcodes} barcodes x 5, K={K}, fp64, "
+                       f"{n_steps + 1} steps, same Philox seed"}
+        out["ok"] = bool(out["mean_rel"] < 1e-9 and out["sd_rel"] < 1e-9 and out["elbo_rel"] < 1e-10)
+    cx.barrier()
+    return out
+
+
+def roofline_of(cx: Ctx, eng, steps_ms_per_step, n_prof, peak, peak_src, key, note=None):
+    ms_tot, ms_p1, ms_p2 = eng.time_steps(n_prof)
+    cx.barrier()
+    alg = eng.algorithmic_bytes_per_step
+    t_k = ms_p2 / n_prof * 1e-3
+    t_p1 = ms_p1 / n_prof * 1e-3
+    plane = eng.data_plane()
+    fused = t_p1 < 0.1 * t_k
+    kname = ("step_kernel<..., W=2> (packed fp32 gradient + optimiser update + next step's partial sums"
+             + ("; persistent: in-kernel reduction / exchange / shared-latent phases included)" if plane["persistent"] else ")")
+             ) if plane["step_kernel"] else ("pass2_kernel<..., FUSE=1>" if fused else "pass2_kernel (+ pass1_kernel)")
+    traffic, tsrc = ncu_traffic(key)
+    ach = alg / t_k / 1e9
+    step_ach = alg / (steps_ms_per_step * 1e-3) / 1e9
+    r = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+         "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+         "kernel_us": t_k * 1e6, "pass1_us": t_p1 * 1e6, "step_us": steps_ms_per_step * 1e3,
+         "kernel_share_of_step": t_k / (ms_tot / n_prof * 1e-3), "step_achieved": step_ach, "step_frac": step_ach / peak,
+         "l2_resident": bool(alg < L2_BYTES)}
+    if plane["persistent"]:
+        r["kernel_us_note"] = "persistent launch: kernel_us = launch duration / steps, i.e. it includes the in-kernel tail"
+    if note:
+        r["note"] = note
+    return r
+
+
+def sub_measure(cx: Ctx, cfg, K, dtype, opt, peak, steps=200):
+    """One extra configuration on one GPU: step time, algorithmic GB/s of the whole step, fraction of peak."""
+    model, da = make_workload(cfg)
+    shape, n_units = count_shape(da)
+    eng = cx.engine(da, model, K, dtype, opt, sharded=False)
+    ms, _ = cx.time_steps(eng, steps, 10)
+    alg = eng.algorithmic_bytes_per_step
+    plane = eng.data_plane()
+    eng.close()
+    step_s = ms / steps * 1e-3
+    return {"model": model, "shape": list(shape), "mc_samples": K, "dtype": dtype, "optimizer": opt,
+            "step_us": step_s * 1e6, "value": n_units * K / step_s, "unit": UNIT, "algorithmic_bytes": alg,
+            "step_achieved": alg / step_s / 1e9, "step_frac": alg / step_s / 1e9 / peak,
+            "step_kernel": plane["step_kernel"], "persistent": plane["persistent"]}
+
+
+def run_ours(args, emit):
     import barbay_b200 as bb
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: no CUDA device visible (there is no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cx = Ctx()
+    torch, world, rank = cx.torch, cx.world, cx.rank
     K = args.mc_samples
-    model, da = make_workload(world, args.scaling)
-    T, B = np.asarray(da.bc_count).shape
-    units_step = B * T * K
+    peak, peak_src = measured_peak_gbs()
 
-    eng = bb.Engine(da, model, n_samples=K, dtype=args.dtype, seed=20261018, device=local_rank, rank=rank, world=world)
-    if world > 1:
-        uid = [bb.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        eng.comm_init(uid[0])
-    # a dedicated (non-default) stream: the engine launches on it and the CUDA events below time it
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    eng.set_stream(stream.cuda_stream)
-    eng.init_params(1)
-    if args.opt == "decayed":
-        eng.set_optimizer("decayed")
-    else:
-        eng.set_optimizer("truncated")
-    alg_bytes = eng.algorithmic_bytes_per_step
+    parity = parity_check(cx) if world > 1 else None
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+    mult = world if args.scaling == "weak" else 1
+    model, da = make_workload(CFG, mult)
+    (T, B), n_cells = count_shape(da)
+    units_step = n_cells * K
+    eng = cx.engine(da, model, K, args.dtype, args.opt)
+    plane = eng.data_plane()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(cx.local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    eng.step(max(args.warmup, 3))
-    barrier()
-    launches0 = eng.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
-    ev0.record(stream)
-    eng.step(args.steps)
-    ev1.record(stream)
-    barrier()
+    ms, launches = cx.time_steps(eng, args.steps, args.warmup)
     t_wall1 = time.time()
-    ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count - launches0
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     value = units_step * args.steps / (ms * 1e-3)
+    breakdown = eng.persist_stats() if plane["persistent"] else None
 
-    # ---- roofline of the dominant kernel, live CUDA-event brackets on the launching stream.
-    # For non-hierarchical models the step is two launches: the fused step kernel (pass 2 of step i + pass 1
-    # of step i+1: theta, accumulators and counts cross HBM exactly once per step) and the merged tail kernel
-    # (partial-sum reduction + shared latents), see DESIGN.md section 4.
     n_prof = min(200, max(10, args.steps))
-    ms_tot, ms_p1, ms_p2 = eng.time_steps(n_prof)
-    barrier()
-    peak, peak_src = measured_peak_gbs()
-    t_p2 = ms_p2 / n_prof * 1e-3
-    t_p1 = ms_p1 / n_prof * 1e-3
-    achieved = alg_bytes / t_p2 / 1e9
-    step_achieved = alg_bytes / (ms / args.steps * 1e-3) / 1e9
-    fused = t_p1 < 0.1 * t_p2
-    roofline = {
-        "bound": "hbm",
-        "kernel": "pass2_kernel<..., FUSE=1> (gradient + fused optimiser update + next step's pass-1 sums)" if fused
-                  else "pass2_kernel (gradient + fused optimiser update)",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
-        # (profiles/r1_final_ncu_fused_kernel.csv; cfg2 fp32 K=8 DecayedADAGrad, 1 GPU) -- null for other configurations
-        "traffic": 188.0e6 if (world == 1 and args.dtype == "f32" and args.opt == "decayed" and K == 8) else None,
-        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-        "kernel_us": t_p2 * 1e6, "pass1_us": t_p1 * 1e6, "step_us": ms / args.steps * 1e3,
-        "kernel_share_of_step": t_p2 / (ms_tot / n_prof * 1e-3),
-        "step_achieved": step_achieved, "step_frac": step_achieved / peak,
-        "note": "K=8: issue-bound (two passes regenerate the Philox/Box-Muller noise: 416 warp instructions per "
-                "column*sample), DRAM ~15% busy, see profiles/r1_final.md; roofline_k1 is the same measurement at the "
-                "reference's default samples_per_step=1",
-    }
-    # the same measurement at the reference's default samples_per_step = 1 (src/vi.jl:98), for context
-    roofline_k1 = None
-    if world == 1 and K != 1:
-        eng1 = bb.Engine(da, model, n_samples=1, dtype=args.dtype, seed=20261018, device=local_rank)
-        eng1.set_stream(stream.cuda_stream)
-        eng1.init_params(1)
-        eng1.set_optimizer(args.opt)
-        eng1.step(20)
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(stream)
-        eng1.step(n_prof)
-        a1.record(stream)
-        torch.cuda.synchronize()
-        step1 = a0.elapsed_time(a1) / n_prof * 1e-3
-        _, _, k1_p2 = eng1.time_steps(n_prof)
-        ab1 = eng1.algorithmic_bytes_per_step
-        roofline_k1 = {"bound": "hbm", "achieved": ab1 / (k1_p2 / n_prof * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                       "frac": ab1 / (k1_p2 / n_prof * 1e-3) / 1e9 / peak, "kernel_us": k1_p2 / n_prof * 1e3,
-                       "step_us": step1 * 1e6, "step_achieved": ab1 / step1 / 1e9, "step_frac": ab1 / step1 / 1e9 / peak,
-                       "value": B * T / step1, "mc_samples": 1}
-        eng1.close()
+    key = f"cfg{CFG}_{args.dtype}_{args.opt}_k{K}_n{world}"
+    roofline = roofline_of(
+        cx, eng, ms / args.steps, n_prof, peak, peak_src, key,
+        note="K=8 is issue-bound, not HBM-bound: both passes regenerate the Philox/Box-Muller noise (see DESIGN.md "
+             "section 5 for the instruction budget); roofline_k1 is the same measurement at the reference's default "
+             "samples_per_step=1")
     clocks = sampler.summary(t_wall0, time.time()) if sampler else None
 
+    # ---- more lines on one GPU: reference default K=1, fp64 (the reference's arithmetic), the reference's default
+    # optimiser, and the other BASELINE configurations
+    extras = {}
+    if world == 1 and not args.no_extras:
+        eng1 = cx.engine(da, model, 1, args.dtype, args.opt, sharded=False)
+        ms1, _ = cx.time_steps(eng1, n_prof, 10)
+        r1 = roofline_of(cx, eng1, ms1 / n_prof, n_prof, peak, peak_src, f"cfg{CFG}_{args.dtype}_{args.opt}_k1_n1")
+        r1["value"] = n_cells / (ms1 / n_prof * 1e-3); r1["mc_samples"] = 1
+        extras["roofline_k1"] = r1
+        eng1.close()
+        if args.dtype != "f64":
+            e64 = cx.engine(da, model, K, "f64", args.opt, sharded=False)
+            ms64, _ = cx.time_steps(e64, n_prof, 10)
+            r64 = roofline_of(cx, e64, ms64 / n_prof, n_prof, peak, peak_src, f"cfg{CFG}_f64_{args.opt}_k{K}_n1")
+            extras["value_f64"] = units_step / (ms64 / n_prof * 1e-3)
+            extras["roofline_f64"] = r64
+            e64.close()
+        if args.opt != "truncated":
+            extras["truncated"] = sub_measure(cx, CFG, K, args.dtype, "truncated", peak)
+        extras["configs"] = {f"cfg{c}": sub_measure(cx, c, K, args.dtype, args.opt, peak) for c in (3, 4, 5)}
+
+    # ---- weak scaling beside the strong headline (10^6 barcodes per GPU)
+    scaling_weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_extras:
+        wmodel, wda = make_workload(CFG, world)
+        _, wcells = count_shape(wda)
+        weng = cx.engine(wda, wmodel, K, args.dtype, args.opt)
+        wsteps = min(args.steps, 500)
+        wms, _ = cx.time_steps(weng, wsteps, 10)
+        scaling_weak = {"value": wcells * K * wsteps / (wms * 1e-3), "unit": UNIT, "ms_per_step": wms / wsteps,
+                        "barcodes": int(wcells // T), "steps": wsteps,
+                        "breakdown_us": weng.persist_stats() if weng.data_plane()["persistent"] else None}
+        weng.close()
+        del wda
+
     # ---- end to end through the public API with HOST buffers: one complete advi()-equivalent call
-    # (pack -> bb_create: H2D of counts/maps -> init -> optimiser -> n steps -> ELBO read-back ->
-    # bb_get_posterior: D2H), timed on the host clock around the whole call.
-    # (all ranks take part; host wall clock, max over ranks)
+    # (bb_create: pack + H2D of counts / maps -> [comm] -> init -> optimiser -> n steps -> ELBO read-back ->
+    # bb_get_posterior: D2H), timed on the host clock around the whole call (all ranks, max over ranks)
     n_e2e = args.e2e_steps
-    barrier()
+    cx.barrier()
     t0 = time.perf_counter()
-    eng2 = bb.Engine(da, model, n_samples=K, dtype=args.dtype, seed=20261018, device=local_rank, rank=rank, world=world)
+    eng2 = bb.Engine(da, model, n_samples=K, dtype=args.dtype, seed=SEED, device=cx.local_rank, rank=rank, world=world)
     t_comm = 0.0
     if world > 1:
         tc0 = time.perf_counter()
         uid2 = [bb.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid2, src=0)
+        cx.dist.broadcast_object_list(uid2, src=0)
         eng2.comm_init(uid2[0])
         t_comm = time.perf_counter() - tc0       # one-time per process: NCCL communicator + CUDA IPC peer mappings
     eng2.init_params(1)
@@ -349,13 +440,10 @@ def main():
     elbo_last = eng2.step(1, elbo_trace=True)            # the step's result read back (8 bytes)
     m, s = eng2.get_posterior()
     dt_e2e = time.perf_counter() - t0
-    if dist is not None:
-        tt = torch.tensor([dt_e2e, t_comm], device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt_e2e, t_comm = float(tt[0].item()), float(tt[1].item())
+    dt_e2e, t_comm = cx.max_over_ranks(dt_e2e, t_comm)
     n_tot = n_e2e + 1
-    h2d = (B * T * 4 + (B * T + 2 * (B - da.n_neutral)) * 4) / world / n_tot     # int32 counts + layout maps per rank
-    d2h = (2 * eng2.D * 8) / n_tot + 8.0 / n_tot                                  # posterior (m, sigma) + ELBO
+    h2d = (n_cells * 4 + (n_cells + 2 * (B - da.n_neutral)) * 4) / world / n_tot     # int32 counts + layout maps per rank
+    d2h = (2 * eng2.D * 8) / n_tot + 8.0 / n_tot                                    # posterior (m, sigma) + ELBO
     e2e = {"value": units_step * n_tot / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": n_tot, "seconds": dt_e2e,
            "what": "one complete advi()-equivalent call through the C ABI from HOST arrays on every rank: bb_create "
@@ -363,12 +451,10 @@ def main():
                    "ELBO read-back + bb_get_posterior (D2H); bytes are amortised over the steps of the call",
            "elbo_last": float(elbo_last[-1]), "posterior_finite": bool(np.isfinite(m).all())}
     if world > 1:
-        # context only (the headline `value` above includes it): the communicator set-up is a fixed per-process
-        # cost, paid once however many steps (the reference's default max_iters is 10 000) or fits follow
         e2e["comm_init_seconds"] = t_comm
         e2e["value_excluding_comm_init"] = units_step * n_tot / max(dt_e2e - t_comm, 1e-9)
     eng2.close()
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_extras:
         # streaming variant per the base contract: every step re-uploads that step's counts from pinned
         # host memory and reads the step's ELBO back
         cnt_host = torch.from_numpy(np.ascontiguousarray(np.asarray(da.bc_count).astype(np.int32))).pin_memory()
@@ -378,7 +464,7 @@ def main():
         t0 = time.perf_counter()
         for _ in range(n_s):
             cnt_dev.copy_(cnt_host, non_blocking=True)
-            tr = eng.step(1, elbo_trace=True)
+            eng.step(1, elbo_trace=True)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         e2e["streaming"] = {"value": units_step * n_s / (t1 - t0), "unit": UNIT,
@@ -394,22 +480,70 @@ def main():
     if sampler:
         sampler.stop()
     if rank == 0:
+        shard_bytes = eng.algorithmic_bytes_per_step
+        if plane["persistent"] and world > 1:
+            dp = "peer_ipc: in-kernel exchange of the step's sums over NVLink peer memory (persistent step kernel)"
+        elif plane["peer_exchange"]:
+            dp = "peer_ipc: exchange of the step's sums over NVLink peer memory inside the tail kernel"
+        elif world > 1:
+            dp = "nccl: one ncclAllReduce of the step's sums per step"
+        else:
+            dp = "none (single GPU)"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"BASELINE configs[1]: fitness_normal, {B} barcodes x {T} time points, {K} MC samples"
                        + (f" ({B // world} barcodes per GPU)" if world > 1 else ""),
                        "optimizer": "DecayedADAGrad" if args.opt == "decayed" else "TruncatedADAGrad(n=100)",
-                       "l2": "inputs_exceed_l2 (per-step working set > 126 MB, no flush needed)",
-                       "parallelism": f"barcode-sharded x{world}, one NCCL all-reduce of {5 * T * K} doubles per step"
-                       if world > 1 else "single GPU"},
-            "roofline": roofline, "roofline_k1": roofline_k1, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                       "l2": ("inputs_exceed_l2 (per-step working set > 126 MB, no flush needed)" if shard_bytes > L2_BYTES
+                              else f"shard_fits_l2 ({shard_bytes / 1e6:.0f} MB per GPU per step < 126 MB L2: the strong-scaling "
+                                   "shard is L2-resident by construction; HBM fraction is reported against algorithmic bytes)"),
+                       "parallelism": f"barcode-sharded x{world}; {5 * T * K} doubles combined per step" if world > 1 else "single GPU",
+                       "data_plane": dp,
+                       "steps_per_launch": plane["persist_chunk"] if plane["persistent"] else 1},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if breakdown:
+            line["breakdown_us"] = breakdown
+        if parity is not None:
+            line["parity"] = parity
+        if scaling_weak is not None:
+            line["scaling_weak"] = scaling_weak
+        line.update(extras)
         emit(line)
     eng.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    if cx.dist is not None:
+        cx.dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--opt", default="decayed", choices=["decayed", "truncated"])
+    ap.add_argument("--mc-samples", type=int, default=K_MC)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the K=1 / fp64 / TruncatedADAGrad / cfg3-5 / weak sub-lines")
+    # the end-to-end call runs the reference's default number of iterations (ADVI(1, 10_000), src/vi.jl:98)
+    ap.add_argument("--e2e-steps", type=int, default=10000)
+    args = ap.parse_args()
+    # exactly ONE line on stdout: libraries (NCCL prints its version banner there) write to fd 1 too, so fd 1
+    # is pointed at stderr for the whole run and the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+    if args.impl == "reference":
+        return run_reference(args, emit)
+    return run_ours(args, emit)
 
 
 if __name__ == "__main__":

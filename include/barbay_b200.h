@@ -19,9 +19,12 @@
  *  - every function returns 0 on success, non-zero on error; bb_last_error()
  *    gives the message (the Julia glue raises it with error(msg), matching the
  *    reference's ErrorException convention, src/vi.jl:107,112,117).
- *  - one handle = one GPU = one host thread (the reference call is synchronous
- *    and single-threaded).  Multi-GPU: one process per GPU, each creating a handle
- *    with its (rank, world); bb_comm_* wires the per-step NCCL all-reduce.
+ *  - one handle = one host thread (the reference call is synchronous and
+ *    single-threaded).  Multi-GPU, two ways: (a) bb_desc.n_devices = N -- ONE
+ *    handle, N GPUs of this process, every entry point one blocking call (the
+ *    library runs one worker thread per device inside the call); (b) one process
+ *    per GPU, each creating a handle with its (rank, world) and bb_comm_* wiring
+ *    the exchange (torchrun-style launchers).
  */
 #ifndef BARBAY_B200_H
 #define BARBAY_B200_H
@@ -32,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BB_ABI_VERSION 1
+#define BB_ABI_VERSION 2   /* 2: bb_desc.n_devices (single-call multi-GPU) */
 
 typedef struct bb_handle bb_handle;
 
@@ -91,6 +94,11 @@ typedef struct bb_desc {
     uint64_t seed;                /* key of the Philox noise lattice */
     int32_t device;               /* CUDA ordinal, -1 = current device */
     int32_t rank, world;          /* this handle owns shard `rank` of `world` of the barcode axis */
+    /* ABI 2.  0 or 1: one GPU (`device`).  N > 1: ONE handle drives the N GPUs device .. device + N - 1 of this
+     * process (rank / world must be 0 / 1): the barcode axis is sharded inside the library, every entry point
+     * stays one blocking call, and the per-step exchange runs over NVLink peer memory -- what a single
+     * BarBay.vi.advi() call (src/vi.jl:86-101) needs to use a whole box. */
+    int32_t n_devices;
 } bb_desc;
 
 /* ---- lifecycle ---- */
@@ -134,6 +142,15 @@ double bb_algorithmic_bytes_per_step(const bb_handle *h);   /* SURVEY §8d figur
 /* n_steps of bb_step timed with CUDA events on the launching stream: whole region, and the summed
  * durations of the pass-1 and pass-2 column kernels (the roofline numerators of bench.py). */
 int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_pass1, float *ms_pass2);
+
+/* Persistent step kernel (several ADVI steps per launch, the tail of each step inside the kernel): SM cycles of
+ * CTA 0 spent in {column phase, arrival -> all ranks' sums, sums -> next step's context}, summed over the
+ * in-kernel tails since the last call; out[3] = number of such tails, out[4] = SM clock in kHz.  Resets the counters. */
+int bb_persist_stats(bb_handle *h, double out[5]);
+
+/* Which kernels / data plane this handle runs: out = {packed step kernel in use, steps per persistent launch
+ * (0: one launch pair per step), NVLink peer-memory exchange on, NCCL communicator present}. */
+int bb_data_plane(bb_handle *h, int32_t out[4]);
 
 /* ---- multi-GPU: one process per GPU; id is an ncclUniqueId (128 bytes) ---- */
 int bb_comm_unique_id(char id[128]);

@@ -41,6 +41,15 @@ int port_num_threads(void) {
 #endif
 }
 
+/* the caller states the thread count (torchrun exports OMP_NUM_THREADS=1 to every rank) */
+void port_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 static inline double softplus(double w) { return (w > 0 ? w : 0) + log1p(exp(-fabs(w))); }
 static inline double sigmoid(double w) { return 1.0 / (1.0 + exp(-w)); }
 

@@ -198,6 +198,8 @@ def test_merged_tail_kernel_equals_separate_kernels(bb, model, dtype, monkeypatc
     programmatic dependent.  Same arithmetic in the same order as reduce_kernel -> shared_kernel with plain
     launches: the trajectories must be bitwise identical."""
     res = {}
+    # one launch pair per step: the persistent step kernel reduces through ticketed groups (another summation order)
+    monkeypatch.setenv("BB_PERSIST", "0")
     for mode in ("default", "no_tail", "no_pdl"):
         monkeypatch.delenv("BB_NO_TAIL", raising=False)
         monkeypatch.delenv("BB_NO_PDL", raising=False)

@@ -123,7 +123,7 @@ def test_c_abi_exports_every_declared_symbol(bb):
     assert declared == bound, declared ^ bound
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.bb_abi_version() == 1
+    assert lib.bb_abi_version() == 2
     assert lib.bb_n_latent(None) == -1 and lib.bb_last_error(None) is not None
 
 
