@@ -56,6 +56,7 @@ _D = C.POINTER(C.c_double)
 SYMBOLS = [
     ("bb_abi_version", C.c_int32, []),
     ("bb_create", C.c_int, [C.POINTER(bb_desc), C.POINTER(_P)]),
+    ("bb_layout_probe", C.c_int, [C.POINTER(bb_desc), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     ("bb_destroy", None, [_P]),
     ("bb_last_error", C.c_char_p, [_P]),
     ("bb_n_latent", C.c_int64, [_P]),
@@ -70,6 +71,8 @@ SYMBOLS = [
     ("bb_step", C.c_int, [_P, C.c_int32, _D]),
     ("bb_step_with_noise", C.c_int, [_P, _D]),
     ("bb_step_count", C.c_int64, [_P]),
+    ("bb_step_until", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_int32),
+                                C.POINTER(C.c_int32), _D, C.POINTER(C.c_int32)]),
     ("bb_state_size", C.c_int64, [_P]),
     ("bb_get_state", C.c_int, [_P, _D]),
     ("bb_set_state", C.c_int, [_P, _D]),
@@ -80,6 +83,10 @@ SYMBOLS = [
     ("bb_time_steps", C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("bb_persist_stats", C.c_int, [_P, _D]),
     ("bb_data_plane", C.c_int, [_P, C.POINTER(C.c_int32)]),
+    ("bb_derived_fitness", C.c_int, [_P, C.c_int32, C.c_uint64, _D, _D]),
+    ("bb_n_derived", C.c_int64, [_P]),
+    ("bb_peer_handle", C.c_int, [_P, C.c_char * 64]),
+    ("bb_peer_attach", C.c_int, [_P, C.c_char_p, C.c_int32]),
     ("bb_comm_unique_id", C.c_int, [C.c_char * 128]),
     ("bb_comm_init", C.c_int, [_P, C.c_char * 128]),
 ]

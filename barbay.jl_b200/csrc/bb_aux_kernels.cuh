@@ -83,8 +83,8 @@ static __global__ void __launch_bounds__(256) xchg_post_kernel(const XchgPostArg
     __threadfence_system();
     __syncthreads();
     if (tid < a.world) {
-        volatile unsigned long long *f = a.peer_flag[tid] + (a.parity * a.world + a.rank);
-        *f = a.seq;
+        unsigned long long *f = a.peer_flag[tid] + (a.parity * a.world + a.rank);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.seq) : "memory");
     }
 }
 
@@ -96,18 +96,24 @@ struct XchgWaitArgs {
     int *err;                                 // set to 1 if a peer never showed up (bounded spin)
 };
 
-// executed by one CTA at the top of the consumer kernel; totals land in `sums`
-__device__ __forceinline__ void xchg_wait_and_sum(const XchgWaitArgs &x, double *sums) {
-    if (!x.buf) return;
+// executed by one CTA at the top of the consumer kernel; totals land in `sums`.  Returns false when a peer never
+// posted (bounded spin, or an earlier exchange of this call already failed): the caller applies NO update, the column
+// kernel behind it sees the same flag and returns, and the host raises the error at the end of bb_step.
+__device__ __forceinline__ bool xchg_wait_and_sum(const XchgWaitArgs &x, double *sums) {
+    if (!x.buf) return true;
     const int tid = threadIdx.x;
+    int bad = 0;
     if (tid < x.world) {
-        const volatile unsigned long long *f = x.flag + (x.parity * x.world + tid);
+        const unsigned long long *f = x.flag + (x.parity * x.world + tid);
         const long long t0 = clock64();
-        while (*f != x.seq) {
-            if (clock64() - t0 > 6000000000LL) { *x.err = 1; break; }      // ~3 s: never hang the GPU
+        unsigned long long v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v == x.seq) break;
+            if (*reinterpret_cast<volatile int *>(x.err) || clock64() - t0 > 6000000000LL) { *x.err = 1; bad = 1; break; }   // ~3 s: never hang the GPU
         }
     }
-    __syncthreads();
+    if (__syncthreads_or(bad)) return false;
     __threadfence_system();
     for (int i = tid; i < x.P; i += blockDim.x) {
         double s = 0.0;
@@ -116,6 +122,46 @@ __device__ __forceinline__ void xchg_wait_and_sum(const XchgWaitArgs &x, double 
         sums[i] = s;
     }
     __syncthreads();
+    return true;
+}
+
+// All-reduce (sum) of a short device vector over the peer exchange buffers: ONE CTA posts this rank's `m` values to
+// every peer, waits for theirs and writes the rank-ordered sum back in place.  Used for the ELBO terms / trace when the
+// handles were wired by bb_peer_attach (no NCCL communicator in the process).
+static __global__ void __launch_bounds__(256) peer_allreduce_kernel(double *vec, int m, const XchgPostArgs xp,
+                                                                    const XchgWaitArgs xw) {
+    const int tid = threadIdx.x;
+    for (int r = 0; r < xp.world; ++r) {
+        double *dst = xp.peer_buf[r] + (size_t)(xp.parity * xp.world + xp.rank) * xp.P;
+        for (int i = tid; i < m; i += blockDim.x) dst[i] = vec[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < xp.world) {
+        unsigned long long *f = xp.peer_flag[tid] + (xp.parity * xp.world + xp.rank);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(xp.seq) : "memory");
+    }
+    XchgWaitArgs w = xw;
+    w.P = xp.P;
+    int bad = 0;
+    if (tid < w.world) {
+        const unsigned long long *f = w.flag + (w.parity * w.world + tid);
+        const long long t0 = clock64();
+        unsigned long long v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v == w.seq) break;
+            if (clock64() - t0 > 6000000000LL) { *w.err = 1; bad = 1; break; }
+        }
+    }
+    if (__syncthreads_or(bad)) return;
+    __threadfence_system();
+    for (int i = tid; i < m; i += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < w.world; ++r)
+            s += *reinterpret_cast<const volatile double *>(w.buf + (size_t)(w.parity * w.world + r) * w.P + i);
+        vec[i] = s;
+    }
 }
 
 // ------------------------------------------------------------------ shared latents
@@ -186,7 +232,7 @@ __device__ __forceinline__ void shared_body(const SharedArgs<real> &a, double *s
     double *lp_t = u_t + (size_t)a.R * a.K * a.tmax;         // [R][K][tmax] log-density pieces
     double *lsig_t = lp_t + (size_t)a.R * a.K * a.tmax;      // [n2] log sigma before the update
     if (do_phase0) shared_phase0<real>(a, scratch);
-    xchg_wait_and_sum(a.xchg, sums);                         // multi-GPU: complete the sums over NVLink peer memory
+    if (!xchg_wait_and_sum(a.xchg, sums)) return;            // multi-GPU: complete the sums over NVLink peer memory
     __syncthreads();
     // ---- phase 1
     for (int j = tid; j < a.R * a.K * a.tmax; j += nthr) {
@@ -314,8 +360,8 @@ __global__ void __launch_bounds__(256) tail_kernel(const ReduceArgs ra, int R, c
         __threadfence_system();
         __syncthreads();
         if ((int)threadIdx.x < xp.world) {
-            volatile unsigned long long *f = xp.peer_flag[threadIdx.x] + (xp.parity * xp.world + xp.rank);
-            *f = xp.seq;
+            unsigned long long *f = xp.peer_flag[threadIdx.x] + (xp.parity * xp.world + xp.rank);
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(xp.seq) : "memory");
         }
     } else {
         for (int i = threadIdx.x; i < nsums; i += blockDim.x) tot[i] = __ldcg(ra.sums + i);

@@ -76,6 +76,27 @@ int bb_create(const bb_desc *desc, bb_handle **out) {
     }
 }
 
+int bb_layout_probe(const bb_desc *desc, int32_t *owned, int64_t info[8]) {
+    if (!desc || !info) { g_create_error = "bb_layout_probe: NULL argument"; return 2; }
+    try {
+        bb::Layout L;
+        bb::build_layout(*desc, L);
+        info[0] = L.D; info[1] = L.n0; info[2] = L.n1; info[3] = L.m0; info[4] = L.m1; info[5] = L.H;
+        info[6] = L.hy_gid0; info[7] = L.cpad;
+        if (owned) {
+            for (long long i = 0; i < L.D; ++i) owned[i] = 0;
+            for (const std::vector<int> *m : {&L.map_lam, &L.map_bc, &L.map_hy, &L.map_sh})
+                for (int ref : *m)
+                    if (ref >= 0) owned[ref] += 1;
+        }
+        g_create_error.clear();
+        return 0;
+    } catch (const std::exception &e) {
+        g_create_error = e.what();
+        return 1;
+    }
+}
+
 void bb_destroy(bb_handle *h) {
     if (!h) return;
     DeviceGuard g(h->eng ? h->eng->home_device : -1);
@@ -134,6 +155,33 @@ int bb_step_with_noise(bb_handle *h, const double *eps) {
     });
 }
 int64_t bb_step_count(const bb_handle *h) { return h && h->eng ? h->eng->step_count : -1; }
+int bb_step_until(bb_handle *h, int32_t max_iters, int32_t every, int32_t window, double rel_tol, int32_t *n_done,
+                  int32_t *converged, double *elbo_out, int32_t *n_elbo) {
+    return guarded(h, [&](bb::EngineBase &e) {
+        if (max_iters < 0 || every < 1 || window < 1 || !(rel_tol >= 0.0) || !n_done || !converged)
+            throw std::runtime_error("bb_step_until: bad arguments");
+        std::vector<double> est;
+        int done = 0, conv = 0;
+        while (done < max_iters && !conv) {
+            const int blk = std::min<int>(every, max_iters - done);
+            if (blk > 1) e.step(blk - 1, nullptr);
+            double v = 0.0;
+            e.step(1, &v);
+            done += blk;
+            est.push_back(v);
+            const size_t n = est.size();
+            if (n >= (size_t)2 * window) {
+                double a = 0.0, b = 0.0;
+                for (int i = 0; i < window; ++i) { a += est[n - 1 - i]; b += est[n - 1 - window - i]; }
+                a /= window; b /= window;
+                conv = std::fabs(a - b) <= rel_tol * std::fabs(a) ? 1 : 0;
+            }
+        }
+        *n_done = done; *converged = conv;
+        if (n_elbo) *n_elbo = (int32_t)est.size();
+        if (elbo_out) std::copy(est.begin(), est.end(), elbo_out);
+    });
+}
 int64_t bb_state_size(const bb_handle *h) { return h && h->eng ? h->eng->state_size() : -1; }
 int bb_get_state(bb_handle *h, double *s) {
     return guarded(h, [&](bb::EngineBase &e) { e.get_state(s); });
@@ -161,10 +209,29 @@ int bb_persist_stats(bb_handle *h, double out[5]) {
         e.persist_stats(out);
     });
 }
+int bb_derived_fitness(bb_handle *h, int32_t n_samples, uint64_t seed, double *median, double *sd) {
+    return guarded(h, [&](bb::EngineBase &e) {
+        if (!median || !sd) throw std::runtime_error("bb_derived_fitness: NULL argument");
+        e.derived_fitness(n_samples, seed, median, sd);
+    });
+}
+int64_t bb_n_derived(const bb_handle *h) { return h && h->eng && h->eng->L.hier ? h->eng->L.bc_block : 0; }
 int bb_data_plane(bb_handle *h, int32_t out[4]) {
     return guarded(h, [&](bb::EngineBase &e) {
         if (!out) throw std::runtime_error("bb_data_plane: NULL argument");
         e.data_plane(out);
+    });
+}
+int bb_peer_handle(bb_handle *h, char out[64]) {
+    return guarded(h, [&](bb::EngineBase &e) {
+        if (!out) throw std::runtime_error("bb_peer_handle: NULL argument");
+        e.peer_handle(out);
+    });
+}
+int bb_peer_attach(bb_handle *h, const char *handles, int32_t n) {
+    return guarded(h, [&](bb::EngineBase &e) {
+        if (!handles) throw std::runtime_error("bb_peer_attach: NULL argument");
+        e.peer_attach(handles, n);
     });
 }
 int bb_comm_unique_id(char id[128]) {

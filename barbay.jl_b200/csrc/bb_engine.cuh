@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "bb_derived.cuh"
 #include "bb_kernel_set.cuh"
 #include "bb_layout.h"
 
@@ -116,6 +117,13 @@ class EngineBase {
     virtual void persist_stats(double out[5]) = 0;
     // out = {packed step kernel in use, steps per persistent launch (0: off), peer-memory exchange on, NCCL communicator present}
     virtual void data_plane(int32_t out[4]) = 0;
+    // one-process-per-GPU wiring without NCCL: every rank exports the CUDA IPC handle of its exchange buffer, the
+    // caller gathers them with whatever transport it has (torch.distributed, MPI, a file) and hands all of them back
+    virtual void peer_handle(char out[64]) = 0;
+    virtual void peer_attach(const char *handles, int n) = 0;
+    // derived bc_fitness rows of the hierarchical models (bb_derived.cuh): median and sd of n draws of
+    // theta + exp(log-tau) theta-tilde per log-tau row, [E M R] each; rows of other shards stay 0
+    virtual void derived_fitness(int n, uint64_t seed, double *median, double *sd) = 0;
     int home_device = -1;      // CUDA ordinal every call of a single-GPU handle runs on (-1: the handle sets devices itself)
     long long launches = 0;
     long long step_count = 0;
@@ -151,6 +159,9 @@ template <typename real> class Engine : public EngineBase {
     void time_steps(int n, float *ms_total, float *ms_pass1, float *ms_pass2) override;
     void comm_init(const char id[128]) override;
     void persist_stats(double out[5]) override;
+    void derived_fitness(int n, uint64_t seed, double *median, double *sd) override;
+    void peer_handle(char out[64]) override;
+    void peer_attach(const char *handles, int n) override;
     void data_plane(int32_t out[4]) override {
         out[0] = stepk_ok_ ? 1 : 0;
         out[1] = (stepk_ok_ && persist_chunk_ > 1 && !(comm_ && !xchg_on_)) ? persist_chunk_ : 0;
@@ -265,7 +276,10 @@ template <typename real> class Engine : public EngineBase {
     void *xchg_mem_ = nullptr;
     std::vector<void *> xchg_peer_mem_;
     DBuf<int> xchg_err_;
-    size_t xchg_flag_off_ = 0;
+    size_t xchg_flag_off_ = 0, xchg_aux_off_ = 0, xchg_aux_flag_off_ = 0;
+    unsigned long long aux_seq_ = 0;
+    static constexpr int kAuxP = 4096;      // doubles per round of the auxiliary all-reduce
+    void peer_allreduce(double *dev, size_t n);
     void setup_peer_exchange();
     void check_peer_exchange();
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -490,6 +504,9 @@ template <typename real> void Engine<real>::size_pass2() {
         if (!L.hier && L.R == 1 && !getenv("BB_NO_STEPK")) {
             const int W = (L.K % 2 == 0) ? 2 : 1;
             StepKernelFn<real> fn = W == 2 ? g.ks.step_w2 : g.ks.step_w1;
+            // odd K (the reference's default K = 1) on one GPU: the round-1 fused kernel keeps 4 CTAs per SM and is the
+            // faster one there (measured: 59.5 vs 67.8 us at cfg2); the unpacked step kernel serves multi-GPU shards
+            if (W == 1 && L.world == 1 && !getenv("BB_STEPK_ODD")) fn = nullptr;
             if (fn) {
                 auto r128 = [](size_t b) { return (b + 127) / 128 * 128; };
                 const int NJ = 2 * L.E, ROWS = g.nt + NJ, npack = L.K / W;
@@ -498,7 +515,7 @@ template <typename real> void Engine<real>::size_pass2() {
                 const int rows = std::max(npack * ((pvs_m + 1) / 2), (pvs_n + 1) / 2);
                 const size_t spb = (size_t)2 * W * sizeof(real);        // one SlotPair
                 const size_t head = 64 + r128((size_t)npack * 3 * g.nt * W * sizeof(real)) +
-                                    r128((size_t)L.K * 3 * g.nt * sizeof(real)) + r128((size_t)4 * (g.nt - 1) * sizeof(double2));
+                                    r128((size_t)4 * (g.nt - 1) * sizeof(double2));
                 auto total = [&](int stage_ring) {
                     return head + 2 * ((1 + npr) * thb + cnb) + (size_t)(1 + stage_ring) * thb + (size_t)rows * BLOCK * spb;
                 };
@@ -518,7 +535,7 @@ template <typename real> void Engine<real>::size_pass2() {
                 if (g.stepk) {
                     assign_blocks(g.stsegs, g.nt, nsm_ * g.step_occ, &g.stblocks);
                     // scratch of the in-kernel tail (totals + shared_body's working arrays) aliases the accumulators
-                    const size_t tail_d = sums_.n + sh_scratch_.n;
+                    const size_t tail_d = sums_.n + sh_scratch_.n + (size_t)L.K * 3 * g.nt;   // + the linear context
                     g.step_persist = tail_d * sizeof(double) <= (size_t)rows * BLOCK * spb && (int)sums_.n <= 4096;
                 }
             }
@@ -873,6 +890,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         a.stage_ring = (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p && m.update && g.p2stage_ring) ? 1 : 0;
         a.l2_ring = (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p && m.update && !(a.stage_ring && g.p2stage_acc)) ? 1 : 0;
         a.stage_acc = g.p2stage_acc; a.nbuf = g.p2nbuf;
+        a.abort = (xchg_on_ && L.world > 1) ? xchg_err_.p : nullptr;
         if (m.stepk) {
             // the packed step kernel: one step behind the tail (programmatic dependent launch), or -- persistent,
             // cooperative -- m.nsteps steps with the tails of steps 2.. inside the kernel
@@ -886,7 +904,8 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
             const bool trunc = opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p;
             sk.stage_ring = (trunc && g.step_stage_ring) ? 1 : 0;
             sk.l2_ring = (trunc && !g.step_stage_ring) ? 1 : 0;
-            sk.acc_rows = g.step_acc_rows;
+            sk.acc_rows = g.step_acc_rows; sk.tail_scratch = (int)sh_scratch_.n;
+            sk.abort = (xchg_on_ && L.world > 1) ? xchg_err_.p : nullptr;
             sk.xpart = xpart_.p;
             sk.ring_n = trunc ? opt_.n : 0; sk.ring_slot = ring_slot_;
             if (m.nsteps > 1) {
@@ -972,6 +991,8 @@ template <typename real> double Engine<real>::finish_elbo(double *logp_k) {
     if (comm_) {
         int rc = NcclApi::get().AllReduce(elbo_out_.p, elbo_out_.p, L.K + 1, kNcclFloat64, kNcclSum, comm_, stream_);
         if (rc != 0) throw std::runtime_error("ncclAllReduce (elbo) failed");
+    } else if (xchg_on_ && L.world > 1 && !raw_elbo_) {
+        peer_allreduce(elbo_out_.p, (size_t)L.K + 1);
     }
     BB_CUDA(cudaMemcpyAsync(out.data(), elbo_out_.p, sizeof(double) * (L.K + 1), cudaMemcpyDeviceToHost, stream_));
     BB_CUDA(cudaStreamSynchronize(stream_));
@@ -1104,6 +1125,8 @@ template <typename real> void Engine<real>::step(int n, double *trace) {
         if (comm_) {
             int rc = NcclApi::get().AllReduce(trace_.p, trace_.p, (size_t)n * (L.K + 1), kNcclFloat64, kNcclSum, comm_, stream_);
             if (rc != 0) throw std::runtime_error("ncclAllReduce (trace) failed");
+        } else if (xchg_on_ && L.world > 1 && !raw_elbo_) {
+            peer_allreduce(trace_.p, (size_t)n * (L.K + 1));
         }
         std::vector<double> h((size_t)n * (L.K + 1));
         BB_CUDA(cudaMemcpyAsync(h.data(), trace_.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, stream_));
@@ -1156,11 +1179,17 @@ template <typename real> void Engine<real>::time_steps(int n, float *ms_total, f
 }
 
 // ------------------------------------------------------------------ state
-template <typename real> long long Engine<real>::state_size() const { return 2 + 4 * L.D; }
+// [step_count, ring_slot, mu[D], omega[D], acc_mu[D], acc_omega[D]] and, for TruncatedADAGrad, the window itself:
+// n slots of (g_mu^2[D], g_omega^2[D]) in reference order, then the shared latents' ring ((n + 1) x 2 nst pairs, raw).
+// A restored run continues exactly like an uninterrupted one (tests/test_gpu_models.py).
+template <typename real> long long Engine<real>::state_size() const {
+    long long n = 2 + 4 * L.D;
+    if (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD) n += 2LL * opt_.n * L.D + 4LL * L.nst * (opt_.n + 1);
+    return n;
+}
 
 template <typename real> void Engine<real>::get_state(double *s) {
-    // [step_count, ring_slot, mu[D], omega[D], acc_mu[D], acc_omega[D]]; the TruncatedADAGrad ring
-    // (n x 2D) is not serialised -- a restored run restarts its window (documented in DESIGN.md).
+    if (!opt_ready_) set_optimizer(opt_);
     s[0] = (double)step_count; s[1] = (double)ring_slot_;
     get_params(s + 2, s + 2 + L.D, false);
     hostvec_a_.ensure(L.D); hostvec_b_.ensure(L.D);
@@ -1168,30 +1197,56 @@ template <typename real> void Engine<real>::get_state(double *s) {
     BB_CUDA(cudaMemcpyAsync(s + 2 + 2 * L.D, hostvec_a_.p, sizeof(double) * L.D, cudaMemcpyDeviceToHost, stream_));
     BB_CUDA(cudaMemcpyAsync(s + 2 + 3 * L.D, hostvec_b_.p, sizeof(double) * L.D, cudaMemcpyDeviceToHost, stream_));
     BB_CUDA(cudaStreamSynchronize(stream_));
+    if (opt_.kind != BB_OPT_TRUNCATED_ADAGRAD) return;
+    double *r = s + 2 + 4 * L.D;
+    for (int slot = 0; slot < opt_.n; ++slot) {
+        gather_to_ref(lam_ring_.p + (size_t)slot * lam_th_.n, bc_ring_.p + (size_t)slot * bc_th_.n,
+                      hy_ring_.p ? hy_ring_.p + (size_t)slot * hy_th_.n : nullptr, nullptr, hostvec_a_.p, hostvec_b_.p, false);
+        BB_CUDA(cudaMemcpyAsync(r + (size_t)slot * 2 * L.D, hostvec_a_.p, sizeof(double) * L.D, cudaMemcpyDeviceToHost, stream_));
+        BB_CUDA(cudaMemcpyAsync(r + (size_t)slot * 2 * L.D + L.D, hostvec_b_.p, sizeof(double) * L.D, cudaMemcpyDeviceToHost, stream_));
+        BB_CUDA(cudaStreamSynchronize(stream_));
+    }
+    double *rs = r + (size_t)2 * opt_.n * L.D;
+    const size_t nsh = (size_t)4 * L.nst * (opt_.n + 1);
+    if (L.rank == 0) BB_CUDA(cudaMemcpy(rs, sh_ring_.p, sizeof(double) * nsh, cudaMemcpyDeviceToHost));
+    else std::fill(rs, rs + nsh, 0.0);           // replicated on every shard: reported once
 }
 
 template <typename real> void Engine<real>::set_state(const double *s) {
     if (!opt_ready_) set_optimizer(opt_);
     set_params(s + 2, s + 2 + L.D);
-    const double *am = s + 2 + 2 * L.D, *ao = s + 2 + 3 * L.D;
     hostvec_a_.ensure(L.D); hostvec_b_.ensure(L.D);
-    BB_CUDA(cudaMemcpyAsync(hostvec_a_.p, am, sizeof(double) * L.D, cudaMemcpyHostToDevice, stream_));
-    BB_CUDA(cudaMemcpyAsync(hostvec_b_.p, ao, sizeof(double) * L.D, cudaMemcpyHostToDevice, stream_));
-    auto run = [&](r2 *dst, const int *map, size_t n) {
-        if (!n) return;
-        scatter_pairs_kernel<real><<<cdiv(n, 256), 256, 0, stream_>>>(dst, map, (long long)n, hostvec_a_.p,
-                                                                      hostvec_b_.p, 0.0, 0.0);
-        ++launches;
+    auto scatter = [&](const double *x, const double *y, r2 *lam, r2 *bc, r2 *hy) {
+        BB_CUDA(cudaMemcpyAsync(hostvec_a_.p, x, sizeof(double) * L.D, cudaMemcpyHostToDevice, stream_));
+        BB_CUDA(cudaMemcpyAsync(hostvec_b_.p, y, sizeof(double) * L.D, cudaMemcpyHostToDevice, stream_));
+        auto run = [&](r2 *dst, const int *map, size_t n) {
+            if (!n || !dst) return;
+            scatter_pairs_kernel<real><<<cdiv(n, 256), 256, 0, stream_>>>(dst, map, (long long)n, hostvec_a_.p,
+                                                                          hostvec_b_.p, 0.0, 0.0);
+            ++launches;
+        };
+        run(lam, map_lam_.p, lam_th_.n);
+        run(bc, map_bc_.p, bc_th_.n);
+        if (L.hier) run(hy, map_hy_.p, hy_th_.n);
+        BB_CUDA(cudaStreamSynchronize(stream_));
     };
-    run(lam_acc_.p, map_lam_.p, lam_acc_.n);
-    run(bc_acc_.p, map_bc_.p, bc_acc_.n);
-    if (L.hier) run(hy_acc_.p, map_hy_.p, hy_acc_.n);
+    const double *am = s + 2 + 2 * L.D, *ao = s + 2 + 3 * L.D;
+    scatter(am, ao, lam_acc_.p, bc_acc_.p, hy_acc_.p);
     std::vector<double2> sh(2 * L.nst);
     for (int i = 0; i < 2 * L.nst; ++i) sh[i] = make_double2(am[i], ao[i]);
     BB_CUDA(cudaMemcpyAsync(sh_acc_.p, sh.data(), sizeof(double2) * sh.size(), cudaMemcpyHostToDevice, stream_));
     BB_CUDA(cudaStreamSynchronize(stream_));
+    if (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD) {
+        const double *r = s + 2 + 4 * L.D;
+        for (int slot = 0; slot < opt_.n; ++slot)
+            scatter(r + (size_t)slot * 2 * L.D, r + (size_t)slot * 2 * L.D + L.D, lam_ring_.p + (size_t)slot * lam_th_.n,
+                    bc_ring_.p + (size_t)slot * bc_th_.n, hy_ring_.p ? hy_ring_.p + (size_t)slot * hy_th_.n : nullptr);
+        BB_CUDA(cudaMemcpy(sh_ring_.p, r + (size_t)2 * opt_.n * L.D, sizeof(double) * 4 * L.nst * (opt_.n + 1),
+                           cudaMemcpyHostToDevice));
+    }
     step_count = (long long)s[0];
     ring_slot_ = (int)s[1];
+    part_step_ = -1;
 }
 
 // ------------------------------------------------------------------ comm
@@ -1262,10 +1317,58 @@ template <typename real> void Engine<real>::alloc_xchg() {
     if (xchg_mem_) return;
     const size_t P = sums_.n;
     xchg_flag_off_ = ((size_t)2 * L.world * P * sizeof(double) + 255) / 256 * 256;
-    const size_t bytes = xchg_flag_off_ + (size_t)2 * L.world * sizeof(unsigned long long);
+    // behind the step exchange: an auxiliary region [2][world][kAuxP] + flags for short all-reduces (ELBO terms)
+    xchg_aux_off_ = (xchg_flag_off_ + (size_t)2 * L.world * sizeof(unsigned long long) + 255) / 256 * 256;
+    xchg_aux_flag_off_ = xchg_aux_off_ + (size_t)2 * L.world * kAuxP * sizeof(double);
+    const size_t bytes = xchg_aux_flag_off_ + (size_t)2 * L.world * sizeof(unsigned long long);
     BB_CUDA(cudaMalloc(&xchg_mem_, bytes));
     BB_CUDA(cudaMemset(xchg_mem_, 0, bytes));
     if (!xchg_err_.p) xchg_err_.alloc(1);
+}
+
+template <typename real> void Engine<real>::peer_allreduce(double *dev, size_t n) {
+    char *base = static_cast<char *>(xchg_mem_);
+    for (size_t off = 0; off < n; off += kAuxP) {
+        const int m = (int)std::min<size_t>(kAuxP, n - off);
+        ++aux_seq_;
+        XchgPostArgs xp{};
+        xp.P = kAuxP; xp.world = L.world; xp.rank = L.rank; xp.parity = (int)(aux_seq_ & 1ull); xp.seq = aux_seq_;
+        for (int r = 0; r < L.world; ++r) {
+            char *pb = static_cast<char *>(xchg_peer_mem_[r]);
+            xp.peer_buf[r] = reinterpret_cast<double *>(pb + xchg_aux_off_);
+            xp.peer_flag[r] = reinterpret_cast<unsigned long long *>(pb + xchg_aux_flag_off_);
+        }
+        XchgWaitArgs xw{};
+        xw.buf = reinterpret_cast<const double *>(base + xchg_aux_off_);
+        xw.flag = reinterpret_cast<const unsigned long long *>(base + xchg_aux_flag_off_);
+        xw.P = kAuxP; xw.world = L.world; xw.parity = xp.parity; xw.seq = aux_seq_; xw.err = xchg_err_.p;
+        peer_allreduce_kernel<<<1, 256, 0, stream_>>>(dev + off, m, xp, xw);
+        ++launches;
+    }
+}
+
+template <typename real> void Engine<real>::peer_handle(char out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    alloc_xchg();
+    cudaIpcMemHandle_t h;
+    BB_CUDA(cudaIpcGetMemHandle(&h, xchg_mem_));
+    std::memcpy(out, &h, 64);
+}
+
+template <typename real> void Engine<real>::peer_attach(const char *handles, int n) {
+    if (n != L.world) throw std::runtime_error("bb_peer_attach: need one handle per rank (world = " + std::to_string(L.world) + ")");
+    if (L.world > MAX_WORLD) throw std::runtime_error("at most 16 ranks");
+    if (xchg_on_) throw std::runtime_error("bb_peer_attach: the exchange of this handle is already wired");
+    alloc_xchg();
+    xchg_peer_mem_.assign(L.world, nullptr);
+    for (int r = 0; r < L.world; ++r) {
+        if (r == L.rank) { xchg_peer_mem_[r] = xchg_mem_; continue; }
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, handles + (size_t)r * 64, 64);
+        BB_CUDA(cudaIpcOpenMemHandle(&xchg_peer_mem_[r], hd, cudaIpcMemLazyEnablePeerAccess));
+    }
+    xchg_on_ = true;
+    size_pass2();
 }
 
 // single-process multi-GPU: every device's exchange buffer, mapped by peer access (no IPC, no NCCL)
@@ -1293,6 +1396,35 @@ template <typename real> void Engine<real>::check_step_sync() {
         throw std::runtime_error("peer-memory exchange timed out: a rank did not post its partial sums; the steps of "
                                  "this call are incomplete");
     }
+}
+
+template <typename real> void Engine<real>::derived_fitness(int n, uint64_t seed, double *median, double *sd) {
+    if (!L.hier) throw std::runtime_error("derived bc_fitness rows exist for the hierarchical models only");
+    if (n < 1 || n > 12000) throw std::runtime_error("n_samples must be in [1, 12000]");
+    std::vector<int> cols;
+    for (const HostSeg &s : L.segs)
+        if (!s.neutral)
+            for (int i = 0; i < s.ncol; ++i) cols.push_back(s.col0 + i);
+    const size_t nout = (size_t)L.bc_block;
+    DBuf<int> dcols;
+    DBuf<double> dmed, dsd;
+    dcols.upload(cols);
+    dmed.alloc(nout); dsd.alloc(nout);
+    if (!cols.empty()) {
+        DerivedArgs<real> a{};
+        a.cols = dcols.p; a.ncols = (int)cols.size(); a.E = L.E; a.cpad = L.cpad; a.n = n;
+        a.bc_th = bc_th_.p; a.hy_th = hy_th_.p; a.hgroup = hgroup_.p; a.map_tau = map_bc_.p; a.off_tau = L.off_bc[1];
+        a.key = philox_key(seed);
+        a.med = dmed.p; a.sd = dsd.p;
+        const long long items = (long long)cols.size() * L.E;
+        const int grid = (int)std::min<long long>(items, (long long)nsm_ * 5);
+        derived_fitness_kernel<real><<<grid, DERIVED_THREADS, (size_t)n * sizeof(float), stream_>>>(a);
+        ++launches;
+    }
+    BB_CUDA(cudaMemcpyAsync(median, dmed.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaMemcpyAsync(sd, dsd.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, stream_));
+    BB_CUDA(cudaStreamSynchronize(stream_));
+    BB_CUDA(cudaGetLastError());
 }
 
 template <typename real> void Engine<real>::persist_stats(double out[5]) {

@@ -743,6 +743,7 @@ pass2_kernel(const P2Args<real> a) {
     // launched as a programmatic dependent of the tail kernel (fused step): everything above ran beside it,
     // its output (the context) is needed from here on.  A no-op for ordinary launches.
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (a.abort && *reinterpret_cast<const volatile int *>(a.abort)) { cp_async_wait<0>(); return; }
     for (int i = tid; i < a.K * 3 * TT; i += BLOCK) {
         const int k = i / (3 * TT), r = i - k * 3 * TT, j = r / TT, t = r - j * TT;
         sctx[k * CS + j * TT + t] = a.ctx[(((size_t)seg.rep * a.K + k) * 3 + j) * a.tmax_ctx + t];

@@ -142,6 +142,11 @@ template <typename real> class MultiEngine : public EngineBase {
         if (ms_pass2) *ms_pass2 = *std::max_element(c.begin(), c.end());
         refresh();
     }
+    void derived_fitness(int n, uint64_t seed, double *median, double *sd) override {
+        gather2(L.bc_block, median, sd, [&](int i, double *a, double *b) { eng_[i]->derived_fitness(n, seed, a, b); });
+    }
+    void peer_handle(char *) override { throw std::runtime_error("a multi-GPU handle wires its devices itself"); }
+    void peer_attach(const char *, int) override { throw std::runtime_error("a multi-GPU handle wires its devices itself"); }
     void comm_init(const char *) override {}          // the devices of one handle are already connected
     void persist_stats(double out[5]) override { run_on(0, [&] { eng_[0]->persist_stats(out); }); }
     void data_plane(int32_t out[4]) override { eng_[0]->data_plane(out); }

@@ -38,10 +38,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    // a bulk copy that never lands (it cannot, short of a programming error) must not hang the GPU: trap after ~2 s
+    const long long t0 = clock64();
     do {
         asm volatile(
             "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
             : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (!ok && clock64() - t0 > 4000000000LL) asm volatile("trap;");
     } while (!ok);
 }
 // global -> shared bulk copy (TMA 1-D); 16-byte aligned addresses, size a multiple of 16
@@ -82,6 +89,7 @@ template <typename real> struct StepArgs {
     OptArgsT<real> opt;
     int stage_pr, stage_ring, l2_ring;
     int acc_rows;                  // budget of the pass-1 accumulators: rows of BLOCK x (2 slots x W samples)
+    int tail_scratch;              // doubles of shared_body's working arrays (the in-kernel tail borrows the accumulators)
     double *xpart;                 // [gridDim.x][P] block partial sums of the next step, output space [k][q][t]
     int ring_n, ring_slot;         // TruncatedADAGrad: step s uses slot (ring_slot + s - step) % ring_n
     // ---- persistent mode
@@ -91,6 +99,7 @@ template <typename real> struct StepArgs {
     XchgPostArgs xp;               // peers' exchange buffers / flags (world == 1: the local one); seq = first in-kernel exchange
     const double *xbuf;            // local exchange buffer [2][world][P]
     const unsigned long long *xflag;
+    const int *abort;              // set by the tail kernel ahead of this launch when its exchange failed -> return
     SharedArgs<real> sa;           // sh_th / sh_acc / sh_pr global; sh_ring_rd = sh_ring_wr = ring BASE; eps_sh = precomputed noise [nsteps][K][2 nst]
 };
 
@@ -308,9 +317,8 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
     P *sctx = reinterpret_cast<P *>(sp);
     const int npack = a.K / W;
     sp += ((size_t)npack * CSP * sizeof(P) + 127) / 128 * 128;
-    real *ctx_lin = nullptr; double2 *s_sh_th = nullptr, *s_sh_acc = nullptr;
+    double2 *s_sh_th = nullptr, *s_sh_acc = nullptr;
     if (persist) {
-        ctx_lin = reinterpret_cast<real *>(sp); sp += ((size_t)a.K * 3 * NT * sizeof(real) + 127) / 128 * 128;
         s_sh_th = reinterpret_cast<double2 *>(sp); sp += (size_t)2 * (NT - 1) * sizeof(double2);
         s_sh_acc = reinterpret_cast<double2 *>(sp); sp += (size_t)2 * (NT - 1) * sizeof(double2);
         sp = step_smem + ((sp - step_smem) + 127) / 128 * 128;
@@ -428,6 +436,10 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
     // context of the first step: from tail_kernel (launched ahead of this kernel; programmatic dependent launch)
     if (tid == 0 && first < ntile) issue_pre(first, 0);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (a.abort && *reinterpret_cast<const volatile int *>(a.abort)) {
+        if (first < ntile) mbar_wait(bars + 0, 0u);        // the copy in flight must land before the CTA retires
+        return;
+    }
     auto pack_ctx = [&](const real *lin) {           // linear [K][3][NT] -> packs [K/W][3 NT]
         for (int i = tid; i < npack * CSP; i += BLOCK) {
             const int kp = i / CSP, j = i - kp * CSP;
@@ -708,6 +720,7 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
         const long long tc2 = clock64();
         double *tot = reinterpret_cast<double *>(facc);          // the accumulators are flushed: reuse as scratch
         double *scratch = tot + a.P;
+        real *ctx_lin = reinterpret_cast<real *>(scratch + a.tail_scratch);    // linear context [K][3][T] of the next step
         for (int j = tid; j < a.P; j += BLOCK) {
             double s = 0.0;
             for (int r = 0; r < world; ++r) s += __ldcg(a.xbuf + (size_t)(parity * world + r) * a.P + j);

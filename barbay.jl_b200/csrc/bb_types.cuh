@@ -106,6 +106,7 @@ template <typename real> struct P2Args {
     double *part;          // fused step: block partial sums of the next step's pass 1, [K][pv][gridDim.x]
     int pv;                // row stride of part (3 nt - 2)
     int acc_slots;         // fused step: rows of BLOCK accumulators in shared memory
+    const int *abort;      // multi-GPU: set by the tail kernel when the exchange of this step failed -> no update
     SupArgs<real> sup;
 };
 

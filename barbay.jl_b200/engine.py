@@ -23,7 +23,7 @@ class Engine:
 
     def __init__(self, data_arrays, model, model_kwargs=None, *, n_samples: int = 1, dtype: str = "f64",
                  seed: int = 0, device: int = -1, rank: int = 0, world: int = 1, corrected_ragged: bool = True,
-                 n_devices: int = 1):
+                 n_devices: int = 1, probe_only: bool = False):
         self._h = C.c_void_p()
         self._lib = _lib.load()
         self.model = _model.resolve(model)
@@ -119,6 +119,18 @@ class Engine:
         self.layout = _model.var_groups(self.model, n_time, n_rep, da.n_neutral, da.n_bc, n_env, n_geno)
         self.n_samples = int(n_samples)
         self.rank, self.world = int(rank), int(world)
+        if probe_only:
+            # host-only dry run of the shard layout (bb_layout_probe: no CUDA call, works without a GPU)
+            D = self.layout.n_latent
+            self.owned = np.zeros(D, dtype=np.int32)
+            info = (C.c_int64 * 8)()
+            rc = self._lib.bb_layout_probe(C.byref(desc), self.owned.ctypes.data_as(C.POINTER(C.c_int32)), info)
+            if rc != 0:
+                raise BarBayError(self._lib.bb_last_error(None).decode("utf8", "replace"))
+            keys = ("D", "n0", "n1", "m0", "m1", "H", "hy_gid0", "cpad")
+            self.probe_info = dict(zip(keys, [int(x) for x in info]))
+            self.D = self.probe_info["D"]
+            return
         rc = self._lib.bb_create(C.byref(desc), C.byref(self._h))
         if rc != 0:
             msg = self._lib.bb_last_error(None).decode("utf8", "replace")
@@ -216,6 +228,15 @@ class Engine:
         self._check(self._lib.bb_step(self._h, int(n_steps), None))
         return None
 
+    def step_until(self, max_iters: int, every: int = 100, window: int = 5, rel_tol: float = 1e-4):
+        """Run until the ELBO estimate (one every ``every`` steps) stops moving: returns (steps done, converged,
+        ELBO estimates).  An extension -- the reference always runs ``max_iters`` (src/vi.jl:98)."""
+        n_done, conv, n_elbo = C.c_int32(), C.c_int32(), C.c_int32()
+        est = np.empty(max(1, max_iters // max(every, 1) + 1))
+        self._check(self._lib.bb_step_until(self._h, int(max_iters), int(every), int(window), float(rel_tol),
+                                            C.byref(n_done), C.byref(conv), _c_doubles(est), C.byref(n_elbo)))
+        return int(n_done.value), bool(conv.value), est[:n_elbo.value].copy()
+
     def step_with_noise(self, eps):
         eps = np.ascontiguousarray(eps, dtype=np.float64).reshape(self.n_samples, self.D)
         self._check(self._lib.bb_step_with_noise(self._h, _c_doubles(eps)))
@@ -254,6 +275,15 @@ class Engine:
         self._check(self._lib.bb_time_steps(self._h, int(n_steps), C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def derived_fitness(self, n_samples: int = 10_000, seed: int = 0):
+        """(median, sd) of ``n_samples`` draws of θ + exp(logτ) θ̃ per logτ row, from the current posterior, on the
+        device (utils.jl:1284-1343; hierarchical models only)."""
+        n = int(self._lib.bb_n_derived(self._h))
+        med, sd = np.zeros(n), np.zeros(n)
+        self._check(self._lib.bb_derived_fitness(self._h, int(n_samples), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                 _c_doubles(med), _c_doubles(sd)))
+        return med, sd
+
     def data_plane(self) -> dict:
         """Which kernels / exchange this handle runs (for reporting)."""
         out = (C.c_int32 * 4)()
@@ -271,6 +301,19 @@ class Engine:
             return {"tails": 0}
         us = lambda cyc: cyc / n / khz * 1e3
         return {"tails": int(n), "column_us": us(out[0]), "exchange_us": us(out[1]), "context_us": us(out[2])}
+
+    def peer_handle(self) -> bytes:
+        """CUDA IPC handle of this rank's exchange buffer (64 bytes): gather them in rank order, then ``peer_attach``."""
+        buf = (C.c_char * 64)()
+        self._check(self._lib.bb_peer_handle(self._h, buf))
+        return bytes(buf.raw)
+
+    def peer_attach(self, handles):
+        """Wire the per-step exchange over NVLink peer memory from the ranks' handles (no NCCL communicator)."""
+        blob = b"".join(handles)
+        if len(blob) != 64 * len(handles):
+            raise BarBayError("peer handles are 64 bytes each")
+        self._check(self._lib.bb_peer_attach(self._h, blob, len(handles)))
 
     def comm_init(self, unique_id: bytes):
         buf = (C.c_char * 128).from_buffer_copy(unique_id)

@@ -106,7 +106,7 @@ function vi(da, model::Function, model_kwargs::Dict, advi, opt; seed::Integer=0,
         isempty(geno_idx) ? 0 : length(unique(geno_idx)), isempty(geno_idx) ? C_NULL : pointer(geno_idx),
         getp(:s_pop_prior, [0.0, 2.0]), getp(:logσ_pop_prior, [0.0, 1.0]), getp(:s_bc_prior, [0.0, 2.0]),
         getp(:logσ_bc_prior, [0.0, 1.0]), getp(:logλ_prior, [3.0, 3.0]), getp(:logτ_prior, [-2.0, 1.0]),
-        1, advi.samples_per_step, UInt64(seed), Int32(device), 0, 1, Int32(n_devices))
+        0, advi.samples_per_step, UInt64(seed), Int32(device), 0, 1, Int32(n_devices))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep begin
         rc = ccall((:bb_create, LIB), Cint, (Ref{BBDesc}, Ref{Ptr{Cvoid}}), desc, h)

@@ -317,13 +317,15 @@ def add_barcode_info(df, var_groups, var_range, output: DataArrays, genotype_col
 
 
 def process_hierarchical_samples(df: pd.DataFrame, output: DataArrays, n_samples: int, genotype_col=None,
-                                 seed: int | None = None, chunk: int = 4096) -> pd.DataFrame:
+                                 seed: int | None = None, chunk: int = 4096, derived=None) -> pd.DataFrame:
     """utils.jl:1284-1343: s = θ + exp(logτ) θ̃ from ``n_samples`` Normal draws per variable;
     the appended ``bc_fitness`` rows carry the *median* in ``mean`` (quirk 5) and the sample std.
 
     The genotype case indexes θ by genotype (``θ_mat[:, geno_idx]``), the evident intent of
     utils.jl:1310, which in the reference only runs when G == 1 or G == M.
     Columns are processed in chunks so 10^6 barcodes do not need n_samples x M x R doubles at once.
+    ``derived`` = (median, sd) per logτ row computed on the device (``Engine.derived_fitness``) replaces the host
+    sampling: at 10^6 barcodes the 3 x 10^4 host normals per row cost more than the whole fit.
     """
     rng = np.random.default_rng(seed)
     vt = df["vartype"].to_numpy()
@@ -340,7 +342,11 @@ def process_hierarchical_samples(df: pd.DataFrame, output: DataArrays, n_samples
     # theta samples; the reference reuses one draw matrix across replicates, which has the same marginals.
     med = np.empty(n_out)
     sd = np.empty(n_out)
-    for a in range(0, n_out, chunk):
+    if derived is not None:
+        med, sd = np.asarray(derived[0], dtype=np.float64), np.asarray(derived[1], dtype=np.float64)
+        if med.shape != (n_out,) or sd.shape != (n_out,):
+            raise ValueError("derived rows do not match the logτ rows")
+    for a in range(0, n_out if derived is None else 0, chunk):
         b = min(n_out, a + chunk)
         idx = th_index[a:b]
         th_s = rng.normal(th[idx, 0], th[idx, 1], size=(n_samples, b - a))
@@ -362,7 +368,8 @@ def process_hierarchical_samples(df: pd.DataFrame, output: DataArrays, n_samples
 
 def advi_to_df(data: pd.DataFrame, dist: MeanFieldPosterior, vars: list, *, id_col="barcode", time_col="time",
                count_col="count", neutral_col="neutral", rep_col=None, env_col=None, genotype_col=None,
-               n_samples: int = 10_000, seed: int | None = None, output: DataArrays | None = None) -> pd.DataFrame:
+               n_samples: int = 10_000, seed: int | None = None, output: DataArrays | None = None,
+               derived=None) -> pd.DataFrame:
     """utils.jl:1409-1462.  ``output`` lets a caller that already packed ``data`` skip the second
     data_to_arrays call the reference makes (:1423-1432)."""
     if output is None:
@@ -385,5 +392,5 @@ def advi_to_df(data: pd.DataFrame, dist: MeanFieldPosterior, vars: list, *, id_c
         add_environment_info(df, var_groups, var_range, output, env_col)
     add_barcode_info(df, var_groups, var_range, output, genotype_col)
     if len(var_groups) == 7 and (output.n_rep > 1 or genotype_col is not None):   # :1457
-        df = process_hierarchical_samples(df, output, n_samples, genotype_col, seed)
+        df = process_hierarchical_samples(df, output, n_samples, genotype_col, seed, derived=derived)
     return df

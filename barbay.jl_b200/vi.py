@@ -56,7 +56,8 @@ def advi(*, data, model, outputname=None, model_kwargs=None, id_col="barcode", t
          count_col="count", neutral_col="neutral", rep_col=None, env_col=None, genotype_col=None,
          advi=None, opt=None, verbose=True,
          # backend extras (not part of the reference signature; defaults keep its behaviour)
-         seed=0, dtype="f64", device=-1, n_devices=1, n_posterior_samples=10_000, return_engine=False):
+         seed=0, dtype="f64", device=-1, n_devices=1, n_posterior_samples=10_000, return_engine=False,
+         elbo_rel_tol=None, elbo_every=100, elbo_window=5, device_derived_rows=True):
     """Fit the mean-field Gaussian posterior of a BarBay model with ADVI on a B200.
 
     Returns the tidy posterior ``DataFrame`` (columns ``mean, std, varname, vartype[, rep][, env], id``)
@@ -64,6 +65,8 @@ def advi(*, data, model, outputname=None, model_kwargs=None, id_col="barcode", t
 
     ``n_devices`` > 1 shards the barcodes over that many GPUs of this process inside the library (one handle, one
     blocking call per step batch, per-step exchange over NVLink peer memory): same posterior as one GPU.
+    ``elbo_rel_tol`` (extension; the reference always runs ``max_iters``, src/vi.jl:98): stop early once the mean of
+    the last ``elbo_window`` ELBO estimates (one every ``elbo_every`` steps) moves by less than that fraction.
     """
     mdl = _model.resolve(model)
     advi_cfg = advi if advi is not None else ADVI(1, 10_000)
@@ -95,14 +98,24 @@ def advi(*, data, model, outputname=None, model_kwargs=None, id_col="barcode", t
     var_names = eng.layout.var_names                                                      # vi.jl:184-198
     eng.init_params(seed)                                                                 # Turing meanfield()
     _apply_optimizer(eng, opt)
-    eng.step(advi_cfg.max_iters)                                                          # vi.jl:201
+    if elbo_rel_tol is None:
+        eng.step(advi_cfg.max_iters)                                                      # vi.jl:201
+    else:
+        n_done, conv, _ = eng.step_until(advi_cfg.max_iters, elbo_every, elbo_window, elbo_rel_tol)
+        if verbose:
+            logger.info("ADVI stopped after %d of %d steps (%s)", n_done, advi_cfg.max_iters,
+                        "ELBO converged" if conv else "max_iters reached")
     m, sigma = eng.get_posterior()
     q = _utils.MeanFieldPosterior.build(m, sigma, eng.layout.ranges_out)
 
+    # derived bc_fitness rows (utils.jl:1284-1343): sampled on the device from the fitted posterior
+    derived = None
+    if mdl.hier and device_derived_rows and (data_arrays.n_rep > 1 or genotype_col is not None):
+        derived = eng.derived_fitness(min(int(n_posterior_samples), 12000), seed)
     df = _utils.advi_to_df(data, q, var_names, id_col=id_col, time_col=time_col, count_col=count_col,
                            neutral_col=neutral_col, rep_col=rep_col, env_col=env_col,
                            genotype_col=genotype_col, n_samples=n_posterior_samples, seed=seed,
-                           output=data_arrays)
+                           output=data_arrays, derived=derived)
     if return_engine:
         return df, eng
     eng.close()

@@ -255,13 +255,24 @@ class Ctx:
         rank, world = (self.rank, self.world) if sharded else (0, 1)
         eng = bb.Engine(da, model, n_samples=K, dtype=dtype, seed=seed, device=self.local_rank, rank=rank, world=world)
         if world > 1:
-            uid = [bb.comm_unique_id() if rank == 0 else None]
-            self.dist.broadcast_object_list(uid, src=0)
-            eng.comm_init(uid[0])
+            self.wire(eng)
         eng.set_stream(self.stream.cuda_stream)
         eng.init_params(1)
         eng.set_optimizer(opt)
         return eng
+
+    def wire(self, eng):
+        """Connect the ranks' handles: CUDA IPC handles of the exchange buffers gathered over torch.distributed
+        (bb_peer_attach: no communicator inside the library); BB_BENCH_NCCL=1 -> bb_comm_init (ncclCommInitRank)."""
+        import barbay_b200 as bb
+        if os.environ.get("BB_BENCH_NCCL"):
+            uid = [bb.comm_unique_id() if self.rank == 0 else None]
+            self.dist.broadcast_object_list(uid, src=0)
+            eng.comm_init(uid[0])
+        else:
+            hs = [None] * self.world
+            self.dist.all_gather_object(hs, eng.peer_handle())
+            eng.peer_attach(hs)
 
     def time_steps(self, eng, steps, warmup):
         """(ms over `steps` steps, max over ranks; launches) -- CUDA events on the launching stream."""
@@ -430,10 +441,8 @@ def run_ours(args, emit):
     t_comm = 0.0
     if world > 1:
         tc0 = time.perf_counter()
-        uid2 = [bb.comm_unique_id() if rank == 0 else None]
-        cx.dist.broadcast_object_list(uid2, src=0)
-        eng2.comm_init(uid2[0])
-        t_comm = time.perf_counter() - tc0       # one-time per process: NCCL communicator + CUDA IPC peer mappings
+        cx.wire(eng2)
+        t_comm = time.perf_counter() - tc0       # gather of the ranks' IPC handles + peer mappings (no NCCL communicator)
     eng2.init_params(1)
     eng2.set_optimizer(args.opt)
     eng2.step(n_e2e)

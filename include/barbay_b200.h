@@ -108,6 +108,14 @@ const char *bb_last_error(const bb_handle *h);   /* h may be NULL: error of the 
 int64_t bb_n_latent(const bb_handle *h);          /* D */
 int32_t bb_abi_version(void);
 
+/* Host-only dry run of the shard layout (no CUDA call; usable without a GPU): which latents of the reference's
+ * VarInfo order the shard (desc->rank, desc->world) owns.  owned[i] (i < D, caller-allocated, may be NULL) = number of
+ * device slots that map to latent i on this shard: over all ranks every latent must be owned exactly once (the
+ * replicated population latents are reported by rank 0).  info[8] = {D, first / end neutral column, first / end
+ * mutant position (genotype models: in the genotype-sorted order), hyper latents owned, first global hyper index,
+ * padded columns}.  Same validation and error messages as bb_create. */
+int bb_layout_probe(const bb_desc *desc, int32_t *owned, int64_t info[8]);
+
 /* ---- variational parameters theta = (mu, omega), sigma = softplus(omega) ---- */
 int bb_init_params(bb_handle *h, uint64_t seed);                         /* meanfield(): mu, omega ~ N(0,1) */
 int bb_set_params(bb_handle *h, const double *mu, const double *omega);  /* [D] each */
@@ -128,8 +136,19 @@ int bb_set_optimizer(bb_handle *h, const bb_opt *opt);                   /* rese
 int bb_step(bb_handle *h, int32_t n_steps, double *elbo_trace);          /* elbo_trace: [n_steps] or NULL */
 int bb_step_with_noise(bb_handle *h, const double *eps);                 /* one step with caller noise eps[K*D] */
 int64_t bb_step_count(const bb_handle *h);
+/* ELBO-trace convergence stop -- an extension: the reference always runs max_iters steps (src/vi.jl:98, 201).
+ * Steps run in blocks of `every` (every - 1 production steps + 1 step that also evaluates the ELBO); the run stops
+ * when the mean of the last `window` ELBO estimates differs from the mean of the `window` estimates before them by
+ * at most rel_tol * |mean|, or after max_iters steps.  n_done / converged are outputs; elbo_out (nullable) receives
+ * the estimates, at most max_iters / every + 1 of them, *n_elbo their number. */
+int bb_step_until(bb_handle *h, int32_t max_iters, int32_t every, int32_t window, double rel_tol, int32_t *n_done,
+                  int32_t *converged, double *elbo_out, int32_t *n_elbo);
 
-/* ---- state (checkpoint / resume; the reference keeps none) ---- */
+/* ---- state (checkpoint / resume; the reference keeps none) ----
+ * [step_count, ring_slot, mu[D], omega[D], acc_mu[D], acc_omega[D]] and, for TruncatedADAGrad, the whole window
+ * (n slots of squared gradients in latent order + the shared latents' ring): 2 + 4 D (+ 2 n D + 4 nst (n + 1))
+ * doubles, bb_state_size() for the current optimiser.  A run restored on a fresh handle (same problem, same
+ * optimiser) continues exactly like the uninterrupted one. */
 int64_t bb_state_size(const bb_handle *h);                               /* doubles needed by get/set_state */
 int bb_get_state(bb_handle *h, double *state);
 int bb_set_state(bb_handle *h, const double *state);
@@ -148,9 +167,24 @@ int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_pass
  * in-kernel tails since the last call; out[3] = number of such tails, out[4] = SM clock in kHz.  Resets the counters. */
 int bb_persist_stats(bb_handle *h, double out[5]);
 
+/* Derived `bc_fitness` rows of the hierarchical models: utils.advi_to_df -> process_hierarchical_samples!
+ * (src/utils.jl:1284-1343) draws n_samples (default 10 000) of theta + exp(log-tau) * theta-tilde per
+ * (barcode[, environment], replicate) from the fitted Normals and reports their median (`mean` column, :1315) and
+ * sample standard deviation.  Computed on the device from the handle's current posterior; median / sd have
+ * bb_n_derived() entries in the order of the log-tau rows (entries owned by other shards are 0). */
+int bb_derived_fitness(bb_handle *h, int32_t n_samples, uint64_t seed, double *median, double *sd);
+int64_t bb_n_derived(const bb_handle *h);
+
 /* Which kernels / data plane this handle runs: out = {packed step kernel in use, steps per persistent launch
  * (0: one launch pair per step), NVLink peer-memory exchange on, NCCL communicator present}. */
 int bb_data_plane(bb_handle *h, int32_t out[4]);
+
+/* ---- multi-GPU, one process per GPU, WITHOUT NCCL: every rank exports the CUDA IPC handle (64 bytes) of its
+ * exchange buffer, the caller gathers the `world` handles in rank order with whatever transport it has
+ * (torch.distributed / MPI / Distributed.jl / a file) and attaches them.  The per-step exchange and the ELBO
+ * reductions then run over NVLink peer memory only; no communicator is created (saves ~1-3 s of ncclCommInitRank). */
+int bb_peer_handle(bb_handle *h, char out[64]);
+int bb_peer_attach(bb_handle *h, const char *handles /* [world][64] */, int32_t n);
 
 /* ---- multi-GPU: one process per GPU; id is an ncclUniqueId (128 bytes) ---- */
 int bb_comm_unique_id(char id[128]);

@@ -16,6 +16,6 @@ e0.record(s); eng.step(n); e1.record(s); torch.cuda.synchronize()
 plain = e0.elapsed_time(e1) / n * 1e3
 tot, p1, p2 = eng.time_steps(n)
 R = np.asarray(da.bc_count); units = R.size * K
-print(json.dumps({"cfg": cfg, "K": K, "opt": os.environ.get("QOPT", "decayed"), "nofuse": os.environ.get("BB_NO_FUSE"),
+print(json.dumps({"plane": eng.data_plane(), "persist": eng.persist_stats(), "cfg": cfg, "K": K, "opt": os.environ.get("QOPT", "decayed"), "nofuse": os.environ.get("BB_NO_FUSE"),
                   "step_us": plain, "bracketed_step_us": tot/n*1e3, "p1_us": p1/n*1e3, "p2_us": p2/n*1e3,
                   "units_per_s": units/(plain*1e-6), "alg_GBs_step": eng.algorithmic_bytes_per_step/(plain*1e-6)/1e9}))

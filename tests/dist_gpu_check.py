@@ -21,6 +21,7 @@ CFG = {"fitness_normal": 2, "replicate_fitness_normal": 3, "multienv_fitness_nor
 def main():
     model = sys.argv[1] if len(sys.argv) > 1 else "fitness_normal"
     dtype = sys.argv[2] if len(sys.argv) > 2 else "f64"
+    wiring = sys.argv[3] if len(sys.argv) > 3 else "peer"        # peer: bb_peer_attach (no NCCL in the library) | nccl
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -29,10 +30,14 @@ def main():
 
     def run(r, w):
         eng = bb.Engine(da, model, n_samples=K, dtype=dtype, seed=11, device=local, rank=r, world=w)
-        if w > 1:
+        if w > 1 and wiring == "nccl":
             uid = [bb.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             eng.comm_init(uid[0])
+        elif w > 1:
+            hs = [None] * w
+            dist.all_gather_object(hs, eng.peer_handle())
+            eng.peer_attach(hs)
         eng.init_params(5)
         eng.set_optimizer("truncated", n=4)
         trace = eng.step(steps, elbo_trace=True)
@@ -48,7 +53,7 @@ def main():
     m_d, s_d = t[0].cpu().numpy(), t[1].cpu().numpy()
     if rank == 0:
         trace_1, m_1, s_1 = run(0, 1)
-        out = {"model": model, "world": world, "dtype": dtype,
+        out = {"model": model, "world": world, "dtype": dtype, "wiring": wiring,
                "elbo_rel": float(np.max(np.abs(trace_d - trace_1) / np.abs(trace_1))),
                "mean_rel": float(np.max(np.abs(m_d - m_1)) / np.max(np.abs(m_1))),
                "std_rel": float(np.max(np.abs(s_d - s_1)) / np.max(np.abs(s_1))),

@@ -4,6 +4,7 @@ import os
 import sys
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -53,3 +54,52 @@ def test_shard_ranges_partition_everything():
         assert ns[0][0][0] == 0 and ns[-1][0][1] == N and ns[0][1][0] == 0 and ns[-1][1][1] == M
         for a, b in zip(ns[:-1], ns[1:]):
             assert a[0][1] == b[0][0] and a[1][1] == b[1][0]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The PRODUCT's shard logic (csrc/bb_layout.cpp), driven through the C ABI on the CPU: bb_layout_probe runs
+# build_layout without any CUDA call.
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("model,spec", [
+    ("fitness_normal", dict(n_neutral=37, n_bc=901, n_time=5)),
+    ("replicate_fitness_normal", dict(n_neutral=20, n_bc=333, n_time=5, n_rep=3)),
+    ("multienv_fitness_normal", dict(n_neutral=11, n_bc=257, n_time=6, envs=[1, 1, 2, 3, 2, 3])),
+    ("genotype_fitness_normal", dict(n_neutral=16, n_bc=600, n_time=5, n_geno=23)),
+    ("multienv_replicate_fitness_normal", dict(n_neutral=9, n_bc=130, n_time=6, n_rep=2, envs=[1, 2, 3, 1, 2, 3])),
+])
+def test_product_shard_layout_owns_every_latent_exactly_once(model, spec, world):
+    """Over the ranks of a `world`-way split every latent of the reference order is owned by exactly one shard
+    (population latents: rank 0), neutral / mutant ranges tile the barcode axis, and -- genotype model -- no genotype
+    group is cut (so theta_g needs no exchange)."""
+    import barbay_b200 as bb
+    da, _ = bb.synth.simulate(model, seed=5, **spec)
+    total = None
+    prev_n1 = prev_m1 = 0
+    g_of = None
+    if "genotype" in model:
+        _, gidx = bb.model.indexin_unique(list(da.genotypes))
+        order = np.argsort(np.asarray(gidx), kind="stable")          # the library's genotype-sorted mutant order
+        g_of = np.asarray(gidx)[order]
+    hyper_owned = 0
+    for rank in range(world):
+        pr = bb.Engine(da, model, n_samples=2, rank=rank, world=world, probe_only=True)
+        info = pr.probe_info
+        total = pr.owned.astype(np.int64) if total is None else total + pr.owned
+        assert info["n0"] == prev_n1 and info["m0"] == prev_m1          # contiguous ranges, rank order
+        prev_n1, prev_m1 = info["n1"], info["m1"]
+        hyper_owned += info["H"]
+        if g_of is not None and 0 < info["m0"] < da.n_bc:
+            assert g_of[info["m0"]] != g_of[info["m0"] - 1]            # cut on a genotype boundary
+    assert prev_n1 == da.n_neutral and prev_m1 == da.n_bc
+    assert total.min() == 1 and total.max() == 1
+    if "genotype" in model:
+        assert hyper_owned == da.n_geno
+    one = bb.Engine(da, model, n_samples=2, probe_only=True)
+    assert one.owned.min() == 1 and one.owned.max() == 1 and one.D == total.size
+
+
+def test_product_layout_probe_validation_messages():
+    import barbay_b200 as bb
+    da, _ = bb.synth.simulate("fitness_normal", n_neutral=4, n_bc=9, n_time=4, seed=1)
+    with pytest.raises(bb.BarBayError, match="rank, world"):
+        bb.Engine(da, "fitness_normal", rank=3, world=2, probe_only=True)

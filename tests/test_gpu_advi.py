@@ -50,33 +50,50 @@ def test_advi_csv_output(bb, tmp_path):
         bb.advi(data=df, model=bb.model.fitness_normal, outputname=name, advi=bb.ADVI(1, 1), verbose=False)
 
 
-def test_posterior_matches_restated_cpu_advi(bb):
-    """Converged posterior mean / sd vs the oracle's ADVI (different noise streams): agreement within
-    Monte-Carlo error.  Both run 1500 steps of DecayedADAGrad with 4 samples per step."""
-    from oracle import advi_ref, philox_ref
-    model = "fitness_normal"
+@pytest.mark.parametrize("model", list(FIXTURES))
+def test_averaged_posterior_matches_restated_cpu_advi(bb, model):
+    """Converged posterior vs the restated CPU ADVI (oracle C port: same optimiser, its own xoshiro noise stream),
+    all four model families.  Both chains run 4000 burn-in steps of DecayedADAGrad(0.03) with 4 samples per step and
+    then average 300 iterates taken every 10 steps, which removes the optimiser's jitter: two independent CPU chains
+    agree to 0.05 sd / 3 % this way, so the gate is |mean_gpu - mean_cpu| <= 0.25 sd and sd within 10 % for every
+    latent above the log-Poisson block (population, hyper and barcode latents), and 0.05 absolute / 35 % for the
+    log-Poisson latents (sd ~ 1e-3 for large counts: their iterates never settle below the step size)."""
+    from oracle import cport
     df, cols = load_fixture(model)
-    da = bb.utils.data_to_arrays(df)
-    priors = {"logλ_prior": np.column_stack([np.log(np.asarray(da.bc_count).T.reshape(-1) + 1.0),
-                                             np.full(np.asarray(da.bc_count).size, 3.0)])}
-    eng = bb.Engine(da, model, dict(priors), n_samples=4, dtype="f64", seed=17)
+    da = bb.utils.data_to_arrays(df, **cols)
+    burn, blocks, every, K, eta = 4000, 300, 10, 4, 0.03
+    pp = cport.ModelPort(model, da.bc_count, da.n_neutral, da.n_bc, envs=da.envs, genotypes=da.genotypes)
+    rng = np.random.default_rng(1)
+    D = pp.D
+    theta = np.concatenate([rng.standard_normal(D), rng.standard_normal(D)])
+    acc = np.full(2 * D, 1e-8)
+    pp.advi_steps(theta, acc, burn, K, eta=eta, seed=1)
+    m_cpu, s_cpu = np.zeros(D), np.zeros(D)
+    for b in range(blocks):
+        pp.advi_steps(theta, acc, every, K, eta=eta, seed=1, first_step=burn + b * every)
+        m_cpu += theta[:D] / blocks
+        s_cpu += np.log1p(np.exp(theta[D:])) / blocks
+
+    eng = bb.Engine(da, model, n_samples=K, dtype="f64", seed=17)
+    assert eng.D == D
     eng.init_params(3)
-    mu0, om0 = eng.get_params()
-    eng.set_optimizer("decayed", eta=0.05)
-    eng.step(1500)
-    m_gpu, s_gpu = eng.get_posterior()
+    eng.set_optimizer("decayed", eta=eta)
+    eng.step(burn)
+    m_gpu, s_gpu = np.zeros(D), np.zeros(D)
+    for b in range(blocks):
+        eng.step(every)
+        m, s = eng.get_posterior()
+        m_gpu += m / blocks
+        s_gpu += s / blocks
     eng.close()
-    prob = oracle_problem(da, model, priors=priors)
-    tr = advi_ref.advi_run(model, prob, 1500, 4, advi_ref.DecayedADAGrad(0.05), mu0, om0, seed=99)
-    m_cpu, s_cpu = tr.mu, tr.sigma
-    lay = bb.model.var_groups(bb.model.fitness_normal, da.n_time, 1, da.n_neutral, da.n_bc)
-    g = {x.name: x for x in lay.groups}
-    sl = slice(g[bb.model.V_S_BC].start, g[bb.model.V_S_BC].start + da.n_bc)
-    # stated bound: |Δmean| <= 4 posterior sd (both chains still jitter with the AdaGrad step) and sd within 50 %
-    assert np.all(np.abs(m_gpu[sl] - m_cpu[sl]) <= 4 * np.maximum(s_gpu[sl], s_cpu[sl]) + 0.02)
-    assert np.all(np.abs(np.log(s_gpu[sl] / s_cpu[sl])) < 0.7)
-    pop = slice(g[bb.model.V_S_POP].start, g[bb.model.V_S_POP].start + g[bb.model.V_S_POP].length)
-    assert np.all(np.abs(m_gpu[pop] - m_cpu[pop]) <= 4 * np.maximum(s_gpu[pop], s_cpu[pop]) + 0.02)
+    n_lam = int(np.sum([np.asarray(c).size for c in da.bc_count])) if isinstance(da.bc_count, list) else np.asarray(da.bc_count).size
+    head, lam = slice(0, D - n_lam), slice(D - n_lam, D)
+    sd = np.maximum(s_gpu, s_cpu)
+    z = np.abs(m_gpu - m_cpu)[head] / sd[head]
+    assert z.max() <= 0.25, (model, z.max())
+    assert np.abs(s_gpu / s_cpu - 1.0)[head].max() <= 0.10, (model, np.abs(s_gpu / s_cpu - 1.0)[head].max())
+    assert np.abs(m_gpu - m_cpu)[lam].max() <= 0.05, (model, np.abs(m_gpu - m_cpu)[lam].max())
+    assert np.abs(s_gpu / s_cpu - 1.0)[lam].max() <= 0.35, (model, np.abs(s_gpu / s_cpu - 1.0)[lam].max())
 
 
 def test_recovers_simulator_ground_truth(bb):
@@ -115,3 +132,45 @@ def test_documented_workflow_with_naive_priors(bb):
     assert np.all(np.abs(pop["mean"].to_numpy() - pri["s_pop_prior"][:, 0]) < 0.2)
     assert list(out.columns) == ["mean", "std", "varname", "vartype", "id"]
     assert np.isfinite(out["mean"]).all() and (out["std"] > 0).all()
+
+
+def test_elbo_trace_convergence_stop(bb):
+    """bb_step_until (extension; the reference runs a fixed max_iters, src/vi.jl:98): stops once the windowed ELBO
+    mean stops moving, reports the estimates it used, and degenerates to a plain max_iters run with rel_tol = 0."""
+    df, _ = load_fixture("fitness_normal")
+    da = bb.utils.data_to_arrays(df)
+    eng = bb.Engine(da, "fitness_normal", n_samples=4, dtype="f64", seed=2)
+    eng.init_params(1)
+    eng.set_optimizer("decayed", eta=0.05)
+    n_done, conv, est = eng.step_until(20000, every=50, window=4, rel_tol=2e-3)
+    assert conv and n_done < 20000 and n_done % 50 == 0 and len(est) == n_done // 50
+    assert eng.step_count == n_done
+    assert est[-1] > est[0]                                    # the ELBO went up on the way
+    n2, conv2, est2 = eng.step_until(130, every=50, window=2, rel_tol=0.0)
+    assert n2 == 130 and not conv2 and len(est2) == 3 and eng.step_count == n_done + 130
+    eng.close()
+    out = bb.advi(data=df, model=bb.model.fitness_normal, advi=bb.ADVI(4, 20000), opt=bb.DecayedADAGrad(0.05),
+                  verbose=False, seed=2, elbo_rel_tol=2e-3, elbo_every=50, elbo_window=4, n_posterior_samples=100)
+    assert np.isfinite(out["mean"]).all()
+
+
+@pytest.mark.parametrize("model", ["replicate_fitness_normal", "genotype_fitness_normal"])
+def test_device_derived_fitness_rows_match_host_sampler(bb, model):
+    """The derived bc_fitness rows (utils.jl:1284-1343: median and sd of 10^4 draws of θ + exp(logτ) θ̃) sampled on the
+    device agree with the host sampler (numpy, its own stream) within Monte-Carlo error: the median's standard error
+    is 1.25 sd / sqrt(n) = 0.0125 sd, the sd's 0.7 % (x ~1.5 for the exp(logτ) tail)."""
+    df, cols = load_fixture(model)
+    kw = dict(data=df, model=getattr(bb.model, model), advi=bb.ADVI(2, 300), opt=bb.DecayedADAGrad(0.05),
+              verbose=False, seed=4, **cols)
+    dev = bb.advi(**kw, device_derived_rows=True)
+    host = bb.advi(**kw, device_derived_rows=False)
+    assert list(dev.columns) == list(host.columns) and len(dev) == len(host)
+    a = dev[dev.vartype == "bc_fitness"].reset_index(drop=True)
+    b = host[host.vartype == "bc_fitness"].reset_index(drop=True)
+    assert len(a) > 0 and (a["varname"] == b["varname"]).all() and (a["id"] == b["id"]).all()
+    sd = b["std"].to_numpy()
+    assert np.max(np.abs(a["mean"].to_numpy() - b["mean"].to_numpy()) / sd) < 0.08
+    assert np.max(np.abs(a["std"].to_numpy() / sd - 1.0)) < 0.06
+    # the fitted rows themselves are untouched by the choice
+    fa, fb = dev[dev.vartype != "bc_fitness"], host[host.vartype != "bc_fitness"]
+    assert np.array_equal(fa["mean"].to_numpy(), fb["mean"].to_numpy())

@@ -1,0 +1,63 @@
+"""GPU parity at the BASELINE sizes against an oracle (not against the GPU itself).
+
+The compiled C/OpenMP port of the reference algorithm (oracle/c/advi_port_models.c, validated against the torch
+transliteration in tests/test_oracle_cport.py) evaluates a 10^6-barcode ELBO gradient in a fraction of a second, so
+every BASELINE configuration is checked at full size: bb_elbo_grad with caller-supplied noise (K = 1) through the C
+ABI, fp64 to rel 1e-9 and fp32 to the stated tolerance (log-joint rel 1e-4, gradient 2e-3 of its max-norm).
+A few production steps (in-kernel Philox, fused / persistent kernels) are then checked through size-independent
+properties: the fp32 and fp64 engines follow the same trajectory, and the run is bitwise reproducible.
+"""
+import numpy as np
+import pytest
+
+from helpers import plausible_theta, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f64": dict(elbo=1e-10, grad=1e-9), "f32": dict(elbo=1e-4, grad=2e-3)}
+
+
+def _port(da, model):
+    from oracle import cport
+    cport.set_threads()
+    return cport.ModelPort(model, da.bc_count, da.n_neutral, da.n_bc, envs=da.envs, genotypes=da.genotypes)
+
+
+@pytest.mark.parametrize("cfg", [2, 3, 4, 5])
+def test_full_size_elbo_gradient_matches_c_port(bb, cfg):
+    model, da, _ = bb.synth.config(cfg)
+    pp = _port(da, model)
+    rng = np.random.default_rng(100 + cfg)
+    mu = omega = eps = None
+    ref = None
+    for dtype in ("f64", "f32"):
+        eng = bb.Engine(da, model, n_samples=1, dtype=dtype, seed=cfg)
+        assert eng.D == pp.D
+        if mu is None:
+            mu, omega = plausible_theta(eng.layout, da, rng)
+            eps = rng.standard_normal((1, eng.D))
+            ref = pp.elbo_grad(mu, omega, eps)
+        eng.set_params(mu, omega)
+        elbo, g_mu, g_om = eng.elbo_grad(eps)
+        eng.close()
+        e_ref, gm_ref, go_ref, _ = ref
+        tol = TOL[dtype]
+        assert abs(elbo - e_ref) <= tol["elbo"] * abs(e_ref), (cfg, dtype, elbo, e_ref)
+        assert rel_err(g_mu, gm_ref) <= tol["grad"], (cfg, dtype, rel_err(g_mu, gm_ref))
+        assert rel_err(g_om, go_ref) <= tol["grad"], (cfg, dtype, rel_err(g_om, go_ref))
+
+
+def test_full_size_steps_fp32_tracks_fp64_and_is_reproducible(bb):
+    """cfg2 at 10^6 barcodes, K = 8: five production steps (packed persistent step kernel).  fp32 follows fp64 within
+    the fp32 tolerance, and two fp32 runs with the same seed agree bitwise."""
+    model, da, _ = bb.synth.config(2)
+    out = {}
+    for tag, dtype in (("f64", "f64"), ("f32a", "f32"), ("f32b", "f32")):
+        eng = bb.Engine(da, model, n_samples=8, dtype=dtype, seed=5)
+        eng.init_params(3)
+        eng.set_optimizer("decayed")
+        eng.step(5)
+        out[tag] = eng.get_params()
+        eng.close()
+    assert np.array_equal(out["f32a"][0], out["f32b"][0]) and np.array_equal(out["f32a"][1], out["f32b"][1])
+    assert rel_err(out["f32a"][0], out["f64"][0]) < 2e-3 and rel_err(out["f32a"][1], out["f64"][1]) < 2e-3

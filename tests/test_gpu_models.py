@@ -196,3 +196,38 @@ def test_c_abi_rejects_bad_arguments(bb):
     with pytest.raises(bb.BarBayError, match="TruncatedADAGrad or DecayedADAGrad"):
         eng.set_optimizer("adam")
     eng.close()
+
+
+@pytest.mark.parametrize("model", ["fitness_normal", "replicate_fitness_normal"])
+@pytest.mark.parametrize("opt", ["truncated", "decayed"])
+def test_checkpoint_resume_on_a_fresh_handle_equals_uninterrupted_run(bb, model, opt):
+    """bb_get_state / bb_set_state carry theta, the accumulators AND the TruncatedADAGrad window (the reference's
+    default optimiser): a run restored on a FRESH handle continues bitwise like the uninterrupted one, past the
+    point where the restored window starts evicting (n = 4, 5 + 6 steps)."""
+    from helpers import load_fixture
+    df, cols = load_fixture(model)
+    da = bb.utils.data_to_arrays(df, **cols)
+    kw = dict(eta=0.1, tau=1.0, n=4) if opt == "truncated" else dict(eta=0.1, pre=1.0, post=0.9)
+
+    def fresh():
+        e = bb.Engine(da, model, n_samples=2, dtype="f64", seed=8)
+        e.init_params(2)
+        e.set_optimizer(opt, **kw)
+        return e
+
+    a = fresh()
+    a.step(11)
+    ref = a.get_params()
+    a.close()
+    b = fresh()
+    b.step(5)
+    state = b.get_state()
+    b.close()
+    c = fresh()
+    c.step(3)                      # state of the fresh handle must be overwritten, not merged
+    c.set_state(state)
+    assert c.step_count == 5
+    c.step(6)
+    got = c.get_params()
+    c.close()
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])

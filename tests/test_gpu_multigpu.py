@@ -10,15 +10,16 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("wiring", ["peer", "nccl"])
 @pytest.mark.parametrize("model", ["fitness_normal", "replicate_fitness_normal", "multienv_fitness_normal",
                                    "genotype_fitness_normal"])
-def test_two_gpu_run_matches_single_gpu(model):
+def test_two_gpu_run_matches_single_gpu(model, wiring):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "dist_gpu_check.py"),
-           model, "f64"]
+           model, "f64", wiring]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
@@ -26,3 +27,53 @@ def test_two_gpu_run_matches_single_gpu(model):
     assert out["all_owned"]
     # identical up to the reduction order of the partial sums (fp64)
     assert out["elbo_rel"] < 1e-10 and out["mean_rel"] < 1e-9 and out["std_rel"] < 1e-9, out
+
+
+@pytest.mark.parametrize("model", ["fitness_normal", "replicate_fitness_normal", "multienv_fitness_normal",
+                                   "genotype_fitness_normal"])
+def test_single_call_multi_gpu_handle_matches_one_gpu(model):
+    """bb_desc.n_devices = 2: ONE handle, one process, every entry point one blocking call (what a single
+    BarBay.vi.advi() needs, src/vi.jl:86-101).  Same posterior, ELBO trace, gradient and noise as one GPU."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import barbay_b200 as bb
+    cfg = {"fitness_normal": 2, "replicate_fitness_normal": 3, "multienv_fitness_normal": 4, "genotype_fitness_normal": 5}[model]
+    _, da, _ = bb.synth.config(cfg, scale=0.003)
+    K, steps = 4, 6
+    res = {}
+    for nd in (1, 2):
+        eng = bb.Engine(da, model, n_samples=K, dtype="f64", seed=11, device=0, n_devices=nd)
+        eng.init_params(5)
+        eng.set_optimizer("truncated", n=4)
+        trace = eng.step(steps, elbo_trace=True)
+        eng.step(steps)
+        elbo, g_mu, g_om = eng.elbo_grad(step=99)
+        state = eng.get_state()
+        m, s = eng.get_posterior()
+        eps = eng.get_noise(3)
+        eng.close()
+        res[nd] = (trace, m, s, elbo, g_mu, g_om, eps, state)
+    a, b = res[1], res[2]
+    rel = lambda x, y: float(np.max(np.abs(np.asarray(x) - np.asarray(y))) / max(np.max(np.abs(np.asarray(y))), 1e-300))
+    assert rel(b[0], a[0]) < 1e-10 and rel(b[1], a[1]) < 1e-9 and rel(b[2], a[2]) < 1e-9
+    assert abs(b[3] - a[3]) <= 1e-10 * abs(a[3]) and rel(b[4], a[4]) < 1e-9 and rel(b[5], a[5]) < 1e-9
+    assert np.array_equal(b[6], a[6])                      # the lattice depends on global ids only
+    assert rel(b[7], a[7]) < 1e-9 and b[7][0] == a[7][0]
+
+
+def test_single_call_multi_gpu_advi():
+    """advi(..., n_devices=2) -- the mirror of BarBay.vi.advi -- returns the same posterior table as one GPU."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import barbay_b200 as bb
+    _, da, _ = bb.synth.config(2, scale=0.002)
+    df = bb.synth.to_tidy(da)
+    kw = dict(data=df, model=bb.model.fitness_normal, advi=bb.ADVI(2, 50), opt=bb.DecayedADAGrad(), verbose=False, seed=3)
+    one = bb.advi(**kw)
+    two = bb.advi(**kw, n_devices=2)
+    assert (one["varname"] == two["varname"]).all()
+    assert np.max(np.abs(one["mean"] - two["mean"])) < 1e-8 and np.max(np.abs(one["std"] / two["std"] - 1)) < 1e-8
