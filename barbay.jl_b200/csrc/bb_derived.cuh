@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(DERIVED_THREADS) derived_fitness_kernel(const 
         double s1 = 0.0, s2 = 0.0;
         for (int i = tid; i < a.n; i += DERIVED_THREADS) {
             uint32_t x[4];
-            philox4x32_10((uint32_t)slot, (STREAM_DERIVED << 24) | (uint32_t)((unsigned long long)slot >> 32), (uint32_t)i, 0u, a.key, x);
+            philox4x32((uint32_t)slot, (STREAM_DERIVED << 24) | (uint32_t)((unsigned long long)slot >> 32), (uint32_t)i, 0u, a.key, x);
             float n0, n1, n2, n3;
             box_muller(x[0], n0, n1, a.key.trig);
             box_muller(x[1], n2, n3, a.key.trig);

@@ -1,4 +1,4 @@
-// Device-side primitives: Philox4x32-10 noise lattice, Box-Muller, scalar math.
+// Device-side primitives: Philox4x32-7 noise lattice, Box-Muller, scalar math.
 // sm_100a only.  See DESIGN.md "Noise lattice" for the counter layout; the oracle
 // restates it independently in oracle/philox_ref.py.
 #pragma once
@@ -24,26 +24,30 @@ template <typename real> __device__ __forceinline__ vec2<real> mk2(real a, real 
     vec2<real> v; v.x = a; v.y = b; return v;
 }
 
-// ---------------------------------------------------------------- Philox4x32-10
-// The ten round keys (k + r * W) are kernel-uniform: they are computed once on the host
-// and sit in the kernel's constant bank, so a round is 2 IMAD.WIDE + 2 LOP3.
+// ---------------------------------------------------------------- Philox4x32-7
+// Philox4x32 (Salmon et al., SC'11) with 7 rounds: the round count the Random123 authors report as the smallest
+// that is Crush-resistant (BigCrush) for the 4x32 variant; 10 is their safety-margin default.  Noise generation
+// is the largest item of the K = 8 step (two passes regenerate it), and the Philox chain is its serial part.
+// The round keys (k + r * W) are kernel-uniform: they are computed once on the host and sit in the kernel's
+// constant bank, so a round is 2 IMAD.WIDE + 2 LOP3.
+constexpr int PHILOX_ROUNDS = 7;
 struct PhiloxKey {
-    uint32_t k0[10], k1[10];
+    uint32_t k0[PHILOX_ROUNDS], k1[PHILOX_ROUNDS];
     const float2 *trig;     // fp32 Box-Muller direction table in global memory (TRIG_N entries), see box_muller
 };
 inline PhiloxKey make_philox_key(uint64_t seed) {
     PhiloxKey k;
     uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
-    for (int r = 0; r < 10; ++r) { k.k0[r] = a; k.k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+    for (int r = 0; r < PHILOX_ROUNDS; ++r) { k.k0[r] = a; k.k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
     k.trig = nullptr;
     return k;
 }
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               const PhiloxKey &key, uint32_t (&out)[4]) {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < PHILOX_ROUNDS; ++r) {
         const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.k0[r], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.k1[r];
         c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
@@ -89,7 +93,7 @@ template <typename real>
 __device__ __forceinline__ void normals8(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                          const PhiloxKey &key, const float2 *tab, real (&n)[8]) {
     uint32_t x[4];
-    philox4x32_10(c0, c1, c2, c3, key, x);
+    philox4x32(c0, c1, c2, c3, key, x);
     box_muller(x[0], n[0], n[1], tab);
     box_muller(x[1], n[2], n[3], tab);
     box_muller(x[2], n[4], n[5], tab);
@@ -102,7 +106,7 @@ __device__ __forceinline__ real stream_normal(uint32_t stream, uint32_t i, uint3
                                               const PhiloxKey &key) {
     // lane i & 7 of normals8(i >> 3, ...): only its own word goes through Box-Muller
     uint32_t x[4];
-    philox4x32_10(i >> 3, stream << 24, k, step, key, x);
+    philox4x32(i >> 3, stream << 24, k, step, key, x);
     const uint32_t w = (i >> 1) & 3u;
     const uint32_t xw = w == 0 ? x[0] : w == 1 ? x[1] : w == 2 ? x[2] : x[3];
     real n0, n1;

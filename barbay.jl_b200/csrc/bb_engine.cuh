@@ -114,7 +114,7 @@ class EngineBase {
     virtual void comm_init(const char id[128]) = 0;
     // persistent step kernel: cycles of CTA 0 in {column phase, arrive -> sums, sums -> context} and the number of
     // in-kernel tails, summed since the last call (then reset); out[4] = SM clock in kHz
-    virtual void persist_stats(double out[5]) = 0;
+    virtual void persist_stats(double out[8]) = 0;
     // out = {packed step kernel in use, steps per persistent launch (0: off), peer-memory exchange on, NCCL communicator present}
     virtual void data_plane(int32_t out[4]) = 0;
     // one-process-per-GPU wiring without NCCL: every rank exports the CUDA IPC handle of its exchange buffer, the
@@ -158,7 +158,7 @@ template <typename real> class Engine : public EngineBase {
     void sync() override { BB_CUDA(cudaStreamSynchronize(stream_)); }
     void time_steps(int n, float *ms_total, float *ms_pass1, float *ms_pass2) override;
     void comm_init(const char id[128]) override;
-    void persist_stats(double out[5]) override;
+    void persist_stats(double out[8]) override;
     void derived_fitness(int n, uint64_t seed, double *median, double *sd) override;
     void peer_handle(char out[64]) override;
     void peer_attach(const char *handles, int n) override;
@@ -514,7 +514,9 @@ template <typename real> void Engine<real>::size_pass2() {
                 const int pvs_m = L.E == 1 ? 2 * g.nt : 3 * g.nt - 2, pvs_n = 3 * g.nt - 2;
                 const int rows = std::max(npack * ((pvs_m + 1) / 2), (pvs_n + 1) / 2);
                 const size_t spb = (size_t)2 * W * sizeof(real);        // one SlotPair
-                const size_t head = 64 + r128((size_t)npack * 3 * g.nt * W * sizeof(real)) +
+                // mbarriers | packed context | persistent: sigma, z, eps of the population latents | their (theta, acc)
+                const size_t head = 128 + r128((size_t)npack * 3 * g.nt * W * sizeof(real)) +
+                                    ((size_t)(2 * (g.nt - 1)) * (1 + 2 * L.K) * sizeof(real) + 15) / 16 * 16 +
                                     r128((size_t)4 * (g.nt - 1) * sizeof(double2));
                 auto total = [&](int stage_ring) {
                     return head + 2 * ((1 + npr) * thb + cnb) + (size_t)(1 + stage_ring) * thb + (size_t)rows * BLOCK * spb;
@@ -535,7 +537,7 @@ template <typename real> void Engine<real>::size_pass2() {
                 if (g.stepk) {
                     assign_blocks(g.stsegs, g.nt, nsm_ * g.step_occ, &g.stblocks);
                     // scratch of the in-kernel tail (totals + shared_body's working arrays) aliases the accumulators
-                    const size_t tail_d = sums_.n + sh_scratch_.n + (size_t)L.K * 3 * g.nt;   // + the linear context
+                    const size_t tail_d = sums_.n + (size_t)L.K * (2 * g.nt + 3 * (g.nt - 1)) + 16;   // totals + working arrays
                     g.step_persist = tail_d * sizeof(double) <= (size_t)rows * BLOCK * spb && (int)sums_.n <= 4096;
                 }
             }
@@ -1427,8 +1429,8 @@ template <typename real> void Engine<real>::derived_fitness(int n, uint64_t seed
     BB_CUDA(cudaGetLastError());
 }
 
-template <typename real> void Engine<real>::persist_stats(double out[5]) {
-    for (int i = 0; i < 5; ++i) out[i] = 0.0;
+template <typename real> void Engine<real>::persist_stats(double out[8]) {
+    for (int i = 0; i < 8; ++i) out[i] = 0.0;
     if (!step_sync_.p) return;
     StepSync h;
     BB_CUDA(cudaMemcpy(&h, step_sync_.p, sizeof(StepSync), cudaMemcpyDeviceToHost));
@@ -1436,6 +1438,7 @@ template <typename real> void Engine<real>::persist_stats(double out[5]) {
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_);
     out[4] = (double)khz;
+    out[5] = (double)h.stat[4]; out[6] = (double)h.stat[5];      // inside "sums -> context": completing the sums, shared-latent phases
     BB_CUDA(cudaMemset(reinterpret_cast<char *>(step_sync_.p) + offsetof(StepSync, stat), 0, sizeof(h.stat)));
 }
 

@@ -26,6 +26,13 @@ namespace bb {
 #ifndef BB_STEP_MIN_BLOCKS
 #define BB_STEP_MIN_BLOCKS 3
 #endif
+#ifndef BB_STEP_UNROLL2
+#define BB_STEP_UNROLL2 1       // packs of pass 2 interleaved per thread (ILP: the step is latency-bound on small shards)
+#endif
+#ifndef BB_STEP_UNROLL1
+#define BB_STEP_UNROLL1 1       // same for the pass-1 loop
+#endif
+constexpr int kStepUnroll2 = BB_STEP_UNROLL2, kStepUnroll1 = BB_STEP_UNROLL1;
 
 // ---------------------------------------------------------------- mbarrier / bulk-copy primitives
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,8 +137,8 @@ __device__ __forceinline__ void column_noise_pack(Pack<real, W> (&eps)[MAXC], in
             for (int l = 0; l < 8; ++l) eps[8 * q + l].v = n[l];
         } else if constexpr (std::is_same<real, float>::value) {
             uint32_t xa[4], xb[4];
-            philox4x32_10(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k0, step, key, xa);
-            philox4x32_10(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k0 + 1u, step, key, xb);
+            philox4x32(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k0, step, key, xa);
+            philox4x32(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k0 + 1u, step, key, xb);
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
                 // box_muller (bb_device.cuh) of both samples; the uniform's offset is one packed add
@@ -312,13 +319,18 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
     constexpr bool F32 = std::is_same<real, float>::value;
     __shared__ float2 strig[F32 ? TRIG_N : 1];
     unsigned char *sp = step_smem;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sp); sp += 64;          // [0,1] staging buffers full, [2] epilogue buffer full
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sp); sp += 128;         // per warp: [0,1] staging buffers full, [2] epilogue buffer full
     constexpr int CSP = 3 * NT;                                           // context entries per pack
     P *sctx = reinterpret_cast<P *>(sp);
     const int npack = a.K / W;
     sp += ((size_t)npack * CSP * sizeof(P) + 127) / 128 * 128;
     double2 *s_sh_th = nullptr, *s_sh_acc = nullptr;
+    real *s_sig = nullptr, *s_z = nullptr, *s_eps = nullptr;       // sigma [2n]; z, eps [K][2n] of the NEXT in-kernel tail
     if (persist) {
+        s_sig = reinterpret_cast<real *>(sp); sp += (size_t)2 * (NT - 1) * sizeof(real);
+        s_z = reinterpret_cast<real *>(sp); sp += (size_t)a.K * 2 * (NT - 1) * sizeof(real);
+        s_eps = reinterpret_cast<real *>(sp); sp += (size_t)a.K * 2 * (NT - 1) * sizeof(real);
+        sp = step_smem + ((sp - step_smem) + 15) / 16 * 16;
         s_sh_th = reinterpret_cast<double2 *>(sp); sp += (size_t)2 * (NT - 1) * sizeof(double2);
         s_sh_acc = reinterpret_cast<double2 *>(sp); sp += (size_t)2 * (NT - 1) * sizeof(double2);
         sp = step_smem + ((sp - step_smem) + 127) / 128 * 128;
@@ -344,8 +356,10 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
     const int nqp = (pvs + 1) >> 1;
     const int nrows = neutral ? NT : ROWS;                       // theta rows of this population
 
-    if (tid == 0) {
-        mbar_init(bars + 0, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 1);
+    const int warp = tid >> 5, lane = tid & 31;
+    uint64_t *wbar = bars + 3 * warp;        // this warp's barriers: every warp runs its own copy pipeline, no block barrier
+    if (tid < 3 * (BLOCK / 32)) {
+        mbar_init(bars + tid, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if constexpr (F32) {
@@ -357,68 +371,48 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
 
     // ---- bulk staging of one tile: rows are contiguous in the class-major SoA, so a row of the tile is ONE copy
     uint32_t ph_full[2] = {0u, 0u}, ph_epi = 0u;
-    auto tile_cols = [&](int tile) {       // columns copied for this tile: whole 32-column groups (segments are padded to 32)
-        return min(BLOCK, (seg.ncol - tile * BLOCK + 31) & ~31);
-    };
-    auto issue_pre = [&](int tile, int buf) {          // thread 0 only
-        const int nc = tile_cols(tile);
-        const uint32_t c = (uint32_t)(seg.col0 + tile * BLOCK);
+    // One copy per (array row, warp): the warp's 32 columns of a row are 256 B (fp32 pairs) of contiguous global memory.
+    // Lane l issues row l of the set (all rows of a tile in ONE instruction slot), lane 0 arms the barrier first.
+    // Segments are padded to 32 columns, so a warp either has a full 32-column slice or none at all.
+    auto warp_has = [&](int tile) { return tile < ntile && tile * BLOCK + warp * 32 < seg.ncol; };
+    auto issue_pre = [&](int tile, int buf) {
+        const uint32_t c = (uint32_t)(seg.col0 + tile * BLOCK + warp * 32);
         unsigned char *base = stage0 + (size_t)buf * buf_bytes;
-        r2 *sth = reinterpret_cast<r2 *>(base);
-        r2 *spr = reinterpret_cast<r2 *>(base + th_bytes);
-        int *scn = reinterpret_cast<int *>(base + (1 + npr) * th_bytes);
-        const uint32_t rb = (uint32_t)nc * sizeof(r2), cb = (uint32_t)nc * sizeof(int);
-        uint32_t total = (uint32_t)nrows * rb + (uint32_t)NT * cb;
-        if (npr) total += (lam_mat ? (uint32_t)NT * rb : 0u) + ((bc_mat && !neutral) ? (uint32_t)NJ * rb : 0u);
-        mbar_expect_tx(bars + buf, total);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const uint32_t o = (uint32_t)t * (uint32_t)cpad + c;
-            bulk_g2s(sth + t * BLOCK, C.lam_th + o, rb, bars + buf);
-            bulk_g2s(scn + t * BLOCK, C.cnt + o, cb, bars + buf);
-        }
-        if (!neutral) {
-#pragma unroll
-            for (int j = 0; j < NJ; ++j)
-                bulk_g2s(sth + (NT + j) * BLOCK, C.bc_th + ((uint32_t)j * (uint32_t)cpad + c), rb, bars + buf);
-        }
-        if (npr) {
-            if (lam_mat) {
-#pragma unroll
-                for (int t = 0; t < NT; ++t)
-                    bulk_g2s(spr + t * BLOCK, C.lam_pr + ((uint32_t)t * (uint32_t)cpad + c), rb, bars + buf);
-            }
-            if (bc_mat && !neutral) {
-#pragma unroll
-                for (int j = 0; j < NJ; ++j)
-                    bulk_g2s(spr + (NT + j) * BLOCK, C.bc_pr + ((uint32_t)j * (uint32_t)cpad + c), rb, bars + buf);
+        r2 *sth = reinterpret_cast<r2 *>(base) + warp * 32;
+        r2 *spr = reinterpret_cast<r2 *>(base + th_bytes) + warp * 32;
+        int *scn = reinterpret_cast<int *>(base + (1 + npr) * th_bytes) + warp * 32;
+        constexpr uint32_t rb = 32 * sizeof(r2), cb = 32 * sizeof(int);
+        const int n_pl = (npr && lam_mat) ? NT : 0, n_pb = (npr && bc_mat && !neutral) ? NJ : 0;
+        if (lane == 0) mbar_expect_tx(wbar + buf, (uint32_t)(nrows + n_pl + n_pb) * rb + (uint32_t)NT * cb);
+        __syncwarp();
+        for (int row = lane; row < nrows + NT + n_pl + n_pb; row += 32) {
+            if (row < NT) bulk_g2s(sth + row * BLOCK, C.lam_th + ((uint32_t)row * (uint32_t)cpad + c), rb, wbar + buf);
+            else if (row < 2 * NT) bulk_g2s(scn + (row - NT) * BLOCK, C.cnt + ((uint32_t)(row - NT) * (uint32_t)cpad + c), cb, wbar + buf);
+            else if (row < NT + nrows) bulk_g2s(sth + (row - NT) * BLOCK, C.bc_th + ((uint32_t)(row - 2 * NT) * (uint32_t)cpad + c), rb, wbar + buf);
+            else if (row < NT + nrows + n_pl) {
+                const int t = row - NT - nrows;
+                bulk_g2s(spr + t * BLOCK, C.lam_pr + ((uint32_t)t * (uint32_t)cpad + c), rb, wbar + buf);
+            } else {
+                const int j = row - NT - nrows - n_pl;
+                bulk_g2s(spr + (NT + j) * BLOCK, C.bc_pr + ((uint32_t)j * (uint32_t)cpad + c), rb, wbar + buf);
             }
         }
     };
-    auto issue_epi = [&](int tile, const r2 *lam_ring, const r2 *bc_ring) {     // thread 0 only
-        const int nc = tile_cols(tile);
-        const uint32_t c = (uint32_t)(seg.col0 + tile * BLOCK);
-        r2 *sac = reinterpret_cast<r2 *>(epi0);
-        r2 *srg = reinterpret_cast<r2 *>(epi0 + th_bytes);
-        const uint32_t rb = (uint32_t)nc * sizeof(r2);
-        mbar_expect_tx(bars + 2, (uint32_t)(1 + nrg) * (uint32_t)nrows * rb);
-#pragma unroll
-        for (int t = 0; t < NT; ++t)
-            bulk_g2s(sac + t * BLOCK, C.lam_acc + ((uint32_t)t * (uint32_t)cpad + c), rb, bars + 2);
-        if (!neutral) {
-#pragma unroll
-            for (int j = 0; j < NJ; ++j)
-                bulk_g2s(sac + (NT + j) * BLOCK, C.bc_acc + ((uint32_t)j * (uint32_t)cpad + c), rb, bars + 2);
-        }
-        if (nrg) {
-#pragma unroll
-            for (int t = 0; t < NT; ++t)
-                bulk_g2s(srg + t * BLOCK, lam_ring + ((uint32_t)t * (uint32_t)cpad + c), rb, bars + 2);
-            if (!neutral) {
-#pragma unroll
-                for (int j = 0; j < NJ; ++j)
-                    bulk_g2s(srg + (NT + j) * BLOCK, bc_ring + ((uint32_t)j * (uint32_t)cpad + c), rb, bars + 2);
-            }
+    auto issue_epi = [&](int tile, const r2 *lam_ring, const r2 *bc_ring) {
+        const uint32_t c = (uint32_t)(seg.col0 + tile * BLOCK + warp * 32);
+        r2 *sac = reinterpret_cast<r2 *>(epi0) + warp * 32;
+        r2 *srg = reinterpret_cast<r2 *>(epi0 + th_bytes) + warp * 32;
+        constexpr uint32_t rb = 32 * sizeof(r2);
+        if (lane == 0) mbar_expect_tx(wbar + 2, (uint32_t)(1 + nrg) * (uint32_t)nrows * rb);
+        __syncwarp();
+        for (int row = lane; row < (1 + nrg) * nrows; row += 32) {
+            const int rr = row < nrows ? row : row - nrows;
+            r2 *dst = (row < nrows ? sac : srg) + rr * BLOCK;
+            const r2 *src = row < nrows ? (rr < NT ? C.lam_acc + ((uint32_t)rr * (uint32_t)cpad + c)
+                                                   : C.bc_acc + ((uint32_t)(rr - NT) * (uint32_t)cpad + c))
+                                        : (rr < NT ? lam_ring + ((uint32_t)rr * (uint32_t)cpad + c)
+                                                   : bc_ring + ((uint32_t)(rr - NT) * (uint32_t)cpad + c));
+            bulk_g2s(dst, src, rb, wbar + 2);
         }
     };
 
@@ -434,10 +428,10 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
         }
 
     // context of the first step: from tail_kernel (launched ahead of this kernel; programmatic dependent launch)
-    if (tid == 0 && first < ntile) issue_pre(first, 0);
+    if (warp_has(first)) issue_pre(first, 0);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (a.abort && *reinterpret_cast<const volatile int *>(a.abort)) {
-        if (first < ntile) mbar_wait(bars + 0, 0u);        // the copy in flight must land before the CTA retires
+        if (warp_has(first)) mbar_wait(wbar + 0, 0u);      // the copies in flight must land before the CTA retires
         return;
     }
     auto pack_ctx = [&](const real *lin) {           // linear [K][3][NT] -> packs [K/W][3 NT]
@@ -448,12 +442,23 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
         }
     };
     pack_ctx(a.ctx);
+    constexpr int N2 = 2 * (NT - 1);
     if (persist) {
-        for (int i = tid; i < 2 * (NT - 1); i += BLOCK) { s_sh_th[i] = a.sa.sh_th[i]; s_sh_acc[i] = a.sa.sh_acc[i]; }
+        // the population latents live in shared memory for the whole launch (every CTA keeps the same replica);
+        // z = mu + sigma eps of the first in-kernel tail (step + 1) is drawn here, later ones at the end of each tail
+        for (int i = tid; i < N2; i += BLOCK) { s_sh_th[i] = a.sa.sh_th[i]; s_sh_acc[i] = a.sa.sh_acc[i]; }
+        for (int j = tid; j < a.K * N2; j += BLOCK) {
+            const int i = j % N2;
+            const double2 th = a.sa.sh_th[i];
+            const real sg = softplus_only<real>((real)th.y);
+            const real e = (real)a.sa.eps_sh[(size_t)a.K * N2 + j];
+            s_eps[j] = e; s_z[j] = fma(sg, e, (real)th.x);
+            if (j < N2) s_sig[i] = sg;
+        }
     }
     __syncthreads();
 
-    long long st_col = 0, st_wait = 0, st_ctx = 0;
+    long long st_col = 0, st_wait = 0, st_ctx = 0, st_a = 0, st_b = 0;
     int abort_flag = 0;
     for (int si = 0; si < a.nsteps; ++si) {
         const uint32_t step = a.step + (uint32_t)si;
@@ -465,15 +470,14 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
         if (si > 0) {
             // (persistent) the buffers are free and this CTA's theta / accumulator stores of the last step are ordered
             // before the bulk copies below by the fences of the in-kernel tail
-            if (tid == 0 && first < ntile) issue_pre(first, 0);
+            if (warp_has(first)) issue_pre(first, 0);
         }
         int buf = 0;
         for (int tile = first; tile < ntile; tile += nblk, buf ^= 1) {
-            __syncthreads();                 // everyone is done with the previous tile's buffers
-            if (tid == 0) {
-                issue_epi(tile, lam_ring, bc_ring);
-                if (tile + nblk < ntile) issue_pre(tile + nblk, buf ^ 1);
-            }
+            if (!warp_has(tile)) continue;   // (warp-uniform) a partial last tile leaves whole warps without columns
+            __syncwarp();                    // the warp is done with the previous tile's buffers
+            issue_epi(tile, lam_ring, bc_ring);
+            if (warp_has(tile + nblk)) issue_pre(tile + nblk, buf ^ 1);
             const int i = tile * BLOCK + tid;
             const bool active = i < seg.ncol;
             const int c = seg.col0 + (active ? i : 0);
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(bc_ring + ((uint32_t)j * (uint32_t)cpad + c)));
                 }
             }
-            mbar_wait(bars + buf, ph_full[buf]); ph_full[buf] ^= 1u;
+            mbar_wait(wbar + buf, ph_full[buf]); ph_full[buf] ^= 1u;
             if (active) {
                 const uint32_t colid = C.col_id ? C.col_id[c] : seg.colid0 + (uint32_t)i;
                 unsigned char *base = stage0 + (size_t)buf * buf_bytes;
@@ -530,7 +534,7 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
                 for (int j = 0; j < NJ; ++j) { sgrb[j] = pk_zero<real, W>(); sgeb[j] = pk_zero<real, W>(); }
 
                 // ---- the K samples, W at a time
-#pragma unroll 1
+#pragma unroll kStepUnroll2
                 for (int kp = 0; kp < npack; ++kp) {
                     P eps[S::MAXC];
                     column_noise_pack<real, W, S::MAXC>(eps, nclass, colid, (uint32_t)(kp * W), step, a.key, strig);
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) { fgrb[j] = pk_hsum(sgrb[j]); fgeb[j] = pk_hsum(sgeb[j]); }
 
-                mbar_wait(bars + 2, ph_epi);      // this tile's accumulators (and ring slot)
+                mbar_wait(wbar + 2, ph_epi);      // this tile's accumulators (and ring slot)
                 // fused optimiser update of every latent of the column
                 auto finish_all = [&](auto mode_tag) {
                     constexpr int MODE = decltype(mode_tag)::value;
@@ -610,7 +614,7 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
 
                 // pass 1 of the next step with the fresh theta (mutant columns; neutral blocks sweep again below)
                 if (!neutral) {
-#pragma unroll 1
+#pragma unroll kStepUnroll1
                     for (int kp = 0; kp < npack; ++kp) {
                         P eps[S::MAXC];
                         column_noise_pack<real, W, S::MAXC>(eps, nclass, colid, (uint32_t)(kp * W), step + 1u, a.key, strig);
@@ -618,7 +622,7 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
                     }
                 }
             } else {
-                mbar_wait(bars + 2, ph_epi);
+                mbar_wait(wbar + 2, ph_epi);
             }
             ph_epi ^= 1u;
         }
@@ -706,6 +710,22 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
                 if (tid < world) st_release_sys(a.xp.peer_flag[tid] + (parity * world + a.xp.rank), seq);
             }
         }
+        // fetched while the sums are on their way: priors and the evicted ring slot of population latent `tid`, the noise
+        // of the tail after this one
+        double2 pri_s = make_double2(0.0, 1.0), pri_l = pri_s, ring_old = make_double2(0.0, 0.0);
+        double2 *ring_wr = nullptr;
+        real eps_next = real(0);
+        {
+            const int t = tid % (NT - 1);
+            pri_s = a.sa.sh_pr[t]; pri_l = a.sa.sh_pr[(NT - 1) + t];
+            if (a.ring_n > 0 && tid < 2 * (NT - 1)) {          // shared-latent ring: n + 1 slots indexed by the step itself
+                const uint32_t n1 = (uint32_t)a.ring_n + 1u;
+                ring_old = __ldcg(a.sa.sh_ring_rd + (size_t)((step + 2u) % n1) * 2 * (NT - 1) + tid);
+                ring_wr = a.sa.sh_ring_wr + (size_t)((step + 1u) % n1) * 2 * (NT - 1);
+            }
+            if (si + 2 < a.nsteps && tid < a.K * 2 * (NT - 1))
+                eps_next = (real)a.sa.eps_sh[(size_t)(si + 2) * a.K * 2 * (NT - 1) + tid];
+        }
         // every CTA: wait for all ranks' sums of this exchange
         if (tid < world) {
             const unsigned long long *f = a.xflag + (parity * world + tid);
@@ -718,31 +738,86 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
         abort_flag = __syncthreads_or(abort_flag);
         if (abort_flag) break;           // no update is applied with incomplete sums; the host reports the error
         const long long tc2 = clock64();
+        // ---- the shared-latent phases, every CTA for itself (same arithmetic as shared_body, bb_aux_kernels.cuh, in the
+        // kernel's own precision and with everything that does not depend on the sums -- noise, sigma, priors, the evicted
+        // ring slot -- fetched before or cached across the wait): ~4 block barriers on the critical path
         double *tot = reinterpret_cast<double *>(facc);          // the accumulators are flushed: reuse as scratch
-        double *scratch = tot + a.P;
-        real *ctx_lin = reinterpret_cast<real *>(scratch + a.tail_scratch);    // linear context [K][3][T] of the next step
+        real *w_lgl = reinterpret_cast<real *>(tot + a.P);       // [K][T] log Lambda
+        real *w_il = w_lgl + a.K * NT;                           // [K][T] 1 / Lambda
+        real *w_g = w_il + a.K * NT;                             // [K][2n] per-sample gradients of the shared latents
+        real *w_u = w_g + a.K * N2;                              // [K][n] sum_all w res
         for (int j = tid; j < a.P; j += BLOCK) {
             double s = 0.0;
             for (int r = 0; r < world; ++r) s += __ldcg(a.xbuf + (size_t)(parity * world + r) * a.P + j);
             tot[j] = s;
         }
-        {
-            SharedArgs<real> sa = a.sa;
-            sa.sh_th = s_sh_th; sa.sh_acc = s_sh_acc; sa.ctx = ctx_lin; sa.scratch = scratch;
-            sa.step = step + 1u;
-            sa.eps_sh = a.sa.eps_sh + (size_t)(si + 1) * a.K * 2 * (NT - 1);
-            if (a.ring_n > 0) {          // shared-latent ring: n + 1 slots indexed by the step itself (bb_aux_kernels.cuh)
-                const uint32_t n1 = (uint32_t)a.ring_n + 1u;
-                sa.sh_ring_rd = a.sa.sh_ring_rd + (size_t)((step + 2u) % n1) * 2 * (NT - 1);
-                sa.sh_ring_wr = a.sa.sh_ring_wr + (size_t)((step + 1u) % n1) * 2 * (NT - 1);
-            }
-            sa.ring_writer = blockIdx.x == 0 ? 1 : 0;
-            sa.xchg.buf = nullptr;
-            __syncthreads();
-            shared_body<real>(sa, tot, scratch, true);
+        __syncthreads();
+        const long long tca = clock64();
+        for (int j = tid; j < a.K * NT; j += BLOCK) {
+            const int k = j / NT, t = j - k * NT;
+            const real lam = (real)tot[((size_t)k * NQ + Q_LAM) * NT + t];
+            w_lgl[j] = bb_log(lam); w_il[j] = real(1) / lam;
         }
         __syncthreads();
-        pack_ctx(ctx_lin);
+        const real nneu = (real)a.sa.n_neutral;
+        real *ctxw = reinterpret_cast<real *>(sctx);             // pack (kp, j) half h at ((kp * CSP + j) * W + h)
+        for (int j = tid; j < a.K * (NT - 1); j += BLOCK) {
+            const int k = j / (NT - 1), t = j - k * (NT - 1);
+            const double *S = tot + (size_t)k * NQ * NT;
+            const real zs = s_z[k * N2 + t], zl = s_z[k * N2 + (NT - 1) + t];
+            const real c = w_lgl[k * NT + t + 1] - w_lgl[k * NT + t];
+            const real wbar = bb_exp(real(-2) * zl);
+            const real av = zs - c;
+            const real dn = (real)S[Q_DN * NT + t], d2n = (real)S[Q_D2N * NT + t];
+            const real am = (real)S[Q_A * NT + t], wm = (real)S[Q_W * NT + t];
+            const real qn = d2n + real(2) * av * dn + nneu * av * av;
+            const real u = wbar * (dn + nneu * av) + (am + av * wm);
+            w_g[k * N2 + t] = -u - (zs - pri_s.x) * pri_s.y;
+            w_g[k * N2 + (NT - 1) + t] = wbar * qn - nneu - (zl - pri_l.x) * pri_l.y;
+            w_u[k * (NT - 1) + t] = u;
+            const int kp = k / W, h = k - kp * W;
+            ctxw[((size_t)kp * CSP + t) * W + h] = c - zs;
+            ctxw[((size_t)kp * CSP + 2 * NT + t) * W + h] = wbar;
+        }
+        __syncthreads();
+        for (int j = tid; j < a.K * NT; j += BLOCK) {
+            const int k = j / NT, t = j - k * NT;
+            const real up = t > 0 ? w_u[k * (NT - 1) + t - 1] : real(0), un = t < NT - 1 ? w_u[k * (NT - 1) + t] : real(0);
+            const int kp = k / W, h = k - kp * W;
+            ctxw[((size_t)kp * CSP + NT + t) * W + h] = (up - un) * w_il[j];
+        }
+        if (tid < N2) {                                          // gradient and optimiser update of population latent `tid`
+            real sg = real(0), sge = real(0);
+            for (int k = 0; k < a.K; ++k) { const real g = w_g[k * N2 + tid]; sg += g; sge = fma(g, s_eps[k * N2 + tid], sge); }
+            double2 th = s_sh_th[tid], ac = s_sh_acc[tid];
+            const real sigma = s_sig[tid], invK = real(1) / real(a.K);
+            const real g0 = -(sg * invK), g1 = -((sge * invK + real(1) / sigma) * bb_exp((real)th.y - sigma));
+            const real q0 = g0 * g0, q1 = g1 * g1;
+            real d0, d1;
+            if (a.sa.opt.kind == 1) {
+                ac.x = fma((real)a.sa.opt.post, (real)ac.x, (real)a.sa.opt.tau * q0);
+                ac.y = fma((real)a.sa.opt.post, (real)ac.y, (real)a.sa.opt.tau * q1);
+                d0 = bb_sqrt((real)ac.x) + real(1e-8); d1 = bb_sqrt((real)ac.y) + real(1e-8);
+            } else {
+                ac.x = fmax((real)ac.x - (real)ring_old.x + q0, real(0));
+                ac.y = fmax((real)ac.y - (real)ring_old.y + q1, real(0));
+                if (blockIdx.x == 0) ring_wr[tid] = make_double2((double)q0, (double)q1);
+                d0 = (real)a.sa.opt.tau + bb_sqrt((real)ac.x) + real(1e-8);
+                d1 = (real)a.sa.opt.tau + bb_sqrt((real)ac.y) + real(1e-8);
+            }
+            th.x = (double)((real)th.x - (real)a.sa.opt.eta * g0 / d0);
+            th.y = (double)((real)th.y - (real)a.sa.opt.eta * g1 / d1);
+            s_sh_th[tid] = th; s_sh_acc[tid] = ac;
+            s_sig[tid] = softplus_only<real>((real)th.y);
+        }
+        __syncthreads();
+        st_a += tca - tc2; st_b += clock64() - tca;
+        // z = mu + sigma eps of the next in-kernel tail, from the noise fetched before the wait
+        if (si + 2 < a.nsteps)
+            for (int j = tid; j < a.K * N2; j += BLOCK) {
+                const int i = j % N2;
+                s_eps[j] = eps_next; s_z[j] = fma(s_sig[i], eps_next, (real)s_sh_th[i].x);
+            }
         __syncthreads();
         // the scratch aliased the accumulators: zero them again for the next column phase
         for (int i = tid; i < a.acc_rows * BLOCK; i += BLOCK) facc[i] = SP{pk_zero<real, W>(), pk_zero<real, W>()};
@@ -753,7 +828,11 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
         if (blockIdx.x == 0) {
             // the shared latents after this launch's in-kernel tails, for the next launch (or any other entry point)
             for (int i = tid; i < 2 * (NT - 1); i += BLOCK) { a.sa.sh_th[i] = s_sh_th[i]; a.sa.sh_acc[i] = s_sh_acc[i]; }
+        }
+        if (blockIdx.x == gridDim.x - 1) {        // a block of the (large) mutant population reports the timings
             if (tid == 0) {
+                atomicAdd(&a.sync->stat[4], (unsigned long long)st_a);
+                atomicAdd(&a.sync->stat[5], (unsigned long long)st_b);
                 atomicAdd(&a.sync->stat[0], (unsigned long long)st_col);
                 atomicAdd(&a.sync->stat[1], (unsigned long long)st_wait);
                 atomicAdd(&a.sync->stat[2], (unsigned long long)st_ctx);

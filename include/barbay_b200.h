@@ -162,10 +162,12 @@ double bb_algorithmic_bytes_per_step(const bb_handle *h);   /* SURVEY §8d figur
  * durations of the pass-1 and pass-2 column kernels (the roofline numerators of bench.py). */
 int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_pass1, float *ms_pass2);
 
-/* Persistent step kernel (several ADVI steps per launch, the tail of each step inside the kernel): SM cycles of
- * CTA 0 spent in {column phase, arrival -> all ranks' sums, sums -> next step's context}, summed over the
- * in-kernel tails since the last call; out[3] = number of such tails, out[4] = SM clock in kHz.  Resets the counters. */
-int bb_persist_stats(bb_handle *h, double out[5]);
+/* Persistent step kernel (several ADVI steps per launch, the tail of each step inside the kernel): SM cycles one
+ * CTA of the mutant population spent in {column phase, arrival -> all ranks' sums (grid reduction + NVLink exchange),
+ * sums -> next step's context}, summed over the in-kernel tails since the last call; out[3] = number of such
+ * tails, out[4] = SM clock in kHz, out[5..6] = the last phase split into {completing the sums, shared-latent
+ * phases}.  Resets the counters. */
+int bb_persist_stats(bb_handle *h, double out[8]);
 
 /* Derived `bc_fitness` rows of the hierarchical models: utils.advi_to_df -> process_hierarchical_samples!
  * (src/utils.jl:1284-1343) draws n_samples (default 10 000) of theta + exp(log-tau) * theta-tilde per

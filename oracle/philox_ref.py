@@ -1,4 +1,4 @@
-"""Oracle for the counter-based noise lattice (Philox4x32-10 + Box-Muller).
+"""Oracle for the counter-based noise lattice (Philox4x32-7 + Box-Muller).
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
@@ -9,9 +9,12 @@ noise lattice; this file restates that definition independently, from the
 specification in DESIGN.md §"Noise lattice", so tests can compare the kernel's
 draws and whole ADVI trajectories.
 
-Philox4x32-10 is the published algorithm of Salmon et al., "Parallel random
-numbers: as easy as 1, 2, 3" (SC'11); the known-answer vectors checked in
-tests/test_oracle_philox.py are the Random123 ``kat_vectors`` for philox4x32-10.
+Philox4x32-R is the published algorithm of Salmon et al., "Parallel random
+numbers: as easy as 1, 2, 3" (SC'11); the lattice uses R = 7 rounds (the smallest
+Crush-resistant count reported there; 10 is the library's safety-margin default).
+The known-answer vectors checked in tests/test_oracle_philox.py are the Random123
+``kat_vectors`` for philox4x32-10: they pin the round function and key schedule of
+this implementation, of which the 7-round lattice is the same loop run 7 times.
 """
 from __future__ import annotations
 
@@ -29,14 +32,17 @@ STREAM_HYPER = 2
 STREAM_INIT = 3
 
 
-def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
-    """Vectorised Philox4x32-10.  Counters are uint32 arrays (broadcastable)."""
+LATTICE_ROUNDS = 7      # the noise lattice uses Philox4x32-7 (DESIGN.md "Noise lattice"); the KATs pin the 10-round function
+
+
+def philox4x32(c0, c1, c2, c3, k0: int, k1: int, rounds: int = 10):
+    """Vectorised Philox4x32-R.  Counters are uint32 arrays (broadcastable)."""
     c0, c1, c2, c3 = np.broadcast_arrays(
         np.asarray(c0, dtype=np.uint64), np.asarray(c1, dtype=np.uint64),
         np.asarray(c2, dtype=np.uint64), np.asarray(c3, dtype=np.uint64))
     k0 &= 0xFFFFFFFF
     k1 &= 0xFFFFFFFF
-    for _ in range(10):
+    for _ in range(rounds):
         p0 = M0 * c0
         p1 = M1 * c2
         hi0, lo0 = p0 >> np.uint64(32), p0 & MASK32
@@ -64,7 +70,7 @@ def box_muller(x: np.ndarray):
 
 def normals8(c0, c1, c2, c3, seed: int):
     """Eight standard normals per counter: word w -> lanes 2w, 2w + 1."""
-    xs = philox4x32_10(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    xs = philox4x32(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, LATTICE_ROUNDS)
     out = []
     for x in xs:
         a, b = box_muller(x)

