@@ -66,6 +66,17 @@ static __global__ void __launch_bounds__(128) reduce_kernel(const ReduceArgs a, 
 // seq + 1 data first).
 constexpr int MAX_WORLD = 16;
 
+// Slot addressing of the exchange buffers: a slot's P doubles are laid out as 16-double (128-byte) lines 4 KB apart.
+// Every CTA of the persistent step kernel reads all `world` slots at the same moment; dense slots (1.6 KB at cfg2) sit
+// in one or two L2 slices and that read alone took 3.8 us of every step (r2 profile), spread lines are served by
+// different slices in parallel.
+constexpr int XCHG_LINE = 16, XCHG_STRIDE = 512;          // doubles per line, doubles between consecutive lines
+__host__ __device__ inline size_t xchg_lines(int P) { return (size_t)(P + XCHG_LINE - 1) / XCHG_LINE; }
+__host__ __device__ inline size_t xchg_slot_doubles(int P) { return xchg_lines(P) * XCHG_STRIDE; }
+__host__ __device__ inline size_t xchg_off(int P, int slot, int j) {
+    return ((size_t)slot * xchg_lines(P) + (size_t)(j >> 4)) * XCHG_STRIDE + (size_t)(j & 15);
+}
+
 struct XchgPostArgs {
     const double *sums;                       // this rank's partial sums [P]
     int P, world, rank, parity;
@@ -77,8 +88,8 @@ struct XchgPostArgs {
 static __global__ void __launch_bounds__(256) xchg_post_kernel(const XchgPostArgs a) {
     const int tid = threadIdx.x;
     for (int r = 0; r < a.world; ++r) {
-        double *dst = a.peer_buf[r] + (size_t)(a.parity * a.world + a.rank) * a.P;
-        for (int i = tid; i < a.P; i += blockDim.x) dst[i] = a.sums[i];
+        double *dst = a.peer_buf[r];
+        for (int i = tid; i < a.P; i += blockDim.x) dst[xchg_off(a.P, a.parity * a.world + a.rank, i)] = a.sums[i];
     }
     __threadfence_system();
     __syncthreads();
@@ -118,7 +129,7 @@ __device__ __forceinline__ bool xchg_wait_and_sum(const XchgWaitArgs &x, double 
     for (int i = tid; i < x.P; i += blockDim.x) {
         double s = 0.0;
         for (int r = 0; r < x.world; ++r)
-            s += *reinterpret_cast<const volatile double *>(x.buf + (size_t)(x.parity * x.world + r) * x.P + i);
+            s += *reinterpret_cast<const volatile double *>(x.buf + xchg_off(x.P, x.parity * x.world + r, i));
         sums[i] = s;
     }
     __syncthreads();
@@ -132,7 +143,7 @@ static __global__ void __launch_bounds__(256) peer_allreduce_kernel(double *vec,
                                                                     const XchgWaitArgs xw) {
     const int tid = threadIdx.x;
     for (int r = 0; r < xp.world; ++r) {
-        double *dst = xp.peer_buf[r] + (size_t)(xp.parity * xp.world + xp.rank) * xp.P;
+        double *dst = xp.peer_buf[r] + (size_t)(xp.parity * xp.world + xp.rank) * xp.P;     // auxiliary region: dense slots
         for (int i = tid; i < m; i += blockDim.x) dst[i] = vec[i];
     }
     __threadfence_system();
@@ -354,8 +365,9 @@ __global__ void __launch_bounds__(256) tail_kernel(const ReduceArgs ra, int R, c
     if (sa.xchg.buf) {
         // multi-GPU: this rank's sums go to every peer, the totals come back inside shared_body
         for (int r = 0; r < xp.world; ++r) {
-            double *dst = xp.peer_buf[r] + (size_t)(xp.parity * xp.world + xp.rank) * xp.P;
-            for (int i = threadIdx.x; i < xp.P; i += blockDim.x) dst[i] = __ldcg(ra.sums + i);
+            double *dst = xp.peer_buf[r];
+            for (int i = threadIdx.x; i < xp.P; i += blockDim.x)
+                dst[xchg_off(xp.P, xp.parity * xp.world + xp.rank, i)] = __ldcg(ra.sums + i);
         }
         __threadfence_system();
         __syncthreads();

@@ -216,7 +216,7 @@ int bb_derived_fitness(bb_handle *h, int32_t n_samples, uint64_t seed, double *m
     });
 }
 int64_t bb_n_derived(const bb_handle *h) { return h && h->eng && h->eng->L.hier ? h->eng->L.bc_block : 0; }
-int bb_data_plane(bb_handle *h, int32_t out[4]) {
+int bb_data_plane(bb_handle *h, int32_t out[8]) {
     return guarded(h, [&](bb::EngineBase &e) {
         if (!out) throw std::runtime_error("bb_data_plane: NULL argument");
         e.data_plane(out);

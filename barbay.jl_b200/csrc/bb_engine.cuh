@@ -116,7 +116,7 @@ class EngineBase {
     // in-kernel tails, summed since the last call (then reset); out[4] = SM clock in kHz
     virtual void persist_stats(double out[8]) = 0;
     // out = {packed step kernel in use, steps per persistent launch (0: off), peer-memory exchange on, NCCL communicator present}
-    virtual void data_plane(int32_t out[4]) = 0;
+    virtual void data_plane(int32_t out[8]) = 0;
     // one-process-per-GPU wiring without NCCL: every rank exports the CUDA IPC handle of its exchange buffer, the
     // caller gathers them with whatever transport it has (torch.distributed, MPI, a file) and hands all of them back
     virtual void peer_handle(char out[64]) = 0;
@@ -162,11 +162,13 @@ template <typename real> class Engine : public EngineBase {
     void derived_fitness(int n, uint64_t seed, double *median, double *sd) override;
     void peer_handle(char out[64]) override;
     void peer_attach(const char *handles, int n) override;
-    void data_plane(int32_t out[4]) override {
+    void data_plane(int32_t out[8]) override {
         out[0] = stepk_ok_ ? 1 : 0;
         out[1] = (stepk_ok_ && persist_chunk_ > 1 && !(comm_ && !xchg_on_)) ? persist_chunk_ : 0;
         out[2] = xchg_on_ ? 1 : 0;
         out[3] = comm_ ? 1 : 0;
+        out[4] = out[5] = out[6] = out[7] = 0;
+        if (stepk_ok_) { out[4] = groups_[0].step_occ; out[5] = groups_[0].step_nbuf; out[6] = groups_[0].step_stage_acc; out[7] = groups_[0].stblocks; }
     }
     // single-process multi-GPU (bb_multi.cuh): exchange buffers of all devices of the handle, peer access enabled
     void *xchg_local() const { return xchg_mem_; }
@@ -190,7 +192,7 @@ template <typename real> class Engine : public EngineBase {
         int facc_slots = 0;        // 0: the fused kernel is not available for this group
         // packed / persistent step kernel (bb_step_kernel.cuh); stepk == nullptr: not available for this shape
         StepKernelFn<real> stepk = nullptr;
-        int step_w = 1, step_acc_rows = 0, step_stage_ring = 0, step_occ = 0;
+        int step_w = 1, step_acc_rows = 0, step_stage_ring = 0, step_occ = 0, step_nbuf = 2, step_stage_acc = 1;
         size_t step_smem = 0;
         SegList stsegs;
         int stblocks = 0;
@@ -242,6 +244,7 @@ template <typename real> class Engine : public EngineBase {
     bool stepk_ok_ = false;        // every launch group (there is one: R == 1) has a step kernel that fits
     int persist_chunk_ = 0;        // steps per persistent launch (0: persistent mode off)
     DBuf<double> xpart_, gpart_, eps_steps_;
+    DBuf<uint4> eps_store_;        // binary16 draws of the next step, written by the step kernel's pass 1 (bb_step_kernel.cuh)
     DBuf<StepSync> step_sync_;
     int step_gsize_ = 32;
     void alloc_xchg();
@@ -433,8 +436,10 @@ template <typename real> void Engine<real>::build_groups() {
         const size_t th_b = (size_t)(L.tmax + L.nj) * BLOCK * sizeof(r2);
         const size_t p1acc = ((size_t)g.kchunk * slot_b + 15) / 16 * 16;
         const size_t trig_b = TrigTab<real>::BYTES;      // fp32: Box-Muller direction table at the head of smem
-        g.p1nbuf = trig_b + p1acc + 2 * th_b <= kMaxSmem ? 2 : 1;
-        g.p1smem = trig_b + p1acc + g.p1nbuf * th_b;
+        // hierarchical models: the hyper latents' draws of all samples of a column, fetched once per tile (bb_kernels.cuh)
+        const size_t hz1_b = L.hier ? (size_t)L.K * L.E * BLOCK * sizeof(real) : 0;
+        g.p1nbuf = trig_b + p1acc + 2 * th_b + hz1_b <= kMaxSmem ? 2 : 1;
+        g.p1smem = trig_b + p1acc + g.p1nbuf * th_b + hz1_b;
         if (g.p1smem > kMaxSmem) throw std::runtime_error("T x E too large for the column kernels' shared memory");
         BB_CUDA(cudaFuncSetAttribute((const void *)g.ks.pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p1smem));
         BB_CUDA(cudaFuncSetAttribute((const void *)g.ks_sup.pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p1smem));
@@ -467,15 +472,16 @@ template <typename real> void Engine<real>::size_pass2() {
         // prefetched set (theta, priors, counts: one or two buffers) + epilogue set (accumulators, ring: one).
         // TruncatedADAGrad: the evicted ring slot is staged too unless that costs the fused step kernel its third
         // resident CTA per SM (cfg2, K = 8) -- then the epilogue reads the slot straight from global memory.
+        const size_t hz2_b = L.hier ? (size_t)L.K * L.E * BLOCK * sizeof(r2) : 0;     // hyper draws of a column, all samples
         auto plan = [&](int stage_ring) {
             const size_t pre_b = (1 + npr) * th_b + cn_b, epi_b = (1 + stage_ring) * th_b;
             g.p2nbuf = 2; g.p2stage_acc = 1; g.p2stage_ring = stage_ring;
             size_t stage_b = 2 * pre_b + epi_b;
-            if (ctx_b + sel_b + stage_b > kMaxSmem) { g.p2nbuf = 1; stage_b = pre_b + epi_b; }
-            if (ctx_b + sel_b + stage_b > kMaxSmem) { g.p2stage_acc = 0; stage_b = th_b + cn_b; }
-            if (ctx_b + sel_b + stage_b > kMaxSmem)
+            if (ctx_b + sel_b + stage_b + hz2_b > kMaxSmem) { g.p2nbuf = 1; stage_b = pre_b + epi_b; }
+            if (ctx_b + sel_b + stage_b + hz2_b > kMaxSmem) { g.p2stage_acc = 0; stage_b = th_b + cn_b; }
+            if (ctx_b + sel_b + stage_b + hz2_b > kMaxSmem)
                 throw std::runtime_error("T x E too large for the column kernels' shared memory");
-            g.p2smem = ctx_b + stage_b;                                               // ELBO = false kernels
+            g.p2smem = ctx_b + stage_b + hz2_b;                                       // ELBO = false kernels
             g.p2smem_elbo = g.p2smem + sel_b;
             // fused step kernel (non-hierarchical, all K samples in one sweep of the mutant accumulators)
             g.facc_slots = 0;
@@ -514,31 +520,44 @@ template <typename real> void Engine<real>::size_pass2() {
                 const int pvs_m = L.E == 1 ? 2 * g.nt : 3 * g.nt - 2, pvs_n = 3 * g.nt - 2;
                 const int rows = std::max(npack * ((pvs_m + 1) / 2), (pvs_n + 1) / 2);
                 const size_t spb = (size_t)2 * W * sizeof(real);        // one SlotPair
-                // mbarriers | packed context | persistent: sigma, z, eps of the population latents | their (theta, acc)
+                // mbarriers | packed context | ... | behind the accumulators: (theta, acc) and sigma of the population latents
                 const size_t head = 128 + r128((size_t)npack * 3 * g.nt * W * sizeof(real)) +
-                                    ((size_t)(2 * (g.nt - 1)) * (1 + 2 * L.K) * sizeof(real) + 15) / 16 * 16 +
-                                    r128((size_t)4 * (g.nt - 1) * sizeof(double2));
-                auto total = [&](int stage_ring) {
-                    return head + 2 * ((1 + npr) * thb + cnb) + (size_t)(1 + stage_ring) * thb + (size_t)rows * BLOCK * spb;
+                                    (size_t)4 * (g.nt - 1) * sizeof(double2) + (size_t)2 * (g.nt - 1) * sizeof(real);
+                auto total = [&](int nbuf, int stage_acc, int stage_ring) {
+                    return head + (size_t)nbuf * ((1 + npr) * thb + cnb) +
+                           (stage_acc ? (size_t)(1 + stage_ring) * thb : 0) + (size_t)rows * BLOCK * spb;
                 };
                 const int min_occ = getenv("BB_STEPK_MIN_OCC") ? atoi(getenv("BB_STEPK_MIN_OCC")) : 3;
-                for (int stage_ring = nrg; stage_ring >= 0; --stage_ring) {
-                    const size_t sm = total(stage_ring);
+                // staging levels, richest first: (double buffer, accumulators [+ ring] staged) ... (single buffer, none).
+                // The level with the most resident CTAs per SM wins (the step is latency-bound: warps, not prefetch depth,
+                // are what it lacks); ties go to the richer level.  BB_STEPK_STAGE=<nbuf><acc><ring> forces one.
+                int best_occ = 0;
+                const char *force = getenv("BB_STEPK_STAGE");
+                for (int lvl = 0; lvl < 6; ++lvl) {
+                    static const int cfgs[6][3] = {{2, 1, 1}, {2, 1, 0}, {1, 1, 1}, {1, 1, 0}, {2, 0, 0}, {1, 0, 0}};
+                    const int nbuf = cfgs[lvl][0], sacc = cfgs[lvl][1], sring = cfgs[lvl][2];
+                    if (sring && !nrg) continue;
+                    if (force && (force[0] - '0' != nbuf || force[1] - '0' != sacc || force[2] - '0' != sring)) continue;
+                    const size_t sm = total(nbuf, sacc, sring);
                     if (sm > kMaxSmem) continue;
                     BB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
                     int occ = 0;
                     BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, BLOCK, sm));
-                    if (occ >= min_occ) {
-                        g.stepk = fn; g.step_w = W; g.step_acc_rows = rows; g.step_stage_ring = stage_ring;
+                    if (occ >= min_occ && occ > best_occ) {
+                        best_occ = occ;
+                        g.stepk = fn; g.step_w = W; g.step_acc_rows = rows; g.step_stage_ring = sring;
+                        g.step_nbuf = nbuf; g.step_stage_acc = sacc;
                         g.step_occ = occ; g.step_smem = sm;
-                        break;
                     }
                 }
+                if (g.stepk)
+                    BB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.step_smem));
                 if (g.stepk) {
                     assign_blocks(g.stsegs, g.nt, nsm_ * g.step_occ, &g.stblocks);
                     // scratch of the in-kernel tail (totals + shared_body's working arrays) aliases the accumulators
-                    const size_t tail_d = sums_.n + (size_t)L.K * (2 * g.nt + 3 * (g.nt - 1)) + 16;   // totals + working arrays
-                    g.step_persist = tail_d * sizeof(double) <= (size_t)rows * BLOCK * spb && (int)sums_.n <= 4096;
+                    const size_t tail_d = sums_.n + (size_t)L.K * (2 * g.nt + 7 * (g.nt - 1)) + 16;   // totals + working arrays
+                    g.step_persist = tail_d * sizeof(double) <= (size_t)rows * BLOCK * spb && (int)sums_.n <= 4096 &&
+                                     L.K * 2 * (g.nt - 1) <= BLOCK;
                 }
             }
         }
@@ -565,11 +584,20 @@ template <typename real> void Engine<real>::size_pass2() {
     if (stepk_ok_) {
         Group &g = groups_[0];
         xpart_.alloc((size_t)g.stblocks * sums_.n);
+        // stored noise: 16 bytes per (sample, Philox call, column).  K >= 2 only: at K = 1 the step is HBM-bound and
+        // regenerating is the cheaper side of the trade (BB_NO_EPS_STORE: always regenerate)
+        eps_store_.release();
+        if (g.step_w == 2 && !getenv("BB_NO_EPS_STORE")) {
+            const size_t nclass = (size_t)g.nt + 2 * L.E;
+            eps_store_.alloc((size_t)L.K * ((nclass + 7) / 8) * L.cpad, false);
+        }
         // persistent mode: default on for multi-GPU shards (the small-shard / strong-scaling path); BB_PERSIST overrides
         int coop = 0;
         BB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
+        // default: on for the shards of a multi-GPU run (tens of microseconds per step: the launch pair and the tail
+        // kernel are a large share), off on one GPU where the plain launch pair measured ~5 % faster at cfg2
         const char *pe = getenv("BB_PERSIST");
-        int want = pe ? atoi(pe) : 256;
+        int want = pe ? atoi(pe) : (L.world > 1 ? 256 : 0);
         if (!coop || !g.step_persist) want = 0;
         if (L.world > 1 && !xchg_on_) want = 0;
         if (want > 1) {
@@ -906,6 +934,8 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
             const bool trunc = opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p;
             sk.stage_ring = (trunc && g.step_stage_ring) ? 1 : 0;
             sk.l2_ring = (trunc && !g.step_stage_ring) ? 1 : 0;
+            sk.nbuf = g.step_nbuf; sk.stage_acc = g.step_stage_acc;
+            sk.eps_buf = eps_store_.p; sk.eps_valid = m.have_xpart ? 1 : 0;     // the launch that left xpart_ left the draws too
             sk.acc_rows = g.step_acc_rows; sk.tail_scratch = (int)sh_scratch_.n;
             sk.abort = (xchg_on_ && L.world > 1) ? xchg_err_.p : nullptr;
             sk.xpart = xpart_.p;
@@ -1318,7 +1348,7 @@ template <typename real> void Engine<real>::setup_peer_exchange() {
 template <typename real> void Engine<real>::alloc_xchg() {
     if (xchg_mem_) return;
     const size_t P = sums_.n;
-    xchg_flag_off_ = ((size_t)2 * L.world * P * sizeof(double) + 255) / 256 * 256;
+    xchg_flag_off_ = ((size_t)2 * L.world * xchg_slot_doubles((int)P) * sizeof(double) + 255) / 256 * 256;   // spread slots, bb_aux_kernels.cuh
     // behind the step exchange: an auxiliary region [2][world][kAuxP] + flags for short all-reduces (ELBO terms)
     xchg_aux_off_ = (xchg_flag_off_ + (size_t)2 * L.world * sizeof(unsigned long long) + 255) / 256 * 256;
     xchg_aux_flag_off_ = xchg_aux_off_ + (size_t)2 * L.world * kAuxP * sizeof(double);

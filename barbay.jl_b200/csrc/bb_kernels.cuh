@@ -311,6 +311,8 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
     const size_t acc_bytes = (((size_t)a.acc_slots * BLOCK * sizeof(real)) + 15) / 16 * 16;
     r2 *stage = reinterpret_cast<r2 *>(smem_raw + acc_bytes);          // [2][nt + nj][BLOCK]
     const int stage_stride = (C.tmax + C.nj) * BLOCK;
+    // hierarchical models: z of the column's hyper latents for all K samples, [K][E][BLOCK] behind the staging buffers
+    real *hzs = reinterpret_cast<real *>(stage + (size_t)a.nbuf * stage_stride) + tid;
 
     auto prefetch = [&](int tile, int buf) {
         const int i = tile * BLOCK + tid;
@@ -373,28 +375,31 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
             }
             const int nclass = seg.neutral ? nt : nt + nj;
 
-            // hierarchical models: the hyper latent's draw of sample k + 1 is loaded while sample k is computed
-            // (an L2 round trip per sample otherwise sits on the critical path of every warp)
-            real zth_nxt[S::MAXE];
-            auto load_zth = [&](int k) {
+            // hierarchical models: the hyper latents' draws of ALL samples of the chunk are fetched here, every load in
+            // flight at once, into a thread-private strip of shared memory (one dependent L2 round trip per sample on
+            // the critical path of every warp otherwise: the long-scoreboard stall of the round-1 profile)
+            if constexpr (HIER) {
+                if (!seg.neutral) {
+                    for (int k = kc0; k < kc1; ++k) {
+#pragma unroll
+                        for (int e = 0; e < S::MAXE; ++e) {
+                            if (e >= ne) break;
+                            hzs[((k - kc0) * ne + e) * BLOCK] = __ldg(&a.hy_zeps[(size_t)k * a.H + hbase + e]).x;
+                        }
+                    }
+                }
+            }
+#pragma unroll kP1Unroll
+            for (int k = kc0; k < kc1; ++k) {
+                real zth[S::MAXE];
                 if constexpr (HIER) {
                     if (!seg.neutral) {
 #pragma unroll
                         for (int e = 0; e < S::MAXE; ++e) {
                             if (e >= ne) break;
-                            zth_nxt[e] = a.hy_zeps[(size_t)k * a.H + hbase + e].x;
+                            zth[e] = hzs[((k - kc0) * ne + e) * BLOCK];
                         }
                     }
-                }
-            };
-            load_zth(kc0);
-#pragma unroll kP1Unroll
-            for (int k = kc0; k < kc1; ++k) {
-                real zth[S::MAXE];
-                if constexpr (HIER) {
-#pragma unroll
-                    for (int e = 0; e < S::MAXE; ++e) zth[e] = zth_nxt[e];
-                    if (k + 1 < kc1) load_zth(k + 1);
                 }
                 real eps[S::MAXC];
                 column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, strig,
@@ -433,8 +438,13 @@ __device__ __forceinline__ void pass1_column_direct(const real *mu, const real *
 // ===================================================================== optimiser
 // AdvancedVI 0.2 optimisers.jl (restated in oracle/advi_ref.py):
 //   DecayedADAGrad   acc = post*acc + pre*g^2 ; delta = eta*g / (sqrt(acc) + 1e-8)
-//   TruncatedADAGrad s   = sum of the last n g^2 (running form: s - evicted + g^2);
-//                    delta = eta*g / (tau + sqrt(s) + 1e-8)
+//   TruncatedADAGrad s   = sum of the last n g^2; delta = eta*g / (tau + sqrt(s) + 1e-8)
+// The window sum is kept in running form, s <- max(s - evicted, 0) + g^2.  The clamp sits BEFORE the new term: in
+// fp32, once the huge squared gradients of the first steps (1e14 for a 1e7-read barcode) have been evicted, the
+// cancellation residue of s - evicted can be any value of magnitude ulp(1e14) ~ 1e7, negative included; clamping
+// s - evicted + g^2 as a whole would then return 0 for a latent whose current g is large and turn the bounded
+// AdaGrad step (|delta| <= eta, as s >= g^2 in exact arithmetic) into eta * g / tau -- a jump that ends in inf / NaN
+// (seen after ~2 300 steps of the documented naive-prior workflow).  With the clamp inside, s >= g^2 always holds.
 template <typename real>
 __device__ __forceinline__ void opt_apply(const OptArgsT<real> &o, real g, real &theta, real &acc, real &ring_slot) {
     const real g2 = g * g;
@@ -443,7 +453,7 @@ __device__ __forceinline__ void opt_apply(const OptArgsT<real> &o, real g, real 
         acc = fma(o.post, acc, o.tau * g2);
         denom = bb_sqrt(acc) + real(1e-8);
     } else {
-        acc = fmax(acc - ring_slot + g2, real(0));
+        acc = fmax(acc - ring_slot, real(0)) + g2;
         ring_slot = g2;
         denom = o.tau + bb_sqrt(acc) + real(1e-8);
     }
@@ -476,8 +486,8 @@ __device__ __forceinline__ void finish_latent_mode(const OptArgsT<real> &o, real
             d0 = bb_sqrt(ac.x) + real(1e-8);
             d1 = bb_sqrt(ac.y) + real(1e-8);
         } else {
-            ac.x = fmax(ac.x - rg.x + q0, real(0));
-            ac.y = fmax(ac.y - rg.y + q1, real(0));
+            ac.x = fmax(ac.x - rg.x, real(0)) + q0;
+            ac.y = fmax(ac.y - rg.y, real(0)) + q1;
             *ring_ptr = mk2<real>(q0, q1);
             d0 = o.tau + bb_sqrt(ac.x) + real(1e-8);
             d1 = o.tau + bb_sqrt(ac.y) + real(1e-8);
@@ -535,8 +545,8 @@ __device__ __forceinline__ void finish_batch(const OptArgsT<real> &o, real invK,
                 d0[i] = bb_sqrt(ac[i].x) + real(1e-8);
                 d1[i] = bb_sqrt(ac[i].y) + real(1e-8);
             } else {
-                ac[i].x = fmax(ac[i].x - rg[i].x + q0, real(0));
-                ac[i].y = fmax(ac[i].y - rg[i].y + q1, real(0));
+                ac[i].x = fmax(ac[i].x - rg[i].x, real(0)) + q0;
+                ac[i].y = fmax(ac[i].y - rg[i].y, real(0)) + q1;
                 g_ring[(size_t)i * cpad] = mk2<real>(q0, q1);
                 d0[i] = o.tau + bb_sqrt(ac[i].x) + real(1e-8);
                 d1[i] = o.tau + bb_sqrt(ac[i].y) + real(1e-8);
@@ -640,6 +650,8 @@ pass2_kernel(const P2Args<real> a) {
     constexpr bool PAIRS = AccLayout<NT, NE>::PAIRS;
     const int pva = AccLayout<NT, NE>::rows(pvs);
     real *facc = reinterpret_cast<real *>(epi0 + (size_t)(nac + nrg) * th_bytes);
+    // hierarchical models (never fused): (z, eps) of the column's hyper latents for all K samples, [K][E][BLOCK]
+    r2 *hzs = reinterpret_cast<r2 *>(facc) + tid;
     if constexpr (FUSE)
         for (int i = tid; i < a.acc_slots * BLOCK; i += BLOCK) facc[i] = real(0);
 
@@ -805,6 +817,14 @@ pass2_kernel(const P2Args<real> a) {
                 hbase = C.hgroup[c];
 #pragma unroll
                 for (int e = 0; e < S::MAXE; ++e) { hc[e] = real(0); hce[e] = real(0); }
+                // every (sample, environment) draw of the column's hyper latents: all loads in flight together
+                for (int k = 0; k < a.K; ++k) {
+#pragma unroll
+                    for (int e = 0; e < S::MAXE; ++e) {
+                        if (e >= ne) break;
+                        hzs[(k * ne + e) * BLOCK] = __ldg(&a.hy_zeps[(size_t)k * a.H + hbase + e]);
+                    }
+                }
             }
         }
         const int nclass = seg.neutral ? nt : nt + nj;
@@ -812,27 +832,19 @@ pass2_kernel(const P2Args<real> a) {
         // the K samples; instantiated twice so the common vector-prior case carries no per-latent prior loads
         auto sample_loop = [&](auto matpr_tag) {
         constexpr bool MATPR = decltype(matpr_tag)::value;
-        // hierarchical models: (z, eps) of the hyper latent for sample k + 1 is loaded while sample k is computed
-        r2 hz_nxt[S::MAXE];
-        auto load_hz = [&](int k) {
+        // hierarchical models: (z, eps) of the column's hyper latents for all K samples were fetched at the top of the
+        // tile into the thread's shared-memory strip (see below)
+#pragma unroll(FUSE ? kFuseUnroll : kP2Unroll)
+        for (int k = 0; k < a.K; ++k) {
+            r2 hz_cur[S::MAXE];
             if constexpr (HIER) {
                 if (!seg.neutral) {
 #pragma unroll
                     for (int e = 0; e < S::MAXE; ++e) {
                         if (e >= ne) break;
-                        hz_nxt[e] = a.hy_zeps[(size_t)k * a.H + hbase + e];
+                        hz_cur[e] = hzs[(k * ne + e) * BLOCK];
                     }
                 }
-            }
-        };
-        load_hz(0);
-#pragma unroll(FUSE ? kFuseUnroll : kP2Unroll)
-        for (int k = 0; k < a.K; ++k) {
-            r2 hz_cur[S::MAXE];
-            if constexpr (HIER) {
-#pragma unroll
-                for (int e = 0; e < S::MAXE; ++e) hz_cur[e] = hz_nxt[e];
-                if (k + 1 < a.K) load_hz(k + 1);
             }
             real eps[S::MAXC];
             column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, strig, a.sup,

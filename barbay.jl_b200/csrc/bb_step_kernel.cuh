@@ -95,6 +95,10 @@ template <typename real> struct StepArgs {
     const real *ctx;               // [K][3][tmax] context of step `step` (written by tail_kernel)
     OptArgsT<real> opt;
     int stage_pr, stage_ring, l2_ring;
+    uint4 *eps_buf;                // stored draws [K / W][MAXC / 8][W][cpad] (see column_noise_pack), or nullptr: regenerate
+    int eps_valid;                 // 1: eps_buf holds the draws of step `step` (written by the previous launch)
+    int nbuf;                      // 2: the next tile is prefetched while this one is computed; 1: single staging buffer
+    int stage_acc;                 // 1: accumulators (and the ring slot) are staged for the epilogue; 0: read from global (L2-prefetched)
     int acc_rows;                  // budget of the pass-1 accumulators: rows of BLOCK x (2 slots x W samples)
     int tail_scratch;              // doubles of shared_body's working arrays (the in-kernel tail borrows the accumulators)
     double *xpart;                 // [gridDim.x][P] block partial sums of the next step, output space [k][q][t]
@@ -124,17 +128,27 @@ __device__ __forceinline__ void slot_to_out(bool neutral, int v, int &q, int &t,
 }
 
 // ---------------------------------------------------------------- noise for a pack of samples
+// The lattice's normals are binary16 values (bb_device.cuh).  `store` (nullable, already offset to the column, row
+// stride `cpad` uint4): the draws are written as half2 (sample k, sample k + 1) per latent -- W uint4 per Philox call
+// and column -- so the pass over the column in the NEXT launch / step reads 16 bytes per sample instead of running
+// Philox + Box-Muller again (column_noise_load).
+template <typename real> __device__ __forceinline__ real h2r(__half h) { return (real)__half2float(h); }
+
 template <typename real, int W, int MAXC>
 __device__ __forceinline__ void column_noise_pack(Pack<real, W> (&eps)[MAXC], int nclass, uint32_t colid, uint32_t k0,
-                                                  uint32_t step, const PhiloxKey &key, const float2 *tab) {
+                                                  uint32_t step, const PhiloxKey &key, const float2 *tab, uint4 *store,
+                                                  size_t cpad) {
 #pragma unroll
     for (int q = 0; q < MAXC / 8; ++q) {
         if (q * 8 >= nclass) break;
+        __half2 hp[4 * W];              // W == 2: hp[l] = (sample k, sample k + 1) of lane l; W == 1: hp[l] = lanes (2l, 2l + 1)
         if constexpr (W == 1) {
             real n[8];
             normals8<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k0, step, key, tab, n);
 #pragma unroll
             for (int l = 0; l < 8; ++l) eps[8 * q + l].v = n[l];
+#pragma unroll
+            for (int l = 0; l < 4; ++l) hp[l] = __floats2half2_rn((float)n[2 * l], (float)n[2 * l + 1]);
         } else if constexpr (std::is_same<real, float>::value) {
             uint32_t xa[4], xb[4];
             philox4x32(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k0, step, key, xa);
@@ -149,15 +163,49 @@ __device__ __forceinline__ void column_noise_pack(Pack<real, W> (&eps)[MAXC], in
                 const float sa = __uint_as_float(__float_as_uint(ra) | ((xa[w] << 21) & 0x80000000u));
                 const float sb = __uint_as_float(__float_as_uint(rb) | ((xb[w] << 21) & 0x80000000u));
                 const float2 da = tab[xa[w] & (TRIG_N - 1)], db = tab[xb[w] & (TRIG_N - 1)];
-                eps[8 * q + 2 * w] = pk_make(sa * da.x, sb * db.x);
-                eps[8 * q + 2 * w + 1] = pk_make(sa * da.y, sb * db.y);
+                hp[2 * w] = __floats2half2_rn(sa * da.x, sb * db.x);          // the binary16 rounding of the lattice
+                hp[2 * w + 1] = __floats2half2_rn(sa * da.y, sb * db.y);
+                eps[8 * q + 2 * w].v = __half22float2(hp[2 * w]);
+                eps[8 * q + 2 * w + 1].v = __half22float2(hp[2 * w + 1]);
             }
         } else {
             real na[8], nb[8];
             normals8<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k0, step, key, tab, na);
             normals8<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k0 + 1u, step, key, tab, nb);
 #pragma unroll
-            for (int l = 0; l < 8; ++l) eps[8 * q + l] = pk_make(na[l], nb[l]);
+            for (int l = 0; l < 8; ++l) {
+                eps[8 * q + l] = pk_make(na[l], nb[l]);
+                hp[l] = __floats2half2_rn((float)na[l], (float)nb[l]);         // exact: the values are binary16 already
+            }
+        }
+        if (store) {
+#pragma unroll
+            for (int h = 0; h < W; ++h) {
+                uint4 v;
+                v.x = *reinterpret_cast<const uint32_t *>(&hp[4 * h]); v.y = *reinterpret_cast<const uint32_t *>(&hp[4 * h + 1]);
+                v.z = *reinterpret_cast<const uint32_t *>(&hp[4 * h + 2]); v.w = *reinterpret_cast<const uint32_t *>(&hp[4 * h + 3]);
+                __stcs(&store[(size_t)(q * W + h) * cpad], v);       // read once, by the next launch / step: streaming
+            }
+        }
+    }
+}
+
+// the draws stored by column_noise_pack: `raw` holds the W uint4 of every Philox call of the pack
+template <typename real, int W, int MAXC>
+__device__ __forceinline__ void column_noise_unpack(Pack<real, W> (&eps)[MAXC], int nclass, const uint4 *raw) {
+#pragma unroll
+    for (int q = 0; q < MAXC / 8; ++q) {
+        if (q * 8 >= nclass) break;
+#pragma unroll
+        for (int h = 0; h < W; ++h) {
+            const uint4 v = raw[q * W + h];
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __half2 hh = *reinterpret_cast<const __half2 *>(&w4[j]);
+                if constexpr (W == 2) eps[8 * q + 4 * h + j] = pk_make(h2r<real>(__low2half(hh)), h2r<real>(__high2half(hh)));
+                else { eps[8 * q + 2 * j].v = h2r<real>(__low2half(hh)); eps[8 * q + 2 * j + 1].v = h2r<real>(__high2half(hh)); }
+            }
         }
     }
 }
@@ -325,22 +373,22 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
     const int npack = a.K / W;
     sp += ((size_t)npack * CSP * sizeof(P) + 127) / 128 * 128;
     double2 *s_sh_th = nullptr, *s_sh_acc = nullptr;
-    real *s_sig = nullptr, *s_z = nullptr, *s_eps = nullptr;       // sigma [2n]; z, eps [K][2n] of the NEXT in-kernel tail
-    if (persist) {
-        s_sig = reinterpret_cast<real *>(sp); sp += (size_t)2 * (NT - 1) * sizeof(real);
-        s_z = reinterpret_cast<real *>(sp); sp += (size_t)a.K * 2 * (NT - 1) * sizeof(real);
-        s_eps = reinterpret_cast<real *>(sp); sp += (size_t)a.K * 2 * (NT - 1) * sizeof(real);
-        sp = step_smem + ((sp - step_smem) + 15) / 16 * 16;
-        s_sh_th = reinterpret_cast<double2 *>(sp); sp += (size_t)2 * (NT - 1) * sizeof(double2);
-        s_sh_acc = reinterpret_cast<double2 *>(sp); sp += (size_t)2 * (NT - 1) * sizeof(double2);
-        sp = step_smem + ((sp - step_smem) + 127) / 128 * 128;
-    }
+    real *s_sig = nullptr;                  // sigma [2n] of the population latents
+    // thread j < K * 2n carries (z, eps) of population latent j % 2n, sample j / 2n, for the NEXT in-kernel tail in two
+    // registers across the column phase (shared memory is the occupancy limiter: three CTAs fit with 288 bytes to spare)
+    real my_z = real(0), my_eps = real(0);
     const int npr = a.stage_pr ? 1 : 0, nrg = a.stage_ring ? 1 : 0;
     constexpr size_t th_bytes = (size_t)ROWS * BLOCK * sizeof(r2), cn_bytes = (size_t)NT * BLOCK * sizeof(int);
     const size_t buf_bytes = (1 + npr) * th_bytes + cn_bytes;
-    unsigned char *stage0 = sp; sp += 2 * buf_bytes;
-    unsigned char *epi0 = sp; sp += (size_t)(1 + nrg) * th_bytes;
+    unsigned char *stage0 = sp; sp += (size_t)a.nbuf * buf_bytes;
+    unsigned char *epi0 = sp; sp += a.stage_acc ? (size_t)(1 + nrg) * th_bytes : 0;
     SP *facc = reinterpret_cast<SP *>(sp);
+    sp += (size_t)a.acc_rows * BLOCK * sizeof(SP);
+    if (persist) {                          // the small persistent state sits behind the (128-byte aligned) big regions
+        s_sh_th = reinterpret_cast<double2 *>(sp); sp += (size_t)2 * (NT - 1) * sizeof(double2);
+        s_sh_acc = reinterpret_cast<double2 *>(sp); sp += (size_t)2 * (NT - 1) * sizeof(double2);
+        s_sig = reinterpret_cast<real *>(sp);
+    }
 
     const int sidx = find_segment(a.segs, blockIdx.x);
     const Seg seg = a.segs.seg[sidx];
@@ -452,7 +500,7 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
             const double2 th = a.sa.sh_th[i];
             const real sg = softplus_only<real>((real)th.y);
             const real e = (real)a.sa.eps_sh[(size_t)a.K * N2 + j];
-            s_eps[j] = e; s_z[j] = fma(sg, e, (real)th.x);
+            my_eps = e; my_z = fma(sg, e, (real)th.x);          // K * 2n <= BLOCK (checked by the host)
             if (j < N2) s_sig[i] = sg;
         }
     }
@@ -473,14 +521,24 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
             if (warp_has(first)) issue_pre(first, 0);
         }
         int buf = 0;
-        for (int tile = first; tile < ntile; tile += nblk, buf ^= 1) {
+        for (int tile = first; tile < ntile; tile += nblk, buf ^= (a.nbuf - 1)) {
             if (!warp_has(tile)) continue;   // (warp-uniform) a partial last tile leaves whole warps without columns
             __syncwarp();                    // the warp is done with the previous tile's buffers
-            issue_epi(tile, lam_ring, bc_ring);
-            if (warp_has(tile + nblk)) issue_pre(tile + nblk, buf ^ 1);
+            if (a.stage_acc) issue_epi(tile, lam_ring, bc_ring);
+            if (a.nbuf == 2 && warp_has(tile + nblk)) issue_pre(tile + nblk, buf ^ 1);
             const int i = tile * BLOCK + tid;
             const bool active = i < seg.ncol;
             const int c = seg.col0 + (active ? i : 0);
+            if (!a.stage_acc && active) {    // the epilogue reads the accumulators from global memory: have them in L2 by then
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(C.lam_acc + ((uint32_t)t * (uint32_t)cpad + c)));
+                if (!neutral) {
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(C.bc_acc + ((uint32_t)j * (uint32_t)cpad + c)));
+                }
+            }
             if (a.l2_ring && active) {
 #pragma unroll
                 for (int t = 0; t < NT; ++t)
@@ -535,9 +593,27 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
 
                 // ---- the K samples, W at a time
 #pragma unroll kStepUnroll2
+                constexpr int NQ8 = S::MAXC / 8, NRAW = NQ8 * W;        // uint4 per (pack, column) of the stored draws
+                const bool eps_stored = a.eps_buf != nullptr && (si > 0 || a.eps_valid);
+                const uint4 *eload = a.eps_buf + c;
+                uint4 raw_nxt[NRAW];
+                auto load_raw = [&](int kp) {
+#pragma unroll
+                    for (int r = 0; r < NRAW; ++r)
+                        if ((r / W) * 8 < nclass) raw_nxt[r] = __ldcs(eload + (size_t)(kp * NRAW + r) * cpad);
+                };
+                if (eps_stored) load_raw(0);
                 for (int kp = 0; kp < npack; ++kp) {
                     P eps[S::MAXC];
-                    column_noise_pack<real, W, S::MAXC>(eps, nclass, colid, (uint32_t)(kp * W), step, a.key, strig);
+                    if (eps_stored) {
+                        uint4 raw[NRAW];
+#pragma unroll
+                        for (int r = 0; r < NRAW; ++r) raw[r] = raw_nxt[r];
+                        if (kp + 1 < npack) load_raw(kp + 1);         // the next pack's draws are in flight during this one
+                        column_noise_unpack<real, W, S::MAXC>(eps, nclass, raw);
+                    } else {
+                        column_noise_pack<real, W, S::MAXC>(eps, nclass, colid, (uint32_t)(kp * W), step, a.key, strig, nullptr, 0);
+                    }
                     const P *crow = sctx + (size_t)kp * CSP;       // {c_t - sbar_t | G_t | wbar_t}
                     P z[NT], g[NT];
 #pragma unroll
@@ -598,15 +674,17 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) { fgrb[j] = pk_hsum(sgrb[j]); fgeb[j] = pk_hsum(sgeb[j]); }
 
-                mbar_wait(wbar + 2, ph_epi);      // this tile's accumulators (and ring slot)
+                if (a.stage_acc) mbar_wait(wbar + 2, ph_epi);      // this tile's accumulators (and ring slot)
                 // fused optimiser update of every latent of the column
                 auto finish_all = [&](auto mode_tag) {
                     constexpr int MODE = decltype(mode_tag)::value;
-                    finish_batch<real, MODE, NT, true>(a.opt, invK, NT, fgr, fge, mu, sg, sth, sac, nrg ? srg : nullptr,
+                    finish_batch<real, MODE, NT, true>(a.opt, invK, NT, fgr, fge, mu, sg, sth, a.stage_acc ? sac : nullptr,
+                                                       (nrg && a.stage_acc) ? srg : nullptr,
                                                        C.lam_th + c, C.lam_acc + c, lam_ring + c, nullptr, (size_t)cpad);
                     if (!neutral)
                         finish_batch<real, MODE, NJ, true>(a.opt, invK, NJ, fgrb, fgeb, mub, sgb, sth + NT * BLOCK,
-                                                           sac + NT * BLOCK, nrg ? srg + NT * BLOCK : nullptr, C.bc_th + c,
+                                                           a.stage_acc ? sac + NT * BLOCK : nullptr,
+                                                           (nrg && a.stage_acc) ? srg + NT * BLOCK : nullptr, C.bc_th + c,
                                                            C.bc_acc + c, bc_ring + c, nullptr, (size_t)cpad);
                 };
                 if (a.opt.kind == 1) finish_all(std::integral_constant<int, 0>{});
@@ -617,14 +695,19 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
 #pragma unroll kStepUnroll1
                     for (int kp = 0; kp < npack; ++kp) {
                         P eps[S::MAXC];
-                        column_noise_pack<real, W, S::MAXC>(eps, nclass, colid, (uint32_t)(kp * W), step + 1u, a.key, strig);
+                        column_noise_pack<real, W, S::MAXC>(eps, nclass, colid, (uint32_t)(kp * W), step + 1u, a.key, strig,
+                                                            a.eps_buf ? a.eps_buf + (size_t)kp * NRAW * cpad + c : nullptr, (size_t)cpad);
                         pass1_pack<real, NT, NE, W>(eps, mu, sg, mub, sgb, false, a.env_of_t, facc + (size_t)kp * nqp * BLOCK + tid);
                     }
                 }
-            } else {
+            } else if (a.stage_acc) {
                 mbar_wait(wbar + 2, ph_epi);
             }
-            ph_epi ^= 1u;
+            if (a.stage_acc) ph_epi ^= 1u;
+            if (a.nbuf == 1 && warp_has(tile + nblk)) {       // single buffer: refill it once the whole warp has read this tile
+                __syncwarp();
+                issue_pre(tile + nblk, 0);
+            }
         }
 
         // ---- block partial sums of the next step -> xpart[block][k][q][t]
@@ -654,7 +737,9 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
 #pragma unroll 1
                     for (int kp = kc0; kp < kc1; ++kp) {
                         P eps[S::MAXC];
-                        column_noise_pack<real, W, S::MAXC>(eps, NT, colid, (uint32_t)(kp * W), step + 1u, a.key, strig);
+                        column_noise_pack<real, W, S::MAXC>(eps, NT, colid, (uint32_t)(kp * W), step + 1u, a.key, strig,
+                                                            a.eps_buf ? a.eps_buf + (size_t)kp * (S::MAXC / 8 * W) * cpad + c : nullptr,
+                                                            (size_t)cpad);
                         pass1_pack<real, NT, NE, W>(eps, mu, sg, mu, sg, true, a.env_of_t, facc + (size_t)(kp - kc0) * nqp * BLOCK + tid);
                     }
                 }
@@ -671,7 +756,7 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
         const unsigned long long seq = a.xp.seq + (unsigned long long)si;
         const int parity = (int)(seq & 1ull);
         const int world = a.xp.world;
-        __shared__ int s_flag;
+        int &s_flag = *reinterpret_cast<int *>(bars + 3 * (BLOCK / 32));     // spare slot of the barrier block
         __threadfence();
         fence_proxy_async();             // this CTA's theta / accumulator stores vs. the next step's bulk copies
         __syncthreads();
@@ -703,7 +788,7 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
                 for (int j = tid; j < a.P; j += BLOCK) {
                     double s = 0.0;
                     for (int g = 0; g < a.ngroups; ++g) s += __ldcg(a.gpart + (size_t)g * a.P + j);
-                    for (int r = 0; r < world; ++r) a.xp.peer_buf[r][(size_t)(parity * world + a.xp.rank) * a.P + j] = s;
+                    for (int r = 0; r < world; ++r) a.xp.peer_buf[r][xchg_off(a.P, parity * world + a.xp.rank, j)] = s;
                 }
                 __threadfence_system();
                 __syncthreads();
@@ -731,6 +816,7 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
             const unsigned long long *f = a.xflag + (parity * world + tid);
             const long long t0 = clock64();
             while (ld_acquire_sys(f) != seq) {
+                __nanosleep(40);         // hundreds of CTAs poll the same line: leave the L2 slice room for the flag's store
                 if (clock64() - t0 > 4000000000LL) { a.sync->err = 1; a.sync->steps_done = si; abort_flag = 1; break; }   // ~2 s
                 if (*reinterpret_cast<volatile int *>(&a.sync->err)) { abort_flag = 1; break; }
             }
@@ -746,9 +832,11 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
         real *w_il = w_lgl + a.K * NT;                           // [K][T] 1 / Lambda
         real *w_g = w_il + a.K * NT;                             // [K][2n] per-sample gradients of the shared latents
         real *w_u = w_g + a.K * N2;                              // [K][n] sum_all w res
+        real *s_z = w_u + a.K * (NT - 1), *s_eps = s_z + a.K * N2;   // [K][2n] this tail's draws, from their owners' registers
+        if (tid < a.K * N2) { s_z[tid] = my_z; s_eps[tid] = my_eps; }
         for (int j = tid; j < a.P; j += BLOCK) {
             double s = 0.0;
-            for (int r = 0; r < world; ++r) s += __ldcg(a.xbuf + (size_t)(parity * world + r) * a.P + j);
+            for (int r = 0; r < world; ++r) s += __ldcg(a.xbuf + xchg_off(a.P, parity * world + r, j));
             tot[j] = s;
         }
         __syncthreads();
@@ -799,8 +887,8 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
                 ac.y = fma((real)a.sa.opt.post, (real)ac.y, (real)a.sa.opt.tau * q1);
                 d0 = bb_sqrt((real)ac.x) + real(1e-8); d1 = bb_sqrt((real)ac.y) + real(1e-8);
             } else {
-                ac.x = fmax((real)ac.x - (real)ring_old.x + q0, real(0));
-                ac.y = fmax((real)ac.y - (real)ring_old.y + q1, real(0));
+                ac.x = fmax((real)ac.x - (real)ring_old.x, real(0)) + q0;
+                ac.y = fmax((real)ac.y - (real)ring_old.y, real(0)) + q1;
                 if (blockIdx.x == 0) ring_wr[tid] = make_double2((double)q0, (double)q1);
                 d0 = (real)a.sa.opt.tau + bb_sqrt((real)ac.x) + real(1e-8);
                 d1 = (real)a.sa.opt.tau + bb_sqrt((real)ac.y) + real(1e-8);
@@ -813,11 +901,10 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
         __syncthreads();
         st_a += tca - tc2; st_b += clock64() - tca;
         // z = mu + sigma eps of the next in-kernel tail, from the noise fetched before the wait
-        if (si + 2 < a.nsteps)
-            for (int j = tid; j < a.K * N2; j += BLOCK) {
-                const int i = j % N2;
-                s_eps[j] = eps_next; s_z[j] = fma(s_sig[i], eps_next, (real)s_sh_th[i].x);
-            }
+        if (si + 2 < a.nsteps && tid < a.K * N2) {
+            const int i = tid % N2;
+            my_eps = eps_next; my_z = fma(s_sig[i], eps_next, (real)s_sh_th[i].x);
+        }
         __syncthreads();
         // the scratch aliased the accumulators: zero them again for the next column phase
         for (int i = tid; i < a.acc_rows * BLOCK; i += BLOCK) facc[i] = SP{pk_zero<real, W>(), pk_zero<real, W>()};

@@ -286,10 +286,11 @@ class Engine:
 
     def data_plane(self) -> dict:
         """Which kernels / exchange this handle runs (for reporting)."""
-        out = (C.c_int32 * 4)()
+        out = (C.c_int32 * 8)()
         self._check(self._lib.bb_data_plane(self._h, out))
         return {"step_kernel": bool(out[0]), "persistent": out[1] > 1, "persist_chunk": int(out[1]),
-                "peer_exchange": bool(out[2]), "nccl": bool(out[3])}
+                "peer_exchange": bool(out[2]), "nccl": bool(out[3]), "ctas_per_sm": int(out[4]),
+                "staging_buffers": int(out[5]), "acc_staged": bool(out[6]), "grid": int(out[7])}
 
     def persist_stats(self) -> dict:
         """Per-step breakdown of the persistent step kernel since the last call (microseconds, CTA 0's clock):

@@ -178,8 +178,9 @@ int bb_derived_fitness(bb_handle *h, int32_t n_samples, uint64_t seed, double *m
 int64_t bb_n_derived(const bb_handle *h);
 
 /* Which kernels / data plane this handle runs: out = {packed step kernel in use, steps per persistent launch
- * (0: one launch pair per step), NVLink peer-memory exchange on, NCCL communicator present}. */
-int bb_data_plane(bb_handle *h, int32_t out[4]);
+ * (0: one launch pair per step), NVLink peer-memory exchange on, NCCL communicator present, resident CTAs per SM of
+ * the step kernel, its staging buffers (1 / 2), accumulators staged (0 / 1), its grid size}. */
+int bb_data_plane(bb_handle *h, int32_t out[8]);
 
 /* ---- multi-GPU, one process per GPU, WITHOUT NCCL: every rank exports the CUDA IPC handle (64 bytes) of its
  * exchange buffer, the caller gathers the `world` handles in rank order with whatever transport it has

@@ -170,7 +170,8 @@ def test_device_derived_fitness_rows_match_host_sampler(bb, model):
     assert len(a) > 0 and (a["varname"] == b["varname"]).all() and (a["id"] == b["id"]).all()
     sd = b["std"].to_numpy()
     assert np.max(np.abs(a["mean"].to_numpy() - b["mean"].to_numpy()) / sd) < 0.08
-    assert np.max(np.abs(a["std"].to_numpy() / sd - 1.0)) < 0.06
+    # exp(logτ) makes the draws heavy-tailed where the fit is still wide: the sample sd itself is noisy there
+    assert np.max(np.abs(a["std"].to_numpy() / sd - 1.0)) < 0.15 and np.median(np.abs(a["std"].to_numpy() / sd - 1.0)) < 0.03
     # the fitted rows themselves are untouched by the choice
     fa, fb = dev[dev.vartype != "bc_fitness"], host[host.vartype != "bc_fitness"]
     assert np.array_equal(fa["mean"].to_numpy(), fb["mean"].to_numpy())
