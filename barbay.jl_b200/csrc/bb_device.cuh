@@ -2,7 +2,6 @@
 // sm_100a only.  See DESIGN.md "Noise lattice" for the counter layout; the oracle
 // restates it independently in oracle/philox_ref.py.
 #pragma once
-#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -71,13 +70,6 @@ __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ft
 // (the XU pipe is the scarce one in the column kernels): TRIG_N = 1024 entries sqrt(2 ln 2) (cos, sin),
 // rounded once from double, cover the half turn a & 1023; bit 10 of the word flips the sign of the radius.  `tab` is the table -- the
 // column kernels pass their shared-memory copy, everything else the global one of the key.
-// Every normal of the lattice is finally ROUNDED TO IEEE binary16 (11 significant bits, round to nearest even):
-// the K = 8 step is bound by instruction dispatch, not by HBM, and most of its instructions regenerate the noise for
-// the second pass over a column; with 16-bit draws the fused step kernel stores them once (16 B per column and
-// sample) and reads them back instead (bb_step_kernel.cuh).  The rounding perturbs the unit variance by < 1e-7.
-__device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
-__device__ __forceinline__ double round_h(double x) { return (double)__half2float(__double2half(x)); }
-
 constexpr int TRIG_N = 1024;
 __device__ __forceinline__ void box_muller(uint32_t x, float &n0, float &n1, const float2 *tab) {
     // j = x >> 11 dropped into the mantissa of 4.0f by one funnel shift: 4 + j 2^-21, minus (4 - 2^-22) -> (j + 0.5) / 2^21, exact
@@ -85,8 +77,7 @@ __device__ __forceinline__ void box_muller(uint32_t x, float &n0, float &n1, con
     const float radius = fast_sqrt(-fast_lg2(u));   // sqrt(-2 ln u) / sqrt(2 ln 2): the table carries the factor
     const float rs = __uint_as_float(__float_as_uint(radius) | ((x << 21) & 0x80000000u));
     const float2 d = tab[x & (TRIG_N - 1)];
-    const float2 r = __half22float2(__floats2half2_rn(rs * d.x, rs * d.y));
-    n0 = r.x; n1 = r.y;
+    n0 = rs * d.x; n1 = rs * d.y;
 }
 __device__ __forceinline__ void box_muller(uint32_t x, double &n0, double &n1, const float2 *) {
     const double u = (static_cast<double>(x >> 11) + 0.5) * (1.0 / 2097152.0);
@@ -94,7 +85,7 @@ __device__ __forceinline__ void box_muller(uint32_t x, double &n0, double &n1, c
     const double radius = sqrt(-2.0 * log(u));
     double s, c;
     sincospi(2.0 * v, &s, &c);
-    n0 = round_h(radius * c); n1 = round_h(radius * s);
+    n0 = radius * c; n1 = radius * s;
 }
 
 // eight normals per counter: word w -> lanes 2w (radius * cos) and 2w + 1 (radius * sin)

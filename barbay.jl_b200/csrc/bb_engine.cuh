@@ -244,7 +244,6 @@ template <typename real> class Engine : public EngineBase {
     bool stepk_ok_ = false;        // every launch group (there is one: R == 1) has a step kernel that fits
     int persist_chunk_ = 0;        // steps per persistent launch (0: persistent mode off)
     DBuf<double> xpart_, gpart_, eps_steps_;
-    DBuf<uint4> eps_store_;        // binary16 draws of the next step, written by the step kernel's pass 1 (bb_step_kernel.cuh)
     DBuf<StepSync> step_sync_;
     int step_gsize_ = 32;
     void alloc_xchg();
@@ -436,10 +435,8 @@ template <typename real> void Engine<real>::build_groups() {
         const size_t th_b = (size_t)(L.tmax + L.nj) * BLOCK * sizeof(r2);
         const size_t p1acc = ((size_t)g.kchunk * slot_b + 15) / 16 * 16;
         const size_t trig_b = TrigTab<real>::BYTES;      // fp32: Box-Muller direction table at the head of smem
-        // hierarchical models: the hyper latents' draws of all samples of a column, fetched once per tile (bb_kernels.cuh)
-        const size_t hz1_b = L.hier ? (size_t)L.K * L.E * BLOCK * sizeof(real) : 0;
-        g.p1nbuf = trig_b + p1acc + 2 * th_b + hz1_b <= kMaxSmem ? 2 : 1;
-        g.p1smem = trig_b + p1acc + g.p1nbuf * th_b + hz1_b;
+        g.p1nbuf = trig_b + p1acc + 2 * th_b <= kMaxSmem ? 2 : 1;
+        g.p1smem = trig_b + p1acc + g.p1nbuf * th_b;
         if (g.p1smem > kMaxSmem) throw std::runtime_error("T x E too large for the column kernels' shared memory");
         BB_CUDA(cudaFuncSetAttribute((const void *)g.ks.pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p1smem));
         BB_CUDA(cudaFuncSetAttribute((const void *)g.ks_sup.pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p1smem));
@@ -472,16 +469,15 @@ template <typename real> void Engine<real>::size_pass2() {
         // prefetched set (theta, priors, counts: one or two buffers) + epilogue set (accumulators, ring: one).
         // TruncatedADAGrad: the evicted ring slot is staged too unless that costs the fused step kernel its third
         // resident CTA per SM (cfg2, K = 8) -- then the epilogue reads the slot straight from global memory.
-        const size_t hz2_b = L.hier ? (size_t)L.K * L.E * BLOCK * sizeof(r2) : 0;     // hyper draws of a column, all samples
         auto plan = [&](int stage_ring) {
             const size_t pre_b = (1 + npr) * th_b + cn_b, epi_b = (1 + stage_ring) * th_b;
             g.p2nbuf = 2; g.p2stage_acc = 1; g.p2stage_ring = stage_ring;
             size_t stage_b = 2 * pre_b + epi_b;
-            if (ctx_b + sel_b + stage_b + hz2_b > kMaxSmem) { g.p2nbuf = 1; stage_b = pre_b + epi_b; }
-            if (ctx_b + sel_b + stage_b + hz2_b > kMaxSmem) { g.p2stage_acc = 0; stage_b = th_b + cn_b; }
-            if (ctx_b + sel_b + stage_b + hz2_b > kMaxSmem)
+            if (ctx_b + sel_b + stage_b > kMaxSmem) { g.p2nbuf = 1; stage_b = pre_b + epi_b; }
+            if (ctx_b + sel_b + stage_b > kMaxSmem) { g.p2stage_acc = 0; stage_b = th_b + cn_b; }
+            if (ctx_b + sel_b + stage_b > kMaxSmem)
                 throw std::runtime_error("T x E too large for the column kernels' shared memory");
-            g.p2smem = ctx_b + stage_b + hz2_b;                                       // ELBO = false kernels
+            g.p2smem = ctx_b + stage_b;                                       // ELBO = false kernels
             g.p2smem_elbo = g.p2smem + sel_b;
             // fused step kernel (non-hierarchical, all K samples in one sweep of the mutant accumulators)
             g.facc_slots = 0;
@@ -584,13 +580,7 @@ template <typename real> void Engine<real>::size_pass2() {
     if (stepk_ok_) {
         Group &g = groups_[0];
         xpart_.alloc((size_t)g.stblocks * sums_.n);
-        // stored noise: 16 bytes per (sample, Philox call, column).  K >= 2 only: at K = 1 the step is HBM-bound and
-        // regenerating is the cheaper side of the trade (BB_NO_EPS_STORE: always regenerate)
-        eps_store_.release();
-        if (g.step_w == 2 && !getenv("BB_NO_EPS_STORE")) {
-            const size_t nclass = (size_t)g.nt + 2 * L.E;
-            eps_store_.alloc((size_t)L.K * ((nclass + 7) / 8) * L.cpad, false);
-        }
+
         // persistent mode: default on for multi-GPU shards (the small-shard / strong-scaling path); BB_PERSIST overrides
         int coop = 0;
         BB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
@@ -935,7 +925,6 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
             sk.stage_ring = (trunc && g.step_stage_ring) ? 1 : 0;
             sk.l2_ring = (trunc && !g.step_stage_ring) ? 1 : 0;
             sk.nbuf = g.step_nbuf; sk.stage_acc = g.step_stage_acc;
-            sk.eps_buf = eps_store_.p; sk.eps_valid = m.have_xpart ? 1 : 0;     // the launch that left xpart_ left the draws too
             sk.acc_rows = g.step_acc_rows; sk.tail_scratch = (int)sh_scratch_.n;
             sk.abort = (xchg_on_ && L.world > 1) ? xchg_err_.p : nullptr;
             sk.xpart = xpart_.p;

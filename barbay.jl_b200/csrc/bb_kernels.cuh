@@ -311,8 +311,6 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
     const size_t acc_bytes = (((size_t)a.acc_slots * BLOCK * sizeof(real)) + 15) / 16 * 16;
     r2 *stage = reinterpret_cast<r2 *>(smem_raw + acc_bytes);          // [2][nt + nj][BLOCK]
     const int stage_stride = (C.tmax + C.nj) * BLOCK;
-    // hierarchical models: z of the column's hyper latents for all K samples, [K][E][BLOCK] behind the staging buffers
-    real *hzs = reinterpret_cast<real *>(stage + (size_t)a.nbuf * stage_stride) + tid;
 
     auto prefetch = [&](int tile, int buf) {
         const int i = tile * BLOCK + tid;
@@ -375,31 +373,28 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
             }
             const int nclass = seg.neutral ? nt : nt + nj;
 
-            // hierarchical models: the hyper latents' draws of ALL samples of the chunk are fetched here, every load in
-            // flight at once, into a thread-private strip of shared memory (one dependent L2 round trip per sample on
-            // the critical path of every warp otherwise: the long-scoreboard stall of the round-1 profile)
-            if constexpr (HIER) {
-                if (!seg.neutral) {
-                    for (int k = kc0; k < kc1; ++k) {
-#pragma unroll
-                        for (int e = 0; e < S::MAXE; ++e) {
-                            if (e >= ne) break;
-                            hzs[((k - kc0) * ne + e) * BLOCK] = __ldg(&a.hy_zeps[(size_t)k * a.H + hbase + e]).x;
-                        }
-                    }
-                }
-            }
-#pragma unroll kP1Unroll
-            for (int k = kc0; k < kc1; ++k) {
-                real zth[S::MAXE];
+            // hierarchical models: the hyper latent's draw of sample k + 1 is loaded while sample k is computed
+            // (an L2 round trip per sample otherwise sits on the critical path of every warp)
+            real zth_nxt[S::MAXE];
+            auto load_zth = [&](int k) {
                 if constexpr (HIER) {
                     if (!seg.neutral) {
 #pragma unroll
                         for (int e = 0; e < S::MAXE; ++e) {
                             if (e >= ne) break;
-                            zth[e] = hzs[((k - kc0) * ne + e) * BLOCK];
+                            zth_nxt[e] = a.hy_zeps[(size_t)k * a.H + hbase + e].x;
                         }
                     }
+                }
+            };
+            load_zth(kc0);
+#pragma unroll kP1Unroll
+            for (int k = kc0; k < kc1; ++k) {
+                real zth[S::MAXE];
+                if constexpr (HIER) {
+#pragma unroll
+                    for (int e = 0; e < S::MAXE; ++e) zth[e] = zth_nxt[e];
+                    if (k + 1 < kc1) load_zth(k + 1);
                 }
                 real eps[S::MAXC];
                 column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, strig,
@@ -650,8 +645,6 @@ pass2_kernel(const P2Args<real> a) {
     constexpr bool PAIRS = AccLayout<NT, NE>::PAIRS;
     const int pva = AccLayout<NT, NE>::rows(pvs);
     real *facc = reinterpret_cast<real *>(epi0 + (size_t)(nac + nrg) * th_bytes);
-    // hierarchical models (never fused): (z, eps) of the column's hyper latents for all K samples, [K][E][BLOCK]
-    r2 *hzs = reinterpret_cast<r2 *>(facc) + tid;
     if constexpr (FUSE)
         for (int i = tid; i < a.acc_slots * BLOCK; i += BLOCK) facc[i] = real(0);
 
@@ -817,14 +810,6 @@ pass2_kernel(const P2Args<real> a) {
                 hbase = C.hgroup[c];
 #pragma unroll
                 for (int e = 0; e < S::MAXE; ++e) { hc[e] = real(0); hce[e] = real(0); }
-                // every (sample, environment) draw of the column's hyper latents: all loads in flight together
-                for (int k = 0; k < a.K; ++k) {
-#pragma unroll
-                    for (int e = 0; e < S::MAXE; ++e) {
-                        if (e >= ne) break;
-                        hzs[(k * ne + e) * BLOCK] = __ldg(&a.hy_zeps[(size_t)k * a.H + hbase + e]);
-                    }
-                }
             }
         }
         const int nclass = seg.neutral ? nt : nt + nj;
@@ -832,19 +817,27 @@ pass2_kernel(const P2Args<real> a) {
         // the K samples; instantiated twice so the common vector-prior case carries no per-latent prior loads
         auto sample_loop = [&](auto matpr_tag) {
         constexpr bool MATPR = decltype(matpr_tag)::value;
-        // hierarchical models: (z, eps) of the column's hyper latents for all K samples were fetched at the top of the
-        // tile into the thread's shared-memory strip (see below)
-#pragma unroll(FUSE ? kFuseUnroll : kP2Unroll)
-        for (int k = 0; k < a.K; ++k) {
-            r2 hz_cur[S::MAXE];
+        // hierarchical models: (z, eps) of the hyper latent for sample k + 1 is loaded while sample k is computed
+        r2 hz_nxt[S::MAXE];
+        auto load_hz = [&](int k) {
             if constexpr (HIER) {
                 if (!seg.neutral) {
 #pragma unroll
                     for (int e = 0; e < S::MAXE; ++e) {
                         if (e >= ne) break;
-                        hz_cur[e] = hzs[(k * ne + e) * BLOCK];
+                        hz_nxt[e] = a.hy_zeps[(size_t)k * a.H + hbase + e];
                     }
                 }
+            }
+        };
+        load_hz(0);
+#pragma unroll(FUSE ? kFuseUnroll : kP2Unroll)
+        for (int k = 0; k < a.K; ++k) {
+            r2 hz_cur[S::MAXE];
+            if constexpr (HIER) {
+#pragma unroll
+                for (int e = 0; e < S::MAXE; ++e) hz_cur[e] = hz_nxt[e];
+                if (k + 1 < a.K) load_hz(k + 1);
             }
             real eps[S::MAXC];
             column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, strig, a.sup,

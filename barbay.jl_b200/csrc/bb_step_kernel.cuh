@@ -95,8 +95,6 @@ template <typename real> struct StepArgs {
     const real *ctx;               // [K][3][tmax] context of step `step` (written by tail_kernel)
     OptArgsT<real> opt;
     int stage_pr, stage_ring, l2_ring;
-    uint4 *eps_buf;                // stored draws [K / W][MAXC / 8][W][cpad] (see column_noise_pack), or nullptr: regenerate
-    int eps_valid;                 // 1: eps_buf holds the draws of step `step` (written by the previous launch)
     int nbuf;                      // 2: the next tile is prefetched while this one is computed; 1: single staging buffer
     int stage_acc;                 // 1: accumulators (and the ring slot) are staged for the epilogue; 0: read from global (L2-prefetched)
     int acc_rows;                  // budget of the pass-1 accumulators: rows of BLOCK x (2 slots x W samples)
@@ -128,27 +126,20 @@ __device__ __forceinline__ void slot_to_out(bool neutral, int v, int &q, int &t,
 }
 
 // ---------------------------------------------------------------- noise for a pack of samples
-// The lattice's normals are binary16 values (bb_device.cuh).  `store` (nullable, already offset to the column, row
-// stride `cpad` uint4): the draws are written as half2 (sample k, sample k + 1) per latent -- W uint4 per Philox call
-// and column -- so the pass over the column in the NEXT launch / step reads 16 bytes per sample instead of running
-// Philox + Box-Muller again (column_noise_load).
-template <typename real> __device__ __forceinline__ real h2r(__half h) { return (real)__half2float(h); }
-
+// Both passes over a column regenerate its draws from the lattice.  Storing them between the passes was built and
+// measured in round 2 (binary16 draws, 16 B per column and sample): 167 us against 142 us for regenerating -- the
+// second pass then waits on its own loads -- see DESIGN.md section 5.
 template <typename real, int W, int MAXC>
 __device__ __forceinline__ void column_noise_pack(Pack<real, W> (&eps)[MAXC], int nclass, uint32_t colid, uint32_t k0,
-                                                  uint32_t step, const PhiloxKey &key, const float2 *tab, uint4 *store,
-                                                  size_t cpad) {
+                                                  uint32_t step, const PhiloxKey &key, const float2 *tab) {
 #pragma unroll
     for (int q = 0; q < MAXC / 8; ++q) {
         if (q * 8 >= nclass) break;
-        __half2 hp[4 * W];              // W == 2: hp[l] = (sample k, sample k + 1) of lane l; W == 1: hp[l] = lanes (2l, 2l + 1)
         if constexpr (W == 1) {
             real n[8];
             normals8<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k0, step, key, tab, n);
 #pragma unroll
             for (int l = 0; l < 8; ++l) eps[8 * q + l].v = n[l];
-#pragma unroll
-            for (int l = 0; l < 4; ++l) hp[l] = __floats2half2_rn((float)n[2 * l], (float)n[2 * l + 1]);
         } else if constexpr (std::is_same<real, float>::value) {
             uint32_t xa[4], xb[4];
             philox4x32(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k0, step, key, xa);
@@ -163,49 +154,15 @@ __device__ __forceinline__ void column_noise_pack(Pack<real, W> (&eps)[MAXC], in
                 const float sa = __uint_as_float(__float_as_uint(ra) | ((xa[w] << 21) & 0x80000000u));
                 const float sb = __uint_as_float(__float_as_uint(rb) | ((xb[w] << 21) & 0x80000000u));
                 const float2 da = tab[xa[w] & (TRIG_N - 1)], db = tab[xb[w] & (TRIG_N - 1)];
-                hp[2 * w] = __floats2half2_rn(sa * da.x, sb * db.x);          // the binary16 rounding of the lattice
-                hp[2 * w + 1] = __floats2half2_rn(sa * da.y, sb * db.y);
-                eps[8 * q + 2 * w].v = __half22float2(hp[2 * w]);
-                eps[8 * q + 2 * w + 1].v = __half22float2(hp[2 * w + 1]);
+                eps[8 * q + 2 * w] = pk_make(sa * da.x, sb * db.x);
+                eps[8 * q + 2 * w + 1] = pk_make(sa * da.y, sb * db.y);
             }
         } else {
             real na[8], nb[8];
             normals8<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k0, step, key, tab, na);
             normals8<real>(colid, (STREAM_COLUMN << 24) | (uint32_t)q, k0 + 1u, step, key, tab, nb);
 #pragma unroll
-            for (int l = 0; l < 8; ++l) {
-                eps[8 * q + l] = pk_make(na[l], nb[l]);
-                hp[l] = __floats2half2_rn((float)na[l], (float)nb[l]);         // exact: the values are binary16 already
-            }
-        }
-        if (store) {
-#pragma unroll
-            for (int h = 0; h < W; ++h) {
-                uint4 v;
-                v.x = *reinterpret_cast<const uint32_t *>(&hp[4 * h]); v.y = *reinterpret_cast<const uint32_t *>(&hp[4 * h + 1]);
-                v.z = *reinterpret_cast<const uint32_t *>(&hp[4 * h + 2]); v.w = *reinterpret_cast<const uint32_t *>(&hp[4 * h + 3]);
-                __stcs(&store[(size_t)(q * W + h) * cpad], v);       // read once, by the next launch / step: streaming
-            }
-        }
-    }
-}
-
-// the draws stored by column_noise_pack: `raw` holds the W uint4 of every Philox call of the pack
-template <typename real, int W, int MAXC>
-__device__ __forceinline__ void column_noise_unpack(Pack<real, W> (&eps)[MAXC], int nclass, const uint4 *raw) {
-#pragma unroll
-    for (int q = 0; q < MAXC / 8; ++q) {
-        if (q * 8 >= nclass) break;
-#pragma unroll
-        for (int h = 0; h < W; ++h) {
-            const uint4 v = raw[q * W + h];
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const __half2 hh = *reinterpret_cast<const __half2 *>(&w4[j]);
-                if constexpr (W == 2) eps[8 * q + 4 * h + j] = pk_make(h2r<real>(__low2half(hh)), h2r<real>(__high2half(hh)));
-                else { eps[8 * q + 2 * j].v = h2r<real>(__low2half(hh)); eps[8 * q + 2 * j + 1].v = h2r<real>(__high2half(hh)); }
-            }
+            for (int l = 0; l < 8; ++l) eps[8 * q + l] = pk_make(na[l], nb[l]);
         }
     }
 }
@@ -593,27 +550,9 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
 
                 // ---- the K samples, W at a time
 #pragma unroll kStepUnroll2
-                constexpr int NQ8 = S::MAXC / 8, NRAW = NQ8 * W;        // uint4 per (pack, column) of the stored draws
-                const bool eps_stored = a.eps_buf != nullptr && (si > 0 || a.eps_valid);
-                const uint4 *eload = a.eps_buf + c;
-                uint4 raw_nxt[NRAW];
-                auto load_raw = [&](int kp) {
-#pragma unroll
-                    for (int r = 0; r < NRAW; ++r)
-                        if ((r / W) * 8 < nclass) raw_nxt[r] = __ldcs(eload + (size_t)(kp * NRAW + r) * cpad);
-                };
-                if (eps_stored) load_raw(0);
                 for (int kp = 0; kp < npack; ++kp) {
                     P eps[S::MAXC];
-                    if (eps_stored) {
-                        uint4 raw[NRAW];
-#pragma unroll
-                        for (int r = 0; r < NRAW; ++r) raw[r] = raw_nxt[r];
-                        if (kp + 1 < npack) load_raw(kp + 1);         // the next pack's draws are in flight during this one
-                        column_noise_unpack<real, W, S::MAXC>(eps, nclass, raw);
-                    } else {
-                        column_noise_pack<real, W, S::MAXC>(eps, nclass, colid, (uint32_t)(kp * W), step, a.key, strig, nullptr, 0);
-                    }
+                    column_noise_pack<real, W, S::MAXC>(eps, nclass, colid, (uint32_t)(kp * W), step, a.key, strig);
                     const P *crow = sctx + (size_t)kp * CSP;       // {c_t - sbar_t | G_t | wbar_t}
                     P z[NT], g[NT];
 #pragma unroll
@@ -695,8 +634,7 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
 #pragma unroll kStepUnroll1
                     for (int kp = 0; kp < npack; ++kp) {
                         P eps[S::MAXC];
-                        column_noise_pack<real, W, S::MAXC>(eps, nclass, colid, (uint32_t)(kp * W), step + 1u, a.key, strig,
-                                                            a.eps_buf ? a.eps_buf + (size_t)kp * NRAW * cpad + c : nullptr, (size_t)cpad);
+                        column_noise_pack<real, W, S::MAXC>(eps, nclass, colid, (uint32_t)(kp * W), step + 1u, a.key, strig);
                         pass1_pack<real, NT, NE, W>(eps, mu, sg, mub, sgb, false, a.env_of_t, facc + (size_t)kp * nqp * BLOCK + tid);
                     }
                 }
@@ -737,9 +675,7 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
 #pragma unroll 1
                     for (int kp = kc0; kp < kc1; ++kp) {
                         P eps[S::MAXC];
-                        column_noise_pack<real, W, S::MAXC>(eps, NT, colid, (uint32_t)(kp * W), step + 1u, a.key, strig,
-                                                            a.eps_buf ? a.eps_buf + (size_t)kp * (S::MAXC / 8 * W) * cpad + c : nullptr,
-                                                            (size_t)cpad);
+                        column_noise_pack<real, W, S::MAXC>(eps, NT, colid, (uint32_t)(kp * W), step + 1u, a.key, strig);
                         pass1_pack<real, NT, NE, W>(eps, mu, sg, mu, sg, true, a.env_of_t, facc + (size_t)(kp - kc0) * nqp * BLOCK + tid);
                     }
                 }

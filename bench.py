@@ -481,6 +481,37 @@ def run_ours(args, emit):
                             "steps": n_s, "what": "per step: pinned-host -> device copy of the count matrix + bb_step "
                             "(with ELBO terms) + ELBO read-back"}
 
+    # ---- second end-to-end figure, from the TIDY DataFrame (what BarBay.vi.advi is handed): data_to_arrays (packing,
+    # src/utils.jl:996-1033) + the fit + advi_to_df (src/utils.jl:1409-1462), each timed
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            tidy = bb.synth.to_tidy_fast(da)
+            t0 = time.perf_counter()
+            da_p = bb.utils.data_to_arrays(tidy)
+            t_pack = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            eng3 = bb.Engine(da_p, model, n_samples=K, dtype=args.dtype, seed=SEED, device=cx.local_rank)
+            eng3.init_params(1)
+            eng3.set_optimizer(args.opt)
+            n_df = min(n_e2e, 2000)
+            eng3.step(n_df)
+            m3, s3 = eng3.get_posterior()
+            t_fit = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            q = bb.utils.MeanFieldPosterior.build(m3, s3, eng3.layout.ranges_out)
+            out_df = bb.utils.advi_to_df(tidy, q, eng3.layout.var_names, output=da_p)
+            t_unpack = time.perf_counter() - t0
+            eng3.close()
+            e2e["from_dataframe"] = {
+                "rows_in": int(len(tidy)), "rows_out": int(len(out_df)), "steps": n_df,
+                "data_to_arrays_s": t_pack, "fit_s": t_fit, "advi_to_df_s": t_unpack,
+                "value": units_step * n_df / (t_pack + t_fit + t_unpack), "unit": UNIT,
+                "what": "tidy DataFrame -> data_to_arrays -> bb_create ... bb_step x steps ... bb_get_posterior -> advi_to_df "
+                        "(posterior DataFrame), host wall clock"}
+            del tidy, out_df
+        except Exception as exc:                                   # reported, never fatal for the headline
+            e2e["from_dataframe"] = {"error": repr(exc)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, cores, sample = cpu_port_rate(da, 15.0, K)

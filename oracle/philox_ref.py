@@ -60,17 +60,12 @@ def word_uniforms(x: np.ndarray):
     return u, v
 
 
-def round_h(a: np.ndarray) -> np.ndarray:
-    """The lattice's normals are IEEE binary16 values (round to nearest even), see DESIGN.md "Noise lattice"."""
-    return np.asarray(a, dtype=np.float64).astype(np.float16).astype(np.float64)
-
-
 def box_muller(x: np.ndarray):
-    """word -> (radius*cos(angle), radius*sin(angle)), each rounded to binary16."""
+    """word -> (radius*cos(angle), radius*sin(angle))."""
     u, v = word_uniforms(x)
     radius = np.sqrt(-2.0 * np.log(u))
     angle = 2.0 * np.pi * v
-    return round_h(radius * np.cos(angle)), round_h(radius * np.sin(angle))
+    return radius * np.cos(angle), radius * np.sin(angle)
 
 
 def normals8(c0, c1, c2, c3, seed: int):

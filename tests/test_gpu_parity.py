@@ -89,15 +89,9 @@ def test_philox_lattice_matches_oracle(bb, model, dtype):
     for step in (0, 5):
         eps = eng.get_noise(step)
         ref = philox_ref.noise(model, prob, K, step, 1234)
-        # every draw is a binary16 value.  fp64 kernels: identical.  fp32 kernels: MUFU lg2 / sqrt and the fp32 direction
-        # table put the unrounded value within 2e-5 of the oracle's, so a draw next to a rounding boundary may land on
-        # the neighbouring binary16 number (one ulp: at most 2^-8 for |eps| in [4, 8)); the rest are identical
-        d = np.abs(eps - ref)
-        if dtype == "f64":
-            assert d.max() <= 1e-12, d.max()
-        else:
-            assert d.max() <= 2.0 ** -8 and np.mean(d == 0) > 0.9, (d.max(), np.mean(d == 0))
-        assert np.array_equal(eps.astype(np.float16).astype(np.float64), eps)
+        # fp32: MUFU lg2/sin/cos in the kernel's Box-Muller -> absolute tolerance on N(0,1) draws
+        atol = 1e-12 if dtype == "f64" else 2e-5
+        assert np.max(np.abs(eps - ref)) <= atol, np.max(np.abs(eps - ref))
     eng.close()
 
 

@@ -40,8 +40,7 @@ def test_lattice_distribution_ks_tails_and_independence():
         p = special.erfc(thr / np.sqrt(2.0))
         got = np.mean(np.abs(x) > thr)
         assert abs(got - p) < 5.0 * np.sqrt(p * (1 - p) / n), (thr, got, p)
-    assert np.abs(x).max() <= np.sqrt(2.0 * np.log(2.0 ** 22)) + 2.0 ** -8
-    assert np.array_equal(x.astype(np.float16).astype(np.float64), x)          # binary16 values
+    assert np.abs(x).max() <= np.sqrt(2.0 * np.log(2.0 ** 22)) + 1e-12
     assert abs(x.mean()) < 5 / np.sqrt(n) and abs(x.var() - 1) < 5 * np.sqrt(2.0 / n) and abs((x ** 4).mean() - 3) < 0.02
     c = np.corrcoef(n8.T)                                # the eight lanes of one counter
     assert np.abs(c - np.eye(8)).max() < 5 / np.sqrt(ncol)
