@@ -114,7 +114,7 @@ class EngineBase {
     virtual void comm_init(const char id[128]) = 0;
     // persistent step kernel: cycles of CTA 0 in {column phase, arrive -> sums, sums -> context} and the number of
     // in-kernel tails, summed since the last call (then reset); out[4] = SM clock in kHz
-    virtual void persist_stats(double out[8]) = 0;
+    virtual void persist_stats(double out[10]) = 0;
     // out = {packed step kernel in use, steps per persistent launch (0: off), peer-memory exchange on, NCCL communicator present}
     virtual void data_plane(int32_t out[8]) = 0;
     // one-process-per-GPU wiring without NCCL: every rank exports the CUDA IPC handle of its exchange buffer, the
@@ -158,7 +158,7 @@ template <typename real> class Engine : public EngineBase {
     void sync() override { BB_CUDA(cudaStreamSynchronize(stream_)); }
     void time_steps(int n, float *ms_total, float *ms_pass1, float *ms_pass2) override;
     void comm_init(const char id[128]) override;
-    void persist_stats(double out[8]) override;
+    void persist_stats(double out[10]) override;
     void derived_fitness(int n, uint64_t seed, double *median, double *sd) override;
     void peer_handle(char out[64]) override;
     void peer_attach(const char *handles, int n) override;
@@ -549,7 +549,9 @@ template <typename real> void Engine<real>::size_pass2() {
                 if (g.stepk)
                     BB_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.step_smem));
                 if (g.stepk) {
-                    assign_blocks(g.stsegs, g.nt, nsm_ * g.step_occ, &g.stblocks);
+                    // BB_STEPK_CTAS (tuning): use fewer resident CTAs per SM than fit
+                    const int use_occ = getenv("BB_STEPK_CTAS") ? std::max(1, std::min(g.step_occ, atoi(getenv("BB_STEPK_CTAS")))) : g.step_occ;
+                    assign_blocks(g.stsegs, g.nt, nsm_ * use_occ, &g.stblocks);
                     // scratch of the in-kernel tail (totals + shared_body's working arrays) aliases the accumulators
                     const size_t tail_d = sums_.n + (size_t)L.K * (2 * g.nt + 7 * (g.nt - 1)) + 16;   // totals + working arrays
                     g.step_persist = tail_d * sizeof(double) <= (size_t)rows * BLOCK * spb && (int)sums_.n <= 4096 &&
@@ -1448,8 +1450,8 @@ template <typename real> void Engine<real>::derived_fitness(int n, uint64_t seed
     BB_CUDA(cudaGetLastError());
 }
 
-template <typename real> void Engine<real>::persist_stats(double out[8]) {
-    for (int i = 0; i < 8; ++i) out[i] = 0.0;
+template <typename real> void Engine<real>::persist_stats(double out[10]) {
+    for (int i = 0; i < 10; ++i) out[i] = 0.0;
     if (!step_sync_.p) return;
     StepSync h;
     BB_CUDA(cudaMemcpy(&h, step_sync_.p, sizeof(StepSync), cudaMemcpyDeviceToHost));
@@ -1458,6 +1460,8 @@ template <typename real> void Engine<real>::persist_stats(double out[8]) {
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_);
     out[4] = (double)khz;
     out[5] = (double)h.stat[4]; out[6] = (double)h.stat[5];      // inside "sums -> context": completing the sums, shared-latent phases
+    out[7] = (double)h.stat[6];                                  // the last-arriving CTA: group sum -> rank sum -> posted to the peers
+    out[8] = (double)h.stat[7];                                  // ... and its column phase (the longest of the grid)
     BB_CUDA(cudaMemset(reinterpret_cast<char *>(step_sync_.p) + offsetof(StepSync, stat), 0, sizeof(h.stat)));
 }
 

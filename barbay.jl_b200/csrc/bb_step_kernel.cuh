@@ -74,6 +74,24 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// fixed-order sums of `n` doubles `stride` apart, two outputs at a time: the loads of a batch (2 x 8) are in flight
+// together -- one L2 round trip per batch instead of one per element -- and the additions keep the element order, so
+// the result does not depend on the batching
+__device__ __forceinline__ void ordered_sum2_cg(const double *p0, const double *p1, int n, size_t stride, double &s0, double &s1) {
+    s0 = 0.0; s1 = 0.0;
+    for (int i = 0; i < n; i += 8) {
+        double v0[8], v1[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const size_t o = (size_t)min(i + u, n - 1) * stride;
+            v0[u] = __ldcg(p0 + o); v1[u] = __ldcg(p1 + o);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (i + u < n) { s0 += v0[u]; s1 += v1[u]; }
+    }
+}
+
 // ---------------------------------------------------------------- arguments
 struct StepSync {                  // global control block of the persistent mode (zeroed once, tickets are monotone)
     unsigned group_ticket[64];
@@ -707,10 +725,13 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
         if (s_flag) {                    // last CTA of the group: sum the group's partials, fixed order
             __threadfence();
             const double *src = a.xpart + (size_t)grp * a.gsize * a.P;
-            for (int j = tid; j < a.P; j += BLOCK) {
-                double s = 0.0;
-                for (int b = 0; b < gsz; ++b) s += __ldcg(src + (size_t)b * a.P + j);
-                a.gpart[(size_t)grp * a.P + j] = s;
+            const long long tr0 = clock64();
+            for (int j = tid; j < a.P; j += 2 * BLOCK) {       // two outputs per thread
+                const int j2 = min(j + BLOCK, a.P - 1);
+                double s0, s1;
+                ordered_sum2_cg(src + j, src + j2, gsz, (size_t)a.P, s0, s1);
+                a.gpart[(size_t)grp * a.P + j] = s0;
+                if (j + BLOCK < a.P) a.gpart[(size_t)grp * a.P + j + BLOCK] = s1;
             }
             __threadfence();
             __syncthreads();
@@ -721,14 +742,23 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
             __syncthreads();
             if (s_flag == 2) {           // last group: the rank's sums go to every peer (world == 1: to the local buffer)
                 __threadfence();
-                for (int j = tid; j < a.P; j += BLOCK) {
-                    double s = 0.0;
-                    for (int g = 0; g < a.ngroups; ++g) s += __ldcg(a.gpart + (size_t)g * a.P + j);
-                    for (int r = 0; r < world; ++r) a.xp.peer_buf[r][xchg_off(a.P, parity * world + a.xp.rank, j)] = s;
+                for (int j = tid; j < a.P; j += 2 * BLOCK) {
+                    const int j2 = min(j + BLOCK, a.P - 1);
+                    double s0, s1;
+                    ordered_sum2_cg(a.gpart + j, a.gpart + j2, a.ngroups, (size_t)a.P, s0, s1);
+                    const size_t o0 = xchg_off(a.P, parity * world + a.xp.rank, j), o1 = xchg_off(a.P, parity * world + a.xp.rank, j2);
+                    for (int r = 0; r < world; ++r) {
+                        a.xp.peer_buf[r][o0] = s0;
+                        if (j + BLOCK < a.P) a.xp.peer_buf[r][o1] = s1;
+                    }
                 }
                 __threadfence_system();
                 __syncthreads();
                 if (tid < world) st_release_sys(a.xp.peer_flag[tid] + (parity * world + a.xp.rank), seq);
+                if (tid == 0) {          // the last-arriving CTA of the grid: its reduction chain and its column phase
+                    atomicAdd(&a.sync->stat[6], (unsigned long long)(clock64() - tr0));
+                    atomicAdd(&a.sync->stat[7], (unsigned long long)(tc1 - tc0));
+                }
             }
         }
         // fetched while the sums are on their way: priors and the evicted ring slot of population latent `tid`, the noise
@@ -770,10 +800,23 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
         real *w_u = w_g + a.K * N2;                              // [K][n] sum_all w res
         real *s_z = w_u + a.K * (NT - 1), *s_eps = s_z + a.K * N2;   // [K][2n] this tail's draws, from their owners' registers
         if (tid < a.K * N2) { s_z[tid] = my_z; s_eps[tid] = my_eps; }
-        for (int j = tid; j < a.P; j += BLOCK) {
-            double s = 0.0;
-            for (int r = 0; r < world; ++r) s += __ldcg(a.xbuf + xchg_off(a.P, parity * world + r, j));
-            tot[j] = s;
+        for (int j = tid; j < a.P; j += 2 * BLOCK) {             // all ranks' sums, rank order; both outputs' loads in flight together
+            const int j2 = min(j + BLOCK, a.P - 1);
+            double s0 = 0.0, s1 = 0.0;
+            for (int r0 = 0; r0 < world; r0 += 8) {
+                double v0[8], v1[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int r = min(r0 + u, world - 1);
+                    v0[u] = __ldcg(a.xbuf + xchg_off(a.P, parity * world + r, j));
+                    v1[u] = __ldcg(a.xbuf + xchg_off(a.P, parity * world + r, j2));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (r0 + u < world) { s0 += v0[u]; s1 += v1[u]; }
+            }
+            tot[j] = s0;
+            if (j + BLOCK < a.P) tot[j + BLOCK] = s1;
         }
         __syncthreads();
         const long long tca = clock64();

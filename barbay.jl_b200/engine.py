@@ -295,14 +295,15 @@ class Engine:
     def persist_stats(self) -> dict:
         """Per-step breakdown of the persistent step kernel since the last call (microseconds, CTA 0's clock):
         column phase, arrival -> all ranks' sums (grid reduction + NVLink exchange), sums -> next context."""
-        out = np.zeros(8)
+        out = np.zeros(10)
         self._check(self._lib.bb_persist_stats(self._h, _c_doubles(out)))
         n, khz = out[3], out[4]
         if n <= 0 or khz <= 0:
             return {"tails": 0}
         us = lambda cyc: cyc / n / khz * 1e3
         return {"tails": int(n), "column_us": us(out[0]), "exchange_us": us(out[1]), "context_us": us(out[2]),
-                "context_sums_us": us(out[5]), "context_shared_us": us(out[6])}
+                "context_sums_us": us(out[5]), "context_shared_us": us(out[6]), "reduce_post_us": us(out[7]),
+                "column_last_us": us(out[8])}
 
     def peer_handle(self) -> bytes:
         """CUDA IPC handle of this rank's exchange buffer (64 bytes): gather them in rank order, then ``peer_attach``."""

@@ -166,8 +166,10 @@ int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_pass
  * CTA of the mutant population spent in {column phase, arrival -> all ranks' sums (grid reduction + NVLink exchange),
  * sums -> next step's context}, summed over the in-kernel tails since the last call; out[3] = number of such
  * tails, out[4] = SM clock in kHz, out[5..6] = the last phase split into {completing the sums, shared-latent
- * phases}.  Resets the counters. */
-int bb_persist_stats(bb_handle *h, double out[8]);
+ * phases}, out[7] = cycles the last-arriving CTA needed from the group sum to the flags posted to the peers,
+ * out[8] = that CTA's column phase (the longest of the grid; minus out[0] = the tile-count imbalance), out[9] = 0.
+ * Resets the counters. */
+int bb_persist_stats(bb_handle *h, double out[10]);
 
 /* Derived `bc_fitness` rows of the hierarchical models: utils.advi_to_df -> process_hierarchical_samples!
  * (src/utils.jl:1284-1343) draws n_samples (default 10 000) of theta + exp(log-tau) * theta-tilde per

@@ -4,11 +4,11 @@ import numpy as np, torch
 import barbay_b200 as bb
 K = int(os.environ.get("QK", "8"))
 cfg = int(os.environ.get("QCFG", "2"))
-model, da, _ = bb.synth.config(cfg)
+model, da, _ = bb.synth.config(cfg, scale=float(os.environ.get('QSCALE', '1.0')))
 eng = bb.Engine(da, model, n_samples=K, dtype=os.environ.get("QDT", "f32"), seed=1, device=0)
 eng.init_params(1); eng.set_optimizer(os.environ.get("QOPT", "decayed"))
 eng.step(20); eng.sync()
-n = 200
+n = int(os.environ.get("QN", "200"))
 s = torch.cuda.Stream(); eng.set_stream(s.cuda_stream)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 eng.step(5); torch.cuda.synchronize()
