@@ -47,6 +47,7 @@ class bb_desc(C.Structure):
         ("logsig_bc_prior", bb_prior), ("loglam_prior", bb_prior), ("logtau_prior", bb_prior),
         ("ragged_as_written", C.c_int32), ("n_samples", C.c_int32), ("seed", C.c_uint64),
         ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("n_devices", C.c_int32),
+        ("env_per_rep", C.c_int32),
     ]
 
 

@@ -203,7 +203,7 @@ int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_pass
         e.time_steps(n_steps, ms_total, ms_pass1, ms_pass2);
     });
 }
-int bb_persist_stats(bb_handle *h, double out[10]) {
+int bb_persist_stats(bb_handle *h, double out[16]) {
     return guarded(h, [&](bb::EngineBase &e) {
         if (!out) throw std::runtime_error("bb_persist_stats: NULL argument");
         e.persist_stats(out);

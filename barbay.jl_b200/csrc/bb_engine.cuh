@@ -114,7 +114,7 @@ class EngineBase {
     virtual void comm_init(const char id[128]) = 0;
     // persistent step kernel: cycles of CTA 0 in {column phase, arrive -> sums, sums -> context} and the number of
     // in-kernel tails, summed since the last call (then reset); out[4] = SM clock in kHz
-    virtual void persist_stats(double out[10]) = 0;
+    virtual void persist_stats(double out[16]) = 0;
     // out = {packed step kernel in use, steps per persistent launch (0: off), peer-memory exchange on, NCCL communicator present}
     virtual void data_plane(int32_t out[8]) = 0;
     // one-process-per-GPU wiring without NCCL: every rank exports the CUDA IPC handle of its exchange buffer, the
@@ -158,7 +158,7 @@ template <typename real> class Engine : public EngineBase {
     void sync() override { BB_CUDA(cudaStreamSynchronize(stream_)); }
     void time_steps(int n, float *ms_total, float *ms_pass1, float *ms_pass2) override;
     void comm_init(const char id[128]) override;
-    void persist_stats(double out[10]) override;
+    void persist_stats(double out[16]) override;
     void derived_fitness(int n, uint64_t seed, double *median, double *sd) override;
     void peer_handle(char out[64]) override;
     void peer_attach(const char *handles, int n) override;
@@ -179,9 +179,10 @@ template <typename real> class Engine : public EngineBase {
     void alloc_exchange() { alloc_xchg(); }
 
   private:
-    struct Group {                 // replicates sharing one T: one launch of each column kernel
+    struct Group {                 // replicates sharing one T (and one environment list): one launch of each column kernel
         int nt = 0;
         unsigned rep_mask = 0;
+        int env_of_t[MAX_NT_DYN] = {};
         SegList p1segs, p2segs;
         int p1blocks = 0, p2blocks = 0;
         KernelSet<real> ks, ks_sup;
@@ -216,7 +217,7 @@ template <typename real> class Engine : public EngineBase {
 
     void build_groups();
     void size_pass2();
-    void assign_blocks(SegList &sl, int nt, int budget, int *nblocks);
+    void assign_blocks(SegList &sl, unsigned rep_mask, int budget, int *nblocks);
     void run_pipeline(const RunMode &m);
     void upload_supplied(const double *x, int K);
     void ensure_supplied(bool dump);
@@ -380,16 +381,16 @@ template <typename real> Engine<real>::~Engine() {
     if (own_stream_) cudaStreamDestroy(own_stream_);
 }
 
-template <typename real> void Engine<real>::assign_blocks(SegList &sl, int nt, int budget, int *nblocks) {
+template <typename real> void Engine<real>::assign_blocks(SegList &sl, unsigned rep_mask, int budget, int *nblocks) {
     // proportional split of the persistent grid among the segments of this launch
     long long tiles_total = 0;
     std::vector<int> tiles;
     for (const HostSeg &s : L.segs)
-        if (s.nt == nt) { tiles.push_back(cdiv(s.ncol, BLOCK)); tiles_total += tiles.back(); }
+        if ((rep_mask >> s.rep) & 1u) { tiles.push_back(cdiv(s.ncol, BLOCK)); tiles_total += tiles.back(); }
     sl.nseg = 0;
     int blk = 0, idx = 0;
     for (const HostSeg &s : L.segs) {
-        if (s.nt != nt) continue;
+        if (!((rep_mask >> s.rep) & 1u)) continue;
         Seg g;
         g.col0 = s.col0; g.ncol = s.ncol; g.rep = s.rep; g.nt = s.nt; g.neutral = s.neutral;
         g.colid0 = s.colid0; g.sh0 = s.sh0;
@@ -404,14 +405,21 @@ template <typename real> void Engine<real>::assign_blocks(SegList &sl, int nt, i
 }
 
 template <typename real> void Engine<real>::build_groups() {
-    std::vector<int> distinct;
-    for (int r = 0; r < L.R; ++r)
-        if (std::find(distinct.begin(), distinct.end(), L.nt[r]) == distinct.end()) distinct.push_back(L.nt[r]);
+    // one launch group per distinct (T_r, environment list of replicate r): the kernels take one env_of_t per launch
+    std::vector<int> lead;         // first replicate of every group
+    auto same = [&](int a, int b) { return L.nt[a] == L.nt[b] && L.env_of_rt[a] == L.env_of_rt[b]; };
+    for (int r = 0; r < L.R; ++r) {
+        bool found = false;
+        for (int l : lead) found = found || same(l, r);
+        if (!found) lead.push_back(r);
+    }
     size_t part_off = 0;
-    for (int nt : distinct) {
+    for (int l : lead) {
         Group g;
+        const int nt = L.nt[l];
         g.nt = nt;
-        for (int r = 0; r < L.R; ++r) if (L.nt[r] == nt) g.rep_mask |= 1u << r;
+        for (int r = 0; r < L.R; ++r) if (same(l, r)) g.rep_mask |= 1u << r;
+        for (int t = 0; t < MAX_NT_DYN; ++t) g.env_of_t[t] = L.env_of_rt[l][t];
         if (!lookup_kernels<real>(nt, L.E, L.hier, false, &g.ks) ||
             !lookup_kernels<real>(nt, L.E, L.hier, true, &g.ks_sup))
             throw std::runtime_error("no kernel instantiation for this shape");
@@ -442,7 +450,7 @@ template <typename real> void Engine<real>::build_groups() {
         BB_CUDA(cudaFuncSetAttribute((const void *)g.ks_sup.pass1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.p1smem));
         int occ1 = 1;
         BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, g.ks.pass1, BLOCK, g.p1smem));
-        assign_blocks(g.p1segs, nt, nsm_ * std::max(occ1, 1), &g.p1blocks);
+        assign_blocks(g.p1segs, g.rep_mask, nsm_ * std::max(occ1, 1), &g.p1blocks);
         g.part_off = part_off;
         part_off += g.p1blocks;
         groups_.push_back(g);
@@ -551,7 +559,7 @@ template <typename real> void Engine<real>::size_pass2() {
                 if (g.stepk) {
                     // BB_STEPK_CTAS (tuning): use fewer resident CTAs per SM than fit
                     const int use_occ = getenv("BB_STEPK_CTAS") ? std::max(1, std::min(g.step_occ, atoi(getenv("BB_STEPK_CTAS")))) : g.step_occ;
-                    assign_blocks(g.stsegs, g.nt, nsm_ * use_occ, &g.stblocks);
+                    assign_blocks(g.stsegs, g.rep_mask, nsm_ * use_occ, &g.stblocks);
                     // scratch of the in-kernel tail (totals + shared_body's working arrays) aliases the accumulators
                     const size_t tail_d = sums_.n + (size_t)L.K * (2 * g.nt + 7 * (g.nt - 1)) + 16;   // totals + working arrays
                     g.step_persist = tail_d * sizeof(double) <= (size_t)rows * BLOCK * spb && (int)sums_.n <= 4096 &&
@@ -568,7 +576,7 @@ template <typename real> void Engine<real>::size_pass2() {
             BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, g.ks.pass2_fused, BLOCK, g.fsmem));
         else
             BB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, g.ks.pass2, BLOCK, g.p2smem));
-        assign_blocks(g.p2segs, g.nt, nsm_ * std::max(occ2, 1), &g.p2blocks);
+        assign_blocks(g.p2segs, g.rep_mask, nsm_ * std::max(occ2, 1), &g.p2blocks);
         g.epart_off = epart_off;
         epart_off += g.p2blocks;
     }
@@ -583,18 +591,18 @@ template <typename real> void Engine<real>::size_pass2() {
         Group &g = groups_[0];
         xpart_.alloc((size_t)g.stblocks * sums_.n);
 
-        // persistent mode: default on for multi-GPU shards (the small-shard / strong-scaling path); BB_PERSIST overrides
         int coop = 0;
         BB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
-        // default: on for the shards of a multi-GPU run (tens of microseconds per step: the launch pair and the tail
-        // kernel are a large share), off on one GPU where the plain launch pair measured ~5 % faster at cfg2
+        // default: on.  For the shards of a multi-GPU run (tens of microseconds per step) the launch pair and the tail
+        // kernel are a large share; on one GPU at cfg2 it measures 147.6 us per step against 149.7 us for the launch pair
+        // (profiles/r2_smallshard.jsonl).  BB_PERSIST=0 selects the launch pair, BB_PERSIST=n the steps per launch.
         const char *pe = getenv("BB_PERSIST");
-        int want = pe ? atoi(pe) : (L.world > 1 ? 256 : 0);
+        int want = pe ? atoi(pe) : 256;
         if (!coop || !g.step_persist) want = 0;
         if (L.world > 1 && !xchg_on_) want = 0;
         if (want > 1) {
             persist_chunk_ = want;
-            step_gsize_ = 32;
+            step_gsize_ = getenv("BB_STEPK_GSIZE") ? std::max(8, atoi(getenv("BB_STEPK_GSIZE"))) : 32;
             while (cdiv(g.stblocks, step_gsize_) > 64) step_gsize_ *= 2;
             gpart_.alloc((size_t)cdiv(g.stblocks, step_gsize_) * sums_.n);
             if (!step_sync_.p) step_sync_.alloc(1);
@@ -821,7 +829,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         if (!m.have_part && !m.have_xpart) {
             P1Args<real> a{};
             a.segs = g.p1segs; a.cols = C; a.K = L.K; a.acc_slots = g.kchunk; a.ne = L.E;
-            for (int t = 0; t < MAX_NT_DYN; ++t) a.env_of_t[t] = L.env_of_t[t];
+            for (int t = 0; t < MAX_NT_DYN; ++t) a.env_of_t[t] = g.env_of_t[t];
             a.key = pkey; a.step = m.step;
             a.hy_zeps = zeps_.p; a.H = L.H;
             a.part = gpart;
@@ -896,7 +904,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
     for (Group &g : groups_) {
         P2Args<real> a{};
         a.segs = g.p2segs; a.cols = C; a.K = L.K; a.ne = L.E;
-        for (int t = 0; t < MAX_NT_DYN; ++t) a.env_of_t[t] = L.env_of_t[t];
+        for (int t = 0; t < MAX_NT_DYN; ++t) a.env_of_t[t] = g.env_of_t[t];
         a.key = pkey; a.step = m.step;
         a.hy_zeps = zeps_.p; a.H = L.H;
         a.ctx = ctx_.p; a.tmax_ctx = L.tmax;
@@ -918,7 +926,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
             // cooperative -- m.nsteps steps with the tails of steps 2.. inside the kernel
             StepArgs<real> sk{};
             sk.segs = g.stsegs; sk.cols = col_arrays(true); sk.K = L.K; sk.P = (int)sums_.n;
-            for (int t = 0; t < MAX_NT_DYN; ++t) sk.env_of_t[t] = L.env_of_t[t];
+            for (int t = 0; t < MAX_NT_DYN; ++t) sk.env_of_t[t] = g.env_of_t[t];
             sk.key = pkey; sk.step = m.step; sk.nsteps = m.nsteps;
             sk.ctx = ctx_.p;
             sk.opt = opt_args<real>(true);
@@ -1450,8 +1458,8 @@ template <typename real> void Engine<real>::derived_fitness(int n, uint64_t seed
     BB_CUDA(cudaGetLastError());
 }
 
-template <typename real> void Engine<real>::persist_stats(double out[10]) {
-    for (int i = 0; i < 10; ++i) out[i] = 0.0;
+template <typename real> void Engine<real>::persist_stats(double out[16]) {
+    for (int i = 0; i < 16; ++i) out[i] = 0.0;
     if (!step_sync_.p) return;
     StepSync h;
     BB_CUDA(cudaMemcpy(&h, step_sync_.p, sizeof(StepSync), cudaMemcpyDeviceToHost));
@@ -1462,6 +1470,7 @@ template <typename real> void Engine<real>::persist_stats(double out[10]) {
     out[5] = (double)h.stat[4]; out[6] = (double)h.stat[5];      // inside "sums -> context": completing the sums, shared-latent phases
     out[7] = (double)h.stat[6];                                  // the last-arriving CTA: group sum -> rank sum -> posted to the peers
     out[8] = (double)h.stat[7];                                  // ... and its column phase (the longest of the grid)
+    for (int i = 0; i < 4; ++i) out[9 + i] = (double)h.stat[8 + i];  // its chain: group sum | tickets + fences | rank sum + peer stores | fence + flags
     BB_CUDA(cudaMemset(reinterpret_cast<char *>(step_sync_.p) + offsetof(StepSync, stat), 0, sizeof(h.stat)));
 }
 

@@ -87,15 +87,23 @@ void build_layout(const bb_desc &d, Layout &L) {
         L.nst += L.nt[r] - 1;
     }
     const bool ragged = *std::min_element(L.nt.begin(), L.nt.end()) != L.tmax;
-    if (ragged && multienv) fail("multienv models with unequal time points per replicate are not supported");
+    if (ragged && multienv && !d.env_per_rep)
+        fail("multienv models with unequal time points per replicate need one environment list per replicate (env_per_rep)");
+    if (d.env_per_rep && d.model != BB_MODEL_MULTIENV_REPLICATE)
+        fail("env_per_rep applies to the multienv x replicate model only");
     if (ragged && d.ragged_as_written)
         fail("the as-written neutral pairing of replicates.jl:599-605 is not implemented; pass corrected=true");
-    L.env_of_t.assign(kMaxNtDyn, 0);
+    L.env_of_rt.assign(L.R, std::vector<int>(kMaxNtDyn, 0));
     if (multienv) {
         if (!d.env_idx) fail("Models with multiple environments require env_idx");
-        for (int t = 0; t < L.tmax; ++t) {
-            if (d.env_idx[t] < 1 || d.env_idx[t] > L.E) fail("env_idx out of range");
-            L.env_of_t[t] = d.env_idx[t] - 1;
+        int off = 0;
+        for (int r = 0; r < L.R; ++r) {
+            const int32_t *idx = d.env_idx + (d.env_per_rep ? off : 0);
+            for (int t = 0; t < L.nt[r]; ++t) {
+                if (idx[t] < 1 || idx[t] > L.E) fail("env_idx out of range");
+                L.env_of_rt[r][t] = idx[t] - 1;
+            }
+            off += L.nt[r];
         }
     }
     std::vector<int> g0;   // 0-based genotype index per reference mutant

@@ -22,7 +22,7 @@ struct Layout {
     std::vector<int> nt;           // [R]
     int tmax = 0, nst = 0;
     std::vector<int> sh0;          // [R] offset of s-bar[r][0] in the s-bar block
-    std::vector<int> env_of_t;     // [tmax] 0-based
+    std::vector<std::vector<int>> env_of_rt;   // [R][kMaxNtDyn] 0-based environment of time point t of replicate r
     int K = 1;
     // shard
     int rank = 0, world = 1;

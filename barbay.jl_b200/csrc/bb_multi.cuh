@@ -148,7 +148,7 @@ template <typename real> class MultiEngine : public EngineBase {
     void peer_handle(char *) override { throw std::runtime_error("a multi-GPU handle wires its devices itself"); }
     void peer_attach(const char *, int) override { throw std::runtime_error("a multi-GPU handle wires its devices itself"); }
     void comm_init(const char *) override {}          // the devices of one handle are already connected
-    void persist_stats(double out[10]) override { run_on(0, [&] { eng_[0]->persist_stats(out); }); }
+    void persist_stats(double out[16]) override { run_on(0, [&] { eng_[0]->persist_stats(out); }); }
     void data_plane(int32_t out[8]) override { eng_[0]->data_plane(out); }
     int n_devices() const { return n_; }
 

@@ -74,20 +74,21 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// fixed-order sums of `n` doubles `stride` apart, two outputs at a time: the loads of a batch (2 x 8) are in flight
-// together -- one L2 round trip per batch instead of one per element -- and the additions keep the element order, so
-// the result does not depend on the batching
+// fixed-order sums of `n` doubles `stride` apart, two outputs at a time: the loads of a batch (2 x B) are in flight
+// together -- one L2 round trip (0.55 us between the last arrival and the next step, r2_tunechain.log) per batch
+// instead of one per element -- and the additions keep the element order, so the result does not depend on the batching
+template <int B>
 __device__ __forceinline__ void ordered_sum2_cg(const double *p0, const double *p1, int n, size_t stride, double &s0, double &s1) {
     s0 = 0.0; s1 = 0.0;
-    for (int i = 0; i < n; i += 8) {
-        double v0[8], v1[8];
+    for (int i = 0; i < n; i += B) {
+        double v0[B], v1[B];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < B; ++u) {
             const size_t o = (size_t)min(i + u, n - 1) * stride;
             v0[u] = __ldcg(p0 + o); v1[u] = __ldcg(p1 + o);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < B; ++u)
             if (i + u < n) { s0 += v0[u]; s1 += v1[u]; }
     }
 }
@@ -99,7 +100,7 @@ struct StepSync {                  // global control block of the persistent mod
     int err;                       // 1: a peer never posted its sums (bounded spin) -- the launch stops stepping
     int steps_done;                // steps completed by the launch that raised err (diagnostic)
     int pad;
-    unsigned long long stat[8];    // CTA 0, summed over the in-kernel tails: cycles {column phase, arrive -> sums, sums -> context}, tails
+    unsigned long long stat[16];   // CTA 0, summed over the in-kernel tails: cycles {column phase, arrive -> sums, sums -> context}, tails
 };
 
 template <typename real> struct StepArgs {
@@ -717,6 +718,10 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
         const long long tc1 = clock64();
         const int grp = blockIdx.x / a.gsize;
         const int gsz = min(a.gsize, (int)gridDim.x - grp * a.gsize);
+        // Measured on the chain of the last-arriving CTA (profiles/r2_tunechain.log, 1/8 of cfg2): group sum 2.2 us with
+        // batches of 8 loads, tickets + fences 1.4, rank sum + stores 1.2, system fence + release stores 2.7 -- the release
+        // stores alone 1.3 (they order the CTA's earlier stores themselves, through the barrier); one fence by thread 0
+        // instead of one per thread: no difference; relaxed polling + one acquire fence: 3 us slower.
         if (tid == 0) {
             const unsigned t = atomicAdd(&a.sync->group_ticket[grp], 1u);
             s_flag = ((t + 1u) % (unsigned)gsz == 0u) ? 1 : 0;
@@ -729,10 +734,11 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
             for (int j = tid; j < a.P; j += 2 * BLOCK) {       // two outputs per thread
                 const int j2 = min(j + BLOCK, a.P - 1);
                 double s0, s1;
-                ordered_sum2_cg(src + j, src + j2, gsz, (size_t)a.P, s0, s1);
+                ordered_sum2_cg<16>(src + j, src + j2, gsz, (size_t)a.P, s0, s1);
                 a.gpart[(size_t)grp * a.P + j] = s0;
                 if (j + BLOCK < a.P) a.gpart[(size_t)grp * a.P + j + BLOCK] = s1;
             }
+            const long long tr1 = clock64();
             __threadfence();
             __syncthreads();
             if (tid == 0) {
@@ -742,22 +748,28 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
             __syncthreads();
             if (s_flag == 2) {           // last group: the rank's sums go to every peer (world == 1: to the local buffer)
                 __threadfence();
+                const long long tr2 = clock64();
                 for (int j = tid; j < a.P; j += 2 * BLOCK) {
                     const int j2 = min(j + BLOCK, a.P - 1);
                     double s0, s1;
-                    ordered_sum2_cg(a.gpart + j, a.gpart + j2, a.ngroups, (size_t)a.P, s0, s1);
+                    ordered_sum2_cg<16>(a.gpart + j, a.gpart + j2, a.ngroups, (size_t)a.P, s0, s1);
                     const size_t o0 = xchg_off(a.P, parity * world + a.xp.rank, j), o1 = xchg_off(a.P, parity * world + a.xp.rank, j2);
                     for (int r = 0; r < world; ++r) {
                         a.xp.peer_buf[r][o0] = s0;
                         if (j + BLOCK < a.P) a.xp.peer_buf[r][o1] = s1;
                     }
                 }
-                __threadfence_system();
-                __syncthreads();
+                const long long tr3 = clock64();
+                __syncthreads();         // the release stores below are cumulative over the CTA's stores above
                 if (tid < world) st_release_sys(a.xp.peer_flag[tid] + (parity * world + a.xp.rank), seq);
                 if (tid == 0) {          // the last-arriving CTA of the grid: its reduction chain and its column phase
-                    atomicAdd(&a.sync->stat[6], (unsigned long long)(clock64() - tr0));
+                    const long long tr4 = clock64();
+                    atomicAdd(&a.sync->stat[6], (unsigned long long)(tr4 - tr0));
                     atomicAdd(&a.sync->stat[7], (unsigned long long)(tc1 - tc0));
+                    atomicAdd(&a.sync->stat[8], (unsigned long long)(tr1 - tr0));      // group sum
+                    atomicAdd(&a.sync->stat[9], (unsigned long long)(tr2 - tr1));      // fence, final ticket, fence
+                    atomicAdd(&a.sync->stat[10], (unsigned long long)(tr3 - tr2));     // rank sum + stores to the peers
+                    atomicAdd(&a.sync->stat[11], (unsigned long long)(tr4 - tr3));     // fence + flags
                 }
             }
         }

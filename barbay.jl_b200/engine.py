@@ -64,12 +64,23 @@ class Engine:
         n_env, n_geno = 1, 0
         if self.model.multienv:
             envs = kw.get("envs", da.envs)
-            if isinstance(envs, str) or (len(envs) and isinstance(envs[0], (list, tuple))):
-                raise BarBayError("Models with multiple environments need one environment list shared by all "
-                                  "replicates")
-            if len(envs) != n_time[0]:
-                raise BarBayError("Number of time points must match list of of environments")   # multienv.jl:146-148
-            uniq, env_idx = _model.indexin_unique(list(envs))
+            if isinstance(envs, str):
+                raise BarBayError("Models with multiple environments need the list of environments (envs)")
+            if len(envs) and isinstance(envs[0], (list, tuple)):
+                # one list per replicate: the Vector{Matrix{Int64}} method (…hierarchical_replicates.jl:449-472)
+                if self.model.name != "multienv_replicate_fitness_normal":
+                    raise BarBayError("one environment list per replicate applies to multienv_replicate_fitness_normal")
+                if len(envs) != n_rep or any(len(es) != t for es, t in zip(envs, n_time)):
+                    raise BarBayError("Number of time points must match list of of environments for all replicates")   # :463-465
+                flat = [e for es in envs for e in es]
+                uniq, env_idx = _model.indexin_unique(flat)          # unique(vcat(envs...)), indexin.(envs, Ref(.)) :468-472
+                desc.env_per_rep = 1
+            else:
+                if len(set(int(t) for t in n_time)) != 1:
+                    raise BarBayError("replicates with unequal numbers of time points need one environment list per replicate")
+                if len(envs) != n_time[0]:
+                    raise BarBayError("Number of time points must match list of of environments")   # multienv.jl:146-148
+                uniq, env_idx = _model.indexin_unique(list(envs))
             n_env = len(uniq)
             env_idx = np.ascontiguousarray(env_idx, dtype=np.int32)
             self._keep.append(env_idx)
@@ -295,7 +306,7 @@ class Engine:
     def persist_stats(self) -> dict:
         """Per-step breakdown of the persistent step kernel since the last call (microseconds, CTA 0's clock):
         column phase, arrival -> all ranks' sums (grid reduction + NVLink exchange), sums -> next context."""
-        out = np.zeros(10)
+        out = np.zeros(16)
         self._check(self._lib.bb_persist_stats(self._h, _c_doubles(out)))
         n, khz = out[3], out[4]
         if n <= 0 or khz <= 0:
@@ -303,7 +314,8 @@ class Engine:
         us = lambda cyc: cyc / n / khz * 1e3
         return {"tails": int(n), "column_us": us(out[0]), "exchange_us": us(out[1]), "context_us": us(out[2]),
                 "context_sums_us": us(out[5]), "context_shared_us": us(out[6]), "reduce_post_us": us(out[7]),
-                "column_last_us": us(out[8])}
+                "column_last_us": us(out[8]),
+                "chain_us": [us(out[9]), us(out[10]), us(out[11]), us(out[12])]}
 
     def peer_handle(self) -> bytes:
         """CUDA IPC handle of this rank's exchange buffer (64 bytes): gather them in rank order, then ``peer_attach``."""

@@ -41,20 +41,28 @@ def _simulate_block(rng, s_cols: np.ndarray, n_time: int, mean_reads: float, noi
 
 def simulate(model: str, n_neutral: int, n_bc: int, n_time: int, *, n_rep: int = 1, envs=None, n_geno: int = 0,
              seed: int = BASE_SEED, mean_reads: float = 100.0) -> tuple[DataArrays, SynthTruth]:
+    """``n_time`` may be a list (one T per replicate: the Vector{Matrix{Int64}} data layout); ``envs`` then is one
+    list per replicate for the multi-environment x replicate model."""
     rng = np.random.Generator(np.random.PCG64(seed))
     B = n_neutral + n_bc
     multienv = "multienv" in model
-    env_idx = np.zeros(n_time, dtype=np.int64)
+    ragged = isinstance(n_time, (list, tuple))
+    n_times = [int(t) for t in n_time] if ragged else [int(n_time)] * n_rep
+    if ragged:
+        n_rep = len(n_times)
+    env_idx_r = [np.zeros(t, dtype=np.int64) for t in n_times]
     n_env = 1
     env_list = "env1"
     if multienv:
-        env_list = list(envs)
+        per_rep = [list(es) for es in envs] if isinstance(envs[0], (list, tuple)) else [list(envs)] * n_rep
         uniq = []
-        for e in env_list:
-            if e not in uniq:
-                uniq.append(e)
-        env_idx = np.asarray([uniq.index(e) for e in env_list])
+        for es in per_rep:
+            for e in es:
+                if e not in uniq:
+                    uniq.append(e)
+        env_idx_r = [np.asarray([uniq.index(e) for e in es]) for es in per_rep]
         n_env = len(uniq)
+        env_list = per_rep if isinstance(envs[0], (list, tuple)) else list(envs)
     theta = None
     genotypes = "N/A"
     if "genotype" in model:
@@ -80,13 +88,17 @@ def simulate(model: str, n_neutral: int, n_bc: int, n_time: int, *, n_rep: int =
             s[e, :, r] = base + dev
     blocks, s_pops = [], []
     for r in range(n_rep):
-        s_cols = np.zeros((n_time - 1, B))
-        for t in range(n_time - 1):
-            s_cols[t, n_neutral:] = s[env_idx[t + 1], :, r]
-        c, sp = _simulate_block(rng, s_cols, n_time, mean_reads)
+        s_cols = np.zeros((n_times[r] - 1, B))
+        for t in range(n_times[r] - 1):
+            s_cols[t, n_neutral:] = s[env_idx_r[r][t + 1], :, r]
+        c, sp = _simulate_block(rng, s_cols, n_times[r], mean_reads)
         blocks.append(c)
         s_pops.append(sp)
-    if n_rep == 1 and "replicate" not in model:
+    if ragged:
+        bc_count = blocks
+        bc_total = [c.sum(axis=1) for c in blocks]
+        nt_field = n_times
+    elif n_rep == 1 and "replicate" not in model:
         bc_count = blocks[0]
         bc_total = bc_count.sum(axis=1)
         nt_field = n_time
@@ -101,7 +113,7 @@ def simulate(model: str, n_neutral: int, n_bc: int, n_time: int, *, n_rep: int =
         neutral_ids=[f"neutral{i + 1:0{width}d}" for i in range(n_neutral)],
         envs=env_list, n_env=n_env, n_rep=n_rep, n_time=nt_field, genotypes=genotypes,
         n_geno=n_geno if "genotype" in model else 0)
-    return da, SynthTruth(s=s, theta=theta, s_pop=np.stack(s_pops, axis=1))
+    return da, SynthTruth(s=s, theta=theta, s_pop=s_pops if ragged else np.stack(s_pops, axis=1))
 
 
 # the BASELINE.json configurations (index = position in BASELINE.json "configs")

@@ -276,12 +276,16 @@ def add_environment_info(df, var_groups, var_range, output: DataArrays, env_col)
         if output.n_env == 1:
             col[s] = "env1"
         elif _model.POP_MARK in name:
-            envs = output.envs if not isinstance(output.envs[0], list) else output.envs[0]
-            tail = list(envs[1:])
+            if isinstance(output.envs[0], list):
+                # one list per replicate (unequal T): every replicate's envs[2:end], replicate after replicate -- the
+                # reference's `output.envs[2:end]` (:1179) does not fit the rows in this case
+                tail = [e for es in output.envs for e in es[1:]]
+            else:
+                tail = list(output.envs[1:])
             n = s.stop - s.start
             col[s] = (tail * (n // max(len(tail), 1)))[:n] if len(tail) != n else tail
         elif name == _model.V_THETA:
-            envs = output.envs if not isinstance(output.envs[0], list) else output.envs[0]
+            envs = output.envs if not isinstance(output.envs[0], list) else [e for es in output.envs for e in es]
             col[s] = np.tile(np.asarray(_unique_list(envs), dtype=object), output.n_bc)
     df[str(env_col)] = col
 

@@ -85,7 +85,10 @@ typedef struct bb_desc {
      * or the R matrices T_r x B of a Vector{Matrix{Int64}} back to back; neutral columns first. */
     const int64_t *bc_count;
     int32_t n_env;                /* E; 1 unless multienv */
-    const int32_t *env_idx;       /* [n_time[0]] 1-based indexin(envs, unique(envs)) (multienv.jl:151-155) or NULL */
+    /* 1-based indexin(envs, unique(envs)) (multienv.jl:151-155) or NULL: [n_time[0]] -- one list shared by all
+     * replicates -- or, with env_per_rep = 1, the replicates' own lists back to back, [sum_r n_time[r]]
+     * (indexin.(envs, Ref(unique(vcat(envs...)))), model_multienv_fitness_normal_hierarchical_replicates.jl:465-472) */
+    const int32_t *env_idx;
     int32_t n_geno;               /* G; 0 unless genotype model */
     const int32_t *geno_idx;      /* [n_bc] 1-based indexin(genotypes, unique(genotypes)) (genotypes.jl:170-174) or NULL */
     bb_prior s_pop_prior, logsig_pop_prior, s_bc_prior, logsig_bc_prior, loglam_prior, logtau_prior;
@@ -99,6 +102,9 @@ typedef struct bb_desc {
      * stays one blocking call, and the per-step exchange runs over NVLink peer memory -- what a single
      * BarBay.vi.advi() call (src/vi.jl:86-101) needs to use a whole box. */
     int32_t n_devices;
+    /* 1: env_idx holds one environment list per replicate (the Vector{Matrix{Int64}} method of the multienv x
+     * replicate model, ...replicates.jl:449-687; required when the replicates have unequal numbers of time points) */
+    int32_t env_per_rep;
 } bb_desc;
 
 /* ---- lifecycle ---- */
@@ -167,9 +173,10 @@ int bb_time_steps(bb_handle *h, int32_t n_steps, float *ms_total, float *ms_pass
  * sums -> next step's context}, summed over the in-kernel tails since the last call; out[3] = number of such
  * tails, out[4] = SM clock in kHz, out[5..6] = the last phase split into {completing the sums, shared-latent
  * phases}, out[7] = cycles the last-arriving CTA needed from the group sum to the flags posted to the peers,
- * out[8] = that CTA's column phase (the longest of the grid; minus out[0] = the tile-count imbalance), out[9] = 0.
+ * out[8] = that CTA's column phase (the longest of the grid; minus out[0] = the tile-count imbalance), out[9..12] =
+ * out[7] split into {group sum, tickets + fences, rank sum + stores to the peers, fence + flags}, out[13..15] = 0.
  * Resets the counters. */
-int bb_persist_stats(bb_handle *h, double out[10]);
+int bb_persist_stats(bb_handle *h, double out[16]);
 
 /* Derived `bc_fitness` rows of the hierarchical models: utils.advi_to_df -> process_hierarchical_samples!
  * (src/utils.jl:1284-1343) draws n_samples (default 10 000) of theta + exp(log-tau) * theta-tilde per

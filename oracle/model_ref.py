@@ -449,6 +449,76 @@ def logjoint_multienv_replicate_fitness_normal(z, R, nt, n_neutral, n_bc, envs, 
 
 
 # --------------------------------------------------------------------------
+# M5v multienv_replicate_fitness_normal, Vector{Matrix{Int64}} method: unequal T
+#     per replicate, one environment list per replicate
+#     (model_multienv_fitness_normal_hierarchical_replicates.jl:449-687)
+# --------------------------------------------------------------------------
+def logjoint_multienv_replicate_fitness_normal_ragged(z, R_list, nt_list, n_neutral, n_bc, envs, priors=None):
+    pr = _pri(priors)
+    Rs = [torch.as_tensor(np.asarray(r), dtype=torch.int64) for r in R_list]
+    nts = [torch.as_tensor(np.asarray(n), dtype=torch.int64) for n in nt_list]
+    n_rep = len(Rs)
+    n_time = [int(r.shape[0]) for r in Rs]
+    if any(n_time[r] != len(envs[r]) for r in range(n_rep)):                             # :463-465
+        raise ValueError("Number of time points must match list of of environments for all replicates")
+    env_unique = []                                                                      # unique(vcat(envs...)) :468
+    for es in envs:
+        for e in es:
+            if e not in env_unique:
+                env_unique.append(e)
+    n_env = len(env_unique)
+    env_idx = [np.asarray([env_unique.index(e) for e in es], dtype=np.int64) for es in envs]   # :472 (0-based here)
+    B = n_neutral + n_bc
+    n_st = sum(t - 1 for t in n_time)
+    n_lam = sum(int(r.numel()) for r in Rs)
+    rep_ranges, time_ranges = [], []                                                     # :478-495
+    a = b = 0
+    for r in range(n_rep):
+        rep_ranges.append((a, a + Rs[r].numel()))
+        a += Rs[r].numel()
+        time_ranges.append((b, b + n_time[r] - 1))
+        b += n_time[r] - 1
+    cur = _Cursor(z)
+    s_t = cur.take("s̲ₜ", n_st)
+    lsig_t = cur.take("logσ̲ₜ", n_st)
+    theta = cur.take("θ̲⁽ᵐ⁾", n_env * n_bc)
+    theta_tilde = cur.take("θ̲̃⁽ᵐ⁾", n_env * n_bc * n_rep)
+    ltau = cur.take("logτ̲⁽ᵐ⁾", n_env * n_bc * n_rep)
+    lsig_m = cur.take("logσ̲⁽ᵐ⁾", n_env * n_bc * n_rep)
+    logLam = cur.take("logΛ̲̲", n_lam)
+    cur.done()
+    lp = _prior(s_t, pr["s_pop_prior"], n_st)
+    lp = lp + _prior(lsig_t, pr["logσ_pop_prior"], n_st)
+    lp = lp + _prior(theta, pr["s_bc_prior"], n_env * n_bc)
+    lp = lp + _prior(theta_tilde, [0.0, 1.0], n_env * n_bc * n_rep)
+    lp = lp + _prior(ltau, pr["logτ_prior"], n_env * n_bc * n_rep)
+    s_m = jl_repeat(theta, outer=n_rep) + torch.exp(ltau) * theta_tilde                  # :557
+    lp = lp + _prior(lsig_m, pr["logσ_bc_prior"], n_env * n_bc * n_rep)
+    lp = lp + _prior(logLam, pr["logλ_prior"], n_lam)
+    Lam = [jl_reshape(torch.exp(logLam)[lo:hi], n_time[r], B) for r, (lo, hi) in enumerate(rep_ranges)]   # :592-595
+    s_m3 = jl_reshape(s_m, n_env, n_bc, n_rep)                                           # :609
+    lsig_m3 = jl_reshape(lsig_m, n_env, n_bc, n_rep)                                     # :610
+    for r in range(n_rep):
+        lp = lp + _count_terms_matrix(Lam[r], Rs[r], nts[r])                             # :615-640
+    for r in range(n_rep):
+        F = Lam[r] / Lam[r].sum(dim=1, keepdim=True)                                     # :598
+        logG = torch.log(F[1:, :] / F[:-1, :])                                           # :601
+        logG_n = jl_vec(logG[:, :n_neutral])                                             # :605
+        logG_m = jl_vec(logG[:, n_neutral:n_neutral + n_bc])                             # :606
+        lo, hi = time_ranges[r]
+        st_r, ls_r = s_t[lo:hi], lsig_t[lo:hi]
+        # neutrals :650-668: repeat(s_t[range], n_neutral) -- outer repeat, pairs ratio (t, n) with s_t[t]
+        lp = lp + mvnormal_diag_logpdf(logG_n, -jl_repeat(st_r, outer=n_neutral),
+                                       jl_repeat(torch.exp(ls_r) ** 2, outer=n_neutral))
+        # mutants :670-684: s_m[env_idx[rep][2:end], :, rep][:] .- repeat(s_t[range], n_bc)
+        rows = torch.as_tensor(env_idx[r][1:], dtype=torch.int64)
+        mean_m = jl_vec(s_m3[rows, :, r]) - jl_repeat(st_r, outer=n_bc)
+        var_m = jl_vec(torch.exp(lsig_m3[rows, :, r])) ** 2
+        lp = lp + mvnormal_diag_logpdf(logG_m, mean_m, var_m)
+    return lp
+
+
+# --------------------------------------------------------------------------
 # Uniform entry: log-joint value and autograd gradient for a problem dict
 # --------------------------------------------------------------------------
 MODELS = (
@@ -478,6 +548,11 @@ def logjoint(model: str, z: torch.Tensor, prob: dict) -> torch.Tensor:
     if model == "genotype_fitness_normal":
         return logjoint_genotype_fitness_normal(z, R, nt, N, M, prob["genotypes"], pri)
     if model == "multienv_replicate_fitness_normal":
+        if isinstance(R, (list, tuple)):
+            envs = prob["envs"]
+            if not isinstance(envs[0], (list, tuple)):
+                envs = [list(envs)] * len(R)
+            return logjoint_multienv_replicate_fitness_normal_ragged(z, R, nt, N, M, envs, pri)
         return logjoint_multienv_replicate_fitness_normal(z, R, nt, N, M, prob["envs"], pri)
     raise ValueError(f"unknown model {model!r}")
 
@@ -490,6 +565,11 @@ def n_latent(model: str, prob: dict) -> int:
         n_rep = len(R)
         n_st = sum(int(np.asarray(r).shape[0]) - 1 for r in R)
         n_lam = sum(int(np.asarray(r).size) for r in R)
+        if model == "multienv_replicate_fitness_normal":
+            envs = prob["envs"]
+            flat = [e for es in envs for e in es] if isinstance(envs[0], (list, tuple)) else list(envs)
+            E = len(_indexin_unique(flat)[0])
+            return 2 * n_st + E * M + 3 * E * M * n_rep + n_lam
         return 2 * n_st + M + 3 * M * n_rep + n_lam
     R = np.asarray(R)
     T = R.shape[0]

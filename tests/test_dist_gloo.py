@@ -66,6 +66,9 @@ def test_shard_ranges_partition_everything():
     ("multienv_fitness_normal", dict(n_neutral=11, n_bc=257, n_time=6, envs=[1, 1, 2, 3, 2, 3])),
     ("genotype_fitness_normal", dict(n_neutral=16, n_bc=600, n_time=5, n_geno=23)),
     ("multienv_replicate_fitness_normal", dict(n_neutral=9, n_bc=130, n_time=6, n_rep=2, envs=[1, 2, 3, 1, 2, 3])),
+    ("replicate_fitness_normal", dict(n_neutral=7, n_bc=90, n_time=[5, 4, 6])),
+    ("multienv_replicate_fitness_normal", dict(n_neutral=9, n_bc=130, n_time=[6, 4, 6],
+                                               envs=[[1, 2, 3, 1, 2, 3], [1, 1, 2, 3], [1, 3, 2, 1, 3, 2]])),
 ])
 def test_product_shard_layout_owns_every_latent_exactly_once(model, spec, world):
     """Over the ranks of a `world`-way split every latent of the reference order is owned by exactly one shard

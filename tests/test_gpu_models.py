@@ -57,6 +57,47 @@ def test_multienv_replicate_model(bb):
     _check_logjoint(bb, da, "multienv_replicate_fitness_normal", {"envs": da.envs}, None, dtype="f32", tol=2e-3)
 
 
+def test_ragged_multienv_replicate_model(bb):
+    """M5, Vector{Matrix{Int64}} method (…hierarchical_replicates.jl:449-687): unequal T per replicate, one
+    environment list per replicate (two replicates share T = 6 but not the list -> three launch groups)."""
+    from helpers import uneven_replicates
+    df, _ = load_fixture("replicate_fitness_normal")
+    df = uneven_replicates(df.assign(env=df.time.map({1: "A", 2: "A", 3: "B", 4: "C", 5: "B"})))
+    da = bb.utils.data_to_arrays(df, rep_col="rep", env_col="env")
+    assert isinstance(da.bc_count, list) and isinstance(da.envs[0], list)
+    model = "multienv_replicate_fitness_normal"
+    _check_logjoint(bb, da, model, {"envs": da.envs}, None)
+    _check_logjoint(bb, da, model, {"envs": da.envs}, None, dtype="f32", tol=2e-3)
+    da, _ = bb.synth.simulate(model, 9, 130, [6, 4, 6], envs=[[1, 2, 3, 1, 2, 3], [1, 1, 2, 3], [1, 3, 2, 1, 3, 2]], seed=5)
+    _check_logjoint(bb, da, model, {"envs": da.envs}, None)
+    with pytest.raises(bb.BarBayError, match="one environment list per replicate"):
+        bb.Engine(da, model, {"envs": [1, 2, 3, 1, 2, 3]})
+
+
+def test_ragged_multienv_replicate_advi_trajectory(bb):
+    """A few optimiser steps of the ragged M5 model with supplied noise == the restated AdvancedVI loop (fp64)."""
+    from oracle import advi_ref
+    model, K, n_steps = "multienv_replicate_fitness_normal", 2, 4
+    da, _ = bb.synth.simulate(model, 6, 40, [5, 4], envs=[["a", "b", "b", "c", "a"], ["a", "c", "b", "b"]], seed=11)
+    eng = bb.Engine(da, model, {"envs": da.envs}, n_samples=K, dtype="f64", seed=2)
+    rng = np.random.default_rng(5)
+    mu, omega = plausible_theta(eng.layout, da, rng)
+    noise = rng.standard_normal((n_steps, K, eng.D))
+    eng.set_params(mu, omega)
+    eng.set_optimizer("truncated", eta=0.1, tau=1.0, n=3)
+    for i in range(n_steps):
+        eng.step_with_noise(noise[i])
+    mu_g, om_g = eng.get_params()
+    tr = advi_ref.advi_run(model, oracle_problem(da, model), n_steps, K, advi_ref.TruncatedADAGrad(0.1, 1.0, 3), mu, omega,
+                           eps_fn=lambda s: noise[s])
+    assert rel_err(mu_g, tr.mu) < 1e-8 and rel_err(om_g, tr.omega) < 1e-8
+    # in-kernel Philox steps run and improve the ELBO
+    eng.init_params(1); eng.set_optimizer("decayed")
+    trace = eng.step(300, elbo_trace=True)
+    assert np.all(np.isfinite(trace)) and np.mean(trace[-20:]) > np.mean(trace[:20])
+    eng.close()
+
+
 @pytest.mark.parametrize("n_time", [3, 6, 11])
 def test_runtime_time_points_fallback(bb, n_time):
     """T without a compiled specialisation runs on the runtime-size kernels."""

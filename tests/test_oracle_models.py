@@ -125,6 +125,41 @@ def test_multienv_replicate_reduces_to_replicate_when_one_env(bb):
     assert abs(a - b) <= 1e-10 * abs(a)
 
 
+def _ragged_multienv_arrays(bb):
+    """Replicate fixture, last time point of the last replicate dropped (test/vi_tests.jl:102-105), with an
+    environment column: one environment list per replicate, of unequal length."""
+    df, _ = load_fixture("replicate_fitness_normal")
+    df = uneven_replicates(df.assign(env=df.time.map({1: "A", 2: "A", 3: "B", 4: "C", 5: "B"})))
+    return bb.utils.data_to_arrays(df, rep_col="rep", env_col="env")
+
+
+def test_ragged_multienv_replicate_model(bb):
+    """M5, Vector{Matrix{Int64}} method (…hierarchical_replicates.jl:449-687): with equal T and one shared
+    environment list it is the Array{Int64,3} method (:158-363) term for term."""
+    da = _ragged_multienv_arrays(bb)
+    assert isinstance(da.bc_count, list) and da.n_time == [5, 4]
+    assert da.envs == [["A", "A", "B", "C", "B"], ["A", "A", "B", "C"]] and da.n_env == 3
+    model = "multienv_replicate_fitness_normal"
+    lay = bb.model.var_groups(bb.model.resolve(model), da.n_time, da.n_rep, da.n_neutral, da.n_bc, da.n_env, 0)
+    prob = oracle_problem(da, model)
+    assert lay.n_latent == model_ref.n_latent(model, prob)
+    rng = np.random.default_rng(8)
+    z = torch.tensor(plausible_latents(lay, da, rng, 1)[0])
+    assert np.isfinite(float(model_ref.logjoint(model, z, prob)))
+    # equal T: the list-of-matrices method == the 3-D method
+    df, _ = load_fixture("replicate_fitness_normal")
+    da3 = bb.utils.data_to_arrays(df.assign(env=df.time.map({1: "A", 2: "A", 3: "B", 4: "C", 5: "B"})), rep_col="rep", env_col="env")
+    R3 = np.asarray(da3.bc_count)
+    lay3 = bb.model.var_groups(bb.model.resolve(model), da3.n_time, da3.n_rep, da3.n_neutral, da3.n_bc, da3.n_env, 0)
+    z3 = torch.tensor(plausible_latents(lay3, da3, rng, 1)[0])
+    prob3 = oracle_problem(da3, model)
+    probv = dict(prob3, bc_count=[R3[:, :, r] for r in range(R3.shape[2])],
+                 bc_total=[np.asarray(da3.bc_total)[:, r] for r in range(R3.shape[2])],
+                 envs=[list(da3.envs)] * R3.shape[2])
+    a, b = float(model_ref.logjoint(model, z3, prob3)), float(model_ref.logjoint(model, z3, probv))
+    assert abs(a - b) <= 1e-12 * abs(a)
+
+
 def test_elbo_gradient_formula(bb):
     """g_mu = mean_k dlogpi/dz, g_omega = (mean_k dlogpi/dz * eps + 1/sigma) * sigmoid(omega)
     equals autograd through the whole ELBO."""
