@@ -201,6 +201,13 @@ template <typename real> struct SharedArgs {
     double *elbo_sh;              // [K+1]: neutral-likelihood + shared-prior log-density per k; sum log sigma
     OptArgsT<double> opt;
     int leader;                   // 1: this rank reports the shared latents' ELBO terms (rank 0)
+    // as-written neutral pairing of the ragged replicate model (replicates.jl:599-605; single shard): the neutral
+    // columns' log-ratio differences [R][K][N][tmax-1] written by pass 1, the s-bar draws handed to pass 2
+    // [R][K][tmax], working arrays [3][R][K][tmax]; aw_d == nullptr: regular pairing
+    const real *aw_d;
+    real *aw_zs;
+    double *aw_tmp;
+    int aw_N;
 };
 
 __device__ __forceinline__ double softplus_d(double w) { return fmax(w, 0.0) + log1p(exp(-fabs(w))); }
@@ -245,8 +252,61 @@ __device__ __forceinline__ void shared_body(const SharedArgs<real> &a, double *s
     if (do_phase0) shared_phase0<real>(a, scratch);
     if (!xchg_wait_and_sum(a.xchg, sums)) return;            // multi-GPU: complete the sums over NVLink peer memory
     __syncthreads();
+    if (a.aw_d) {
+        // ---- phase 1, as-written pairing (model_fitness_normal_hierarchical_replicates.jl:599-605): vec(logGamma_n) is
+        // time-fastest, element kk = n (T_r - 1) + t, while the mean / variance vectors repeat every population latent N
+        // times in a row, element kk -> latent kk div N.  Ratio (n, t) is therefore scored against
+        // Normal(-sbar_p, sigma_p), p = (n (T_r - 1) + t) div N, and latent p collects the N ratios kk in [p N, (p+1) N).
+        // The neutral residual sums cannot be formed from per-time totals (c_t varies inside a latent's set), so the
+        // few neutral columns export their differences and the sums are taken here.
+        const int RKt = a.R * a.K * a.tmax, N = a.aw_N;
+        double *c_a = a.aw_tmp, *wb_a = c_a + RKt, *zs_a = wb_a + RKt;
+        for (int j = tid; j < RKt; j += nthr) {
+            const int t = j % a.tmax, k = (j / a.tmax) % a.K, r = j / (a.tmax * a.K);
+            if (t >= a.nt[r] - 1) continue;
+            const double *S = sums + (size_t)(r * a.K + k) * NQ * a.tmax;
+            const double zs = z_t[(size_t)k * n2 + a.sh0[r] + t], zl = z_t[(size_t)k * n2 + a.nst + a.sh0[r] + t];
+            c_a[j] = log(S[Q_LAM * a.tmax + t + 1]) - log(S[Q_LAM * a.tmax + t]);
+            wb_a[j] = exp(-2.0 * zl);
+            zs_a[j] = zs;
+            a.aw_zs[j] = (real)zs;
+        }
+        __syncthreads();
+        for (int j = tid; j < RKt; j += nthr) {
+            const int t = j % a.tmax, k = (j / a.tmax) % a.K, r = j / (a.tmax * a.K);
+            const int nt = a.nt[r], ntm = nt - 1;
+            u_t[j] = 0.0; lp_t[j] = 0.0;
+            if (t >= ntm) continue;
+            const int is = a.sh0[r] + t, il = a.nst + a.sh0[r] + t;
+            const size_t row = (size_t)(r * a.K + k) * a.tmax;
+            const double *S = sums + (size_t)(r * a.K + k) * NQ * a.tmax;
+            const real *d = a.aw_d + (size_t)(r * a.K + k) * N * (a.tmax - 1);
+            real *ctx = a.ctx + (size_t)(r * a.K + k) * 3 * a.tmax;
+            const double zs = zs_a[j], zl = z_t[(size_t)k * n2 + il], c = c_a[j], wbar = wb_a[j];
+            double s1 = 0.0, s2 = 0.0;             // latent p = t: its N ratios
+            for (int kk = t * N; kk < (t + 1) * N; ++kk) {
+                const int n = kk / ntm, tp = kk - n * ntm;
+                const double res = (double)d[(size_t)n * (a.tmax - 1) + tp] - c_a[row + tp] + zs;
+                s1 += res; s2 += res * res;
+            }
+            double uc = 0.0;                       // time t: sum_n w res of its N ratios (the coupling through c_t)
+            for (int n = 0; n < N; ++n) {
+                const int p = (n * ntm + t) / N;
+                uc += wb_a[row + p] * ((double)d[(size_t)n * (a.tmax - 1) + t] - c + zs_a[row + p]);
+            }
+            const double mut = S[Q_A * a.tmax + t] + (zs - c) * S[Q_W * a.tmax + t];   // mutants: regular pairing
+            const double2 ps = a.sh_pr[is], pl = a.sh_pr[il];
+            scratch[(size_t)k * n2 + is] = -(wbar * s1 + mut) - (zs - ps.x) * ps.y;
+            scratch[(size_t)k * n2 + il] = wbar * s2 - a.n_neutral - (zl - pl.x) * pl.y;
+            u_t[j] = uc + mut;
+            lp_t[j] = -a.n_neutral * zl - 0.5 * wbar * s2 - 0.5 * (zs - ps.x) * (zs - ps.x) * ps.y -
+                      0.5 * (zl - pl.x) * (zl - pl.x) * pl.y;
+            ctx[0 * a.tmax + t] = (real)(c - zs);
+            ctx[2 * a.tmax + t] = (real)wbar;
+        }
+    }
     // ---- phase 1
-    for (int j = tid; j < a.R * a.K * a.tmax; j += nthr) {
+    for (int j = tid; j < a.R * a.K * a.tmax && !a.aw_d; j += nthr) {
         const int t = j % a.tmax, k = (j / a.tmax) % a.K, r = j / (a.tmax * a.K);
         const int nt = a.nt[r];
         u_t[j] = 0.0; lp_t[j] = 0.0;

@@ -263,6 +263,8 @@ template <typename real> class Engine : public EngineBase {
     DBuf<uint32_t> col_id_;
     DBuf<double> part_, sums_, epart_, hy_epart_, elbo_sh_, elbo_out_, sh_scratch_;
     DBuf<real> ctx_;
+    DBuf<real> aw_d_, aw_zs_;  // as-written neutral pairing (ragged replicate model): see shared_body
+    DBuf<double> aw_tmp_;
     DBuf<r2> zeps_, hcontrib_, hsum_;
     // parity / gradient outputs
     DBuf<real> sup_lam_, sup_bc_, sup_hy_, dump_lam_, dump_bc_, dump_hy_, dump_hc_;
@@ -354,6 +356,11 @@ template <typename real> Engine<real>::Engine(const bb_desc &d) {
     sh_scratch_.alloc((size_t)3 * L.K * 2 * L.nst + (size_t)2 * L.R * L.K * L.tmax + 2 * L.nst);
     elbo_sh_.alloc(L.K + 1);
     elbo_out_.alloc(L.K + 1);
+    if (L.as_written) {            // buffers of the as-written neutral pairing (bb_aux_kernels.cuh, shared_body)
+        aw_d_.alloc((size_t)L.R * L.K * std::max(L.N, 1) * (L.tmax - 1));
+        aw_zs_.alloc((size_t)L.R * L.K * L.tmax);
+        aw_tmp_.alloc((size_t)3 * L.R * L.K * L.tmax);
+    }
     build_groups();
 
     // algorithmic bytes per step of this shard: theta + accumulators read and written
@@ -834,6 +841,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
             a.hy_zeps = zeps_.p; a.H = L.H;
             a.part = gpart;
             a.pv = g.pv; a.sup = sup; a.nbuf = g.p1nbuf;
+            a.aw_d = aw_d_.p; a.aw_N = L.N;
             (m.sup ? g.ks_sup.pass1 : g.ks.pass1)<<<g.p1blocks, BLOCK, g.p1smem, stream_>>>(a);
             ++launches;
         }
@@ -892,6 +900,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         sa.elbo_sh = m.want_elbo ? elbo_sh_.p : nullptr;
         sa.opt = opt_args<double>(m.update);
         sa.leader = L.rank == 0 ? 1 : 0;
+        sa.aw_d = aw_d_.p; sa.aw_zs = aw_zs_.p; sa.aw_tmp = aw_tmp_.p; sa.aw_N = L.N;
         if (use_tail)
             tail_kernel<real><<<cdiv((long long)nwarps * 32, 256) + 1, 256, tail_smem, stream_>>>(ra, L.R, xp, sa, ticket_.p,
                                                                                              (int)sums_.n);
@@ -921,6 +930,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         a.l2_ring = (opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p && m.update && !(a.stage_ring && g.p2stage_acc)) ? 1 : 0;
         a.stage_acc = g.p2stage_acc; a.nbuf = g.p2nbuf;
         a.abort = (xchg_on_ && L.world > 1) ? xchg_err_.p : nullptr;
+        a.aw_zs = aw_zs_.p; a.aw_N = L.N;
         if (m.stepk) {
             // the packed step kernel: one step behind the tail (programmatic dependent launch), or -- persistent,
             // cooperative -- m.nsteps steps with the tails of steps 2.. inside the kernel

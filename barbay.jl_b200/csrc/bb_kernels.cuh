@@ -214,7 +214,7 @@ __device__ __forceinline__ void flush_rows(const real *sacc, int nk, int pvs, in
 template <typename real, int NT, int NE, bool HIER>
 __device__ __forceinline__ void pass1_sample(const real *eps, const real *mu, const real *sg, const real *mub,
                                              const real *sgb, const real *zth, bool neutral, int nt, int ne,
-                                             const int *env_of_t, real *acc) {
+                                             const int *env_of_t, real *acc, real *neu_out = nullptr) {
     using S = Shape<NT, NE, HIER>;
     using r2 = vec2<real>;
     constexpr bool PAIRS = AccLayout<NT, NE>::PAIRS;
@@ -238,6 +238,7 @@ __device__ __forceinline__ void pass1_sample(const real *eps, const real *mu, co
             const real d = z[t + 1] - z[t];
             add(nt + t, d);
             add(2 * nt - 1 + t, d * d);
+            if (neu_out) neu_out[t] = d;          // as-written pairing: the tail pairs the ratios itself
         }
     } else {
         real zs[S::MAXE], w[S::MAXE];
@@ -399,8 +400,11 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
                 real eps[S::MAXC];
                 column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, strig,
                                                  a.sup, c, cpad, C.tmax, C.nj);
+                real *neu_out = nullptr;
+                if (a.aw_d && seg.neutral)
+                    neu_out = a.aw_d + (((size_t)seg.rep * a.K + k) * a.aw_N + i) * (C.tmax - 1);
                 pass1_sample<real, NT, NE, HIER>(eps, mu, sg, mub, sgb, zth, seg.neutral, nt, ne, a.env_of_t,
-                                                 sacc + (size_t)(k - kc0) * pva * BLOCK + (PAIRS ? 2 * tid : tid));
+                                                 sacc + (size_t)(k - kc0) * pva * BLOCK + (PAIRS ? 2 * tid : tid), neu_out);
             }
         }
         cp_async_wait<0>();
@@ -875,8 +879,15 @@ pass2_kernel(const P2Args<real> a) {
 #pragma unroll
                 for (int t = 0; t < S::MAXT - 1; ++t) {
                     if (t >= nt - 1) break;
-                    const real res = z[t + 1] - z[t] - cE(t);
-                    const real u = cW(t) * res;
+                    real ce = cE(t), cw = cW(t);
+                    if (a.aw_zs) {                 // as-written pairing: population latent p instead of t
+                        const int p = (i * (nt - 1) + t) / a.aw_N;
+                        const real *zsr = a.aw_zs + ((size_t)seg.rep * a.K + k) * a.tmax_ctx;
+                        ce += zsr[t] - zsr[p];
+                        cw = crow[2 * TT + p];
+                    }
+                    const real res = z[t + 1] - z[t] - ce;
+                    const real u = cw * res;
                     g[t] += u - uprev;
                     uprev = u;
                 }

@@ -91,8 +91,12 @@ void build_layout(const bb_desc &d, Layout &L) {
         fail("multienv models with unequal time points per replicate need one environment list per replicate (env_per_rep)");
     if (d.env_per_rep && d.model != BB_MODEL_MULTIENV_REPLICATE)
         fail("env_per_rep applies to the multienv x replicate model only");
-    if (ragged && d.ragged_as_written)
-        fail("the as-written neutral pairing of replicates.jl:599-605 is not implemented; pass corrected=true");
+    // the Vector{Matrix{Int64}} method of the replicate model pairs the neutral ratios as written in
+    // replicates.jl:599-605; the multienv x replicate method (…replicates.jl:650-668) pairs them by time
+    L.as_written = ragged && d.ragged_as_written && d.model == BB_MODEL_REPLICATE;
+    if (L.as_written && d.world > 1)
+        fail("the as-written neutral pairing of replicates.jl:599-605 runs on a single shard; pass corrected=true "
+             "(ragged_as_written = 0) to shard a fit with unequal time points per replicate");
     L.env_of_rt.assign(L.R, std::vector<int>(kMaxNtDyn, 0));
     if (multienv) {
         if (!d.env_idx) fail("Models with multiple environments require env_idx");

@@ -22,6 +22,7 @@ struct Layout {
     std::vector<int> nt;           // [R]
     int tmax = 0, nst = 0;
     std::vector<int> sh0;          // [R] offset of s-bar[r][0] in the s-bar block
+    bool as_written = false;       // ragged replicate model: neutral pairing of replicates.jl:599-605
     std::vector<std::vector<int>> env_of_rt;   // [R][kMaxNtDyn] 0-based environment of time point t of replicate r
     int K = 1;
     // shard

@@ -78,6 +78,10 @@ template <typename real> struct P1Args {
     double *part;          // [gridDim.x][K][pv] block partial sums (double)
     int pv;                // slots per sample: nt + 2 (nt - 1)
     int nbuf;              // staging buffers (2, or 1 when shared memory is short)
+    // as-written neutral pairing of the ragged replicate model (replicates.jl:599-605): every neutral column also
+    // stores its log-ratio differences d[t] = z[t+1] - z[t] per sample, [R][K][N][tmax-1]; nullptr otherwise
+    real *aw_d;
+    int aw_N;
     SupArgs<real> sup;
 };
 
@@ -107,6 +111,11 @@ template <typename real> struct P2Args {
     int pv;                // row stride of part (3 nt - 2)
     int acc_slots;         // fused step: rows of BLOCK accumulators in shared memory
     const int *abort;      // multi-GPU: set by the tail kernel when the exchange of this step failed -> no update
+    // as-written neutral pairing (replicates.jl:599-605): ratio (t, n) of neutral n is paired with population latent
+    // p = (n (T_r - 1) + t) div N; aw_zs = this step's s-bar draws [R][K][tmax] (the context rows hold c_t - sbar_t and
+    // wbar_t under the regular index); nullptr otherwise
+    const real *aw_zs;
+    int aw_N;
     SupArgs<real> sup;
 };
 

@@ -22,7 +22,7 @@ class Engine:
     """
 
     def __init__(self, data_arrays, model, model_kwargs=None, *, n_samples: int = 1, dtype: str = "f64",
-                 seed: int = 0, device: int = -1, rank: int = 0, world: int = 1, corrected_ragged: bool = True,
+                 seed: int = 0, device: int = -1, rank: int = 0, world: int = 1, corrected_ragged: bool = False,
                  n_devices: int = 1, probe_only: bool = False):
         self._h = C.c_void_p()
         self._lib = _lib.load()

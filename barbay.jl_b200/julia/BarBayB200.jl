@@ -59,6 +59,7 @@ struct BBDesc
     rank::Int32
     world::Int32
     n_devices::Int32     # ABI 2: N > 1 = one handle drives N GPUs of this process (single blocking advi call)
+    env_per_rep::Int32   # 1: env_idx holds one environment list per replicate
 end
 
 # model function name -> bb_model (the reference dispatches on the name too, src/vi.jl:111-169)
@@ -89,13 +90,17 @@ Replacement for `Turing.vi(bayes_model, advi; optimizer=opt)` (src/vi.jl:201).  
 src/utils.jl:1049-1060, and is typed `::Distributions.Sampleable`, :1411) accepts it.
 """
 function vi(da, model::Function, model_kwargs::Dict, advi, opt; seed::Integer=0, dtype::Symbol=:f64,
-            device::Integer=-1, n_devices::Integer=1)
+            device::Integer=-1, n_devices::Integer=1, corrected_ragged::Bool=false)
     keep = Any[]
     kw = Dict{Symbol,Any}(model_kwargs)
     counts = da.bc_count isa Vector ? reduce(vcat, vec.(da.bc_count)) : vec(da.bc_count)
     n_time = Int32.(da.bc_count isa Vector ? size.(da.bc_count, 1) :
                     fill(size(da.bc_count, 1), ndims(da.bc_count) == 3 ? size(da.bc_count, 3) : 1))
-    env_idx = haskey(kw, :envs) ? Int32.(indexin(kw[:envs], unique(kw[:envs]))) : Int32[]
+    # one environment list shared by all replicates, or one list per replicate (the Vector{Matrix} method of the
+    # multienv x replicate model, …replicates.jl:465-472): indexin.(envs, Ref(unique(vcat(envs...)))) back to back
+    env_per_rep = haskey(kw, :envs) && eltype(kw[:envs]) <: AbstractVector
+    env_flat = haskey(kw, :envs) ? (env_per_rep ? reduce(vcat, kw[:envs]) : kw[:envs]) : Any[]
+    env_idx = isempty(env_flat) ? Int32[] : Int32.(indexin(env_flat, unique(env_flat)))
     geno_idx = haskey(kw, :genotypes) ? Int32.(indexin(kw[:genotypes], unique(kw[:genotypes]))) : Int32[]
     push!(keep, counts, n_time, env_idx, geno_idx)
     getp(k, d) = prior(get(kw, k, d), keep)
@@ -106,7 +111,8 @@ function vi(da, model::Function, model_kwargs::Dict, advi, opt; seed::Integer=0,
         isempty(geno_idx) ? 0 : length(unique(geno_idx)), isempty(geno_idx) ? C_NULL : pointer(geno_idx),
         getp(:s_pop_prior, [0.0, 2.0]), getp(:logσ_pop_prior, [0.0, 1.0]), getp(:s_bc_prior, [0.0, 2.0]),
         getp(:logσ_bc_prior, [0.0, 1.0]), getp(:logλ_prior, [3.0, 3.0]), getp(:logτ_prior, [-2.0, 1.0]),
-        0, advi.samples_per_step, UInt64(seed), Int32(device), 0, 1, Int32(n_devices))
+        Int32(corrected_ragged ? 0 : 1), advi.samples_per_step, UInt64(seed), Int32(device), 0, 1, Int32(n_devices),
+        Int32(env_per_rep))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep begin
         rc = ccall((:bb_create, LIB), Cint, (Ref{BBDesc}, Ref{Ptr{Cvoid}}), desc, h)

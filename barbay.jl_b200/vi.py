@@ -57,7 +57,7 @@ def advi(*, data, model, outputname=None, model_kwargs=None, id_col="barcode", t
          advi=None, opt=None, verbose=True,
          # backend extras (not part of the reference signature; defaults keep its behaviour)
          seed=0, dtype="f64", device=-1, n_devices=1, n_posterior_samples=10_000, return_engine=False,
-         elbo_rel_tol=None, elbo_every=100, elbo_window=5, device_derived_rows=True):
+         elbo_rel_tol=None, elbo_every=100, elbo_window=5, device_derived_rows=True, corrected_ragged=False):
     """Fit the mean-field Gaussian posterior of a BarBay model with ADVI on a B200.
 
     Returns the tidy posterior ``DataFrame`` (columns ``mean, std, varname, vartype[, rep][, env], id``)
@@ -67,6 +67,10 @@ def advi(*, data, model, outputname=None, model_kwargs=None, id_col="barcode", t
     blocking call per step batch, per-step exchange over NVLink peer memory): same posterior as one GPU.
     ``elbo_rel_tol`` (extension; the reference always runs ``max_iters``, src/vi.jl:98): stop early once the mean of
     the last ``elbo_window`` ELBO estimates (one every ``elbo_every`` steps) moves by less than that fraction.
+    ``corrected_ragged``: replicates with unequal numbers of time points are fitted with the reference's neutral
+    pairing as written (model_fitness_normal_hierarchical_replicates.jl:599-605: ratio (t, n) against
+    ``s̄[⌈k / N⌉]``) by default; ``True`` pairs ratio (t, n) with ``s̄[t]`` like every other method of the reference
+    does (required for ``n_devices`` > 1 on such data).
     """
     mdl = _model.resolve(model)
     advi_cfg = advi if advi is not None else ADVI(1, 10_000)
@@ -94,7 +98,7 @@ def advi(*, data, model, outputname=None, model_kwargs=None, id_col="barcode", t
         model_kwargs = {"genotypes": data_arrays.genotypes, **model_kwargs}
 
     eng = Engine(data_arrays, mdl, model_kwargs, n_samples=advi_cfg.samples_per_step, dtype=dtype, seed=seed,
-                 device=device, n_devices=n_devices)
+                 device=device, n_devices=n_devices, corrected_ragged=corrected_ragged)
     var_names = eng.layout.var_names                                                      # vi.jl:184-198
     eng.init_params(seed)                                                                 # Turing meanfield()
     _apply_optimizer(eng, opt)

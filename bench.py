@@ -340,7 +340,19 @@ def roofline_of(cx: Ctx, eng, steps_ms_per_step, n_prof, peak, peak_src, key, no
          "kernel_share_of_step": t_k / (ms_tot / n_prof * 1e-3), "step_achieved": step_ach, "step_frac": step_ach / peak,
          "l2_resident": bool(alg < L2_BYTES)}
     if plane["persistent"]:
-        r["kernel_us_note"] = "persistent launch: kernel_us = launch duration / steps, i.e. it includes the in-kernel tail"
+        # one launch covers up to persist_chunk steps: bytes and duration are those of the launch, the ratio is per step
+        spl = max(1, min(int(plane["persist_chunk"]), int(n_prof)))
+        r["steps_per_launch"] = spl
+        r["algorithmic_bytes_per_step"] = alg
+        r["algorithmic_bytes_per_launch"] = alg * spl
+        r["launch_us"] = t_k * 1e6 * spl
+        if traffic is not None:
+            r["traffic_per_step"] = traffic
+            r["traffic"] = traffic * spl
+            r["traffic_note"] = ("ncu capture of a ONE-step launch of the same kernel (BB_PERSIST=0), scaled by "
+                                 "steps_per_launch")
+        r["kernel_us_note"] = ("persistent launch: kernel_us = launch duration / steps, i.e. it includes the in-kernel "
+                               "reduction and shared-latent phases of every step")
     if note:
         r["note"] = note
     return r

@@ -92,7 +92,10 @@ typedef struct bb_desc {
     int32_t n_geno;               /* G; 0 unless genotype model */
     const int32_t *geno_idx;      /* [n_bc] 1-based indexin(genotypes, unique(genotypes)) (genotypes.jl:170-174) or NULL */
     bb_prior s_pop_prior, logsig_pop_prior, s_bc_prior, logsig_bc_prior, loglam_prior, logtau_prior;
-    int32_t ragged_as_written;    /* 1: reproduce the neutral pairing of replicates.jl:599-605 for unequal T (default of the reference) */
+    /* Replicate model with unequal T per replicate (the Vector{Matrix{Int64}} method): 1 = the neutral pairing as
+     * written in replicates.jl:599-605 -- ratio k of vec(logGamma_n) against sbar[ceil(k / N)]; the reference's
+     * behaviour; world must be 1 -- 0 = ratio (t, n) against sbar[t] like every other method of the reference. */
+    int32_t ragged_as_written;
     int32_t n_samples;            /* K = advi.samples_per_step (src/vi.jl:98) */
     uint64_t seed;                /* key of the Philox noise lattice */
     int32_t device;               /* CUDA ordinal, -1 = current device */

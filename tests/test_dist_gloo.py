@@ -85,7 +85,7 @@ def test_product_shard_layout_owns_every_latent_exactly_once(model, spec, world)
         g_of = np.asarray(gidx)[order]
     hyper_owned = 0
     for rank in range(world):
-        pr = bb.Engine(da, model, n_samples=2, rank=rank, world=world, probe_only=True)
+        pr = bb.Engine(da, model, n_samples=2, rank=rank, world=world, probe_only=True, corrected_ragged=True)
         info = pr.probe_info
         total = pr.owned.astype(np.int64) if total is None else total + pr.owned
         assert info["n0"] == prev_n1 and info["m0"] == prev_m1          # contiguous ranges, rank order
@@ -103,6 +103,11 @@ def test_product_shard_layout_owns_every_latent_exactly_once(model, spec, world)
 
 def test_product_layout_probe_validation_messages():
     import barbay_b200 as bb
+    rag, _ = bb.synth.simulate("replicate_fitness_normal", n_neutral=4, n_bc=9, n_time=[4, 3], seed=1)
+    with pytest.raises(bb.BarBayError, match="single shard"):          # as-written pairing (the default) does not shard
+        bb.Engine(rag, "replicate_fitness_normal", rank=0, world=2, probe_only=True)
+    bb.Engine(rag, "replicate_fitness_normal", probe_only=True)
+    bb.Engine(rag, "replicate_fitness_normal", rank=1, world=2, probe_only=True, corrected_ragged=True)
     da, _ = bb.synth.simulate("fitness_normal", n_neutral=4, n_bc=9, n_time=4, seed=1)
     with pytest.raises(bb.BarBayError, match="rank, world"):
         bb.Engine(da, "fitness_normal", rank=3, world=2, probe_only=True)

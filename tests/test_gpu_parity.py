@@ -15,13 +15,13 @@ MODELS = ["fitness_normal", "replicate_fitness_normal", "multienv_fitness_normal
 TOL = {"f64": dict(logp=1e-9, grad=1e-9), "f32": dict(logp=1e-4, grad=2e-3)}
 
 
-def _setup(bb, model, K, dtype, uneven=False, kwargs=None):
+def _setup(bb, model, K, dtype, uneven=False, kwargs=None, **engine_kw):
     df, cols = load_fixture(model)
     if uneven:
         df = uneven_replicates(df)
     da = bb.utils.data_to_arrays(df, **cols)
     kw = dict(kwargs or {})
-    eng = bb.Engine(da, model, kw, n_samples=K, dtype=dtype, seed=1234)
+    eng = bb.Engine(da, model, kw, n_samples=K, dtype=dtype, seed=1234, **engine_kw)
     return da, eng
 
 
@@ -66,7 +66,7 @@ def test_elbo_gradient_with_supplied_noise(bb, model, dtype):
 def test_uneven_replicates_corrected_pairing(bb):
     from oracle import model_ref
     model, K = "replicate_fitness_normal", 2
-    da, eng = _setup(bb, model, K, "f64", uneven=True)
+    da, eng = _setup(bb, model, K, "f64", uneven=True, corrected_ragged=True)
     assert isinstance(da.bc_count, list) and da.n_time == [5, 4]
     rng = np.random.default_rng(3)
     z = plausible_latents(eng.layout, da, rng, K)
@@ -76,6 +76,62 @@ def test_uneven_replicates_corrected_pairing(bb):
         lp_ref, g_ref = model_ref.logjoint_and_grad(model, z[k], prob)
         assert abs(logp[k] - lp_ref) <= 1e-9 * abs(lp_ref)
         assert rel_err(grad[k], g_ref) <= 1e-9
+    eng.close()
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_uneven_replicates_as_written_pairing(bb, dtype):
+    """The reference's own behaviour for unequal T per replicate (the default): neutral ratio k of vec(logGamma_n)
+    against s-bar[ceil(k / N)] (model_fitness_normal_hierarchical_replicates.jl:599-605)."""
+    from oracle import model_ref
+    model, K = "replicate_fitness_normal", 3
+    da, eng = _setup(bb, model, K, dtype, uneven=True)
+    rng = np.random.default_rng(3)
+    z = plausible_latents(eng.layout, da, rng, K)
+    logp, grad = eng.logjoint_grad(z)
+    prob = oracle_problem(da, model, corrected=False)
+    prob_c = oracle_problem(da, model, corrected=True)
+    for k in range(K):
+        lp_ref, g_ref = model_ref.logjoint_and_grad(model, z[k], prob)
+        assert abs(logp[k] - lp_ref) <= TOL[dtype]["logp"] * abs(lp_ref), (logp[k], lp_ref)
+        assert rel_err(grad[k], g_ref) <= TOL[dtype]["grad"], rel_err(grad[k], g_ref)
+        if dtype == "f64":       # and it is NOT the corrected pairing
+            lp_c, g_c = model_ref.logjoint_and_grad(model, z[k], prob_c)
+            assert abs(lp_ref - lp_c) > 1e-6 * abs(lp_ref) and rel_err(grad[k], g_c) > 1e-6
+    eng.close()
+
+
+@pytest.mark.parametrize("opt", ["decayed", "truncated"])
+def test_uneven_replicates_as_written_trajectory(bb, opt):
+    """Optimiser trajectory and ELBO of the as-written ragged model == the restated AdvancedVI loop (fp64); a
+    synthetic with three replicates (T = 5, 4, 6) and N that does not divide the ratios evenly."""
+    from oracle import advi_ref
+    model, K, n_steps = "replicate_fitness_normal", 2, 5
+    da, _ = bb.synth.simulate(model, 7, 60, [5, 4, 6], seed=13)
+    eng = bb.Engine(da, model, n_samples=K, dtype="f64", seed=3)
+    rng = np.random.default_rng(21)
+    mu, omega = plausible_theta(eng.layout, da, rng)
+    noise = rng.standard_normal((n_steps, K, eng.D))
+    eng.set_params(mu, omega)
+    prob = oracle_problem(da, model, corrected=False)
+    elbo, g_mu, g_om = eng.elbo_grad(noise[0])
+    e_ref, gm_ref, go_ref, _ = advi_ref.elbo_value_and_grad(model, prob, mu, omega, noise[0])
+    assert abs(elbo - e_ref) <= 1e-9 * abs(e_ref) and rel_err(g_mu, gm_ref) <= 1e-9 and rel_err(g_om, go_ref) <= 1e-9
+    if opt == "decayed":
+        eng.set_optimizer("decayed", eta=0.1, pre=1.0, post=0.9)
+        ref_opt = advi_ref.DecayedADAGrad(0.1, 1.0, 0.9)
+    else:
+        eng.set_optimizer("truncated", eta=0.1, tau=1.0, n=3)
+        ref_opt = advi_ref.TruncatedADAGrad(0.1, 1.0, 3)
+    for i in range(n_steps):
+        eng.step_with_noise(noise[i])
+    mu_g, om_g = eng.get_params()
+    tr = advi_ref.advi_run(model, prob, n_steps, K, ref_opt, mu, omega, eps_fn=lambda s: noise[s])
+    assert rel_err(mu_g, tr.mu) < 1e-8 and rel_err(om_g, tr.omega) < 1e-8
+    # the in-kernel lattice path runs too and improves the ELBO
+    eng.init_params(1); eng.set_optimizer("decayed")
+    trace = eng.step(300, elbo_trace=True)
+    assert np.all(np.isfinite(trace)) and np.mean(trace[-20:]) > np.mean(trace[:20])
     eng.close()
 
 
