@@ -600,11 +600,13 @@ template <typename real> void Engine<real>::size_pass2() {
 
         int coop = 0;
         BB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
-        // default: on.  For the shards of a multi-GPU run (tens of microseconds per step) the launch pair and the tail
-        // kernel are a large share; on one GPU at cfg2 it measures 147.6 us per step against 149.7 us for the launch pair
-        // (profiles/r2_smallshard.jsonl).  BB_PERSIST=0 selects the launch pair, BB_PERSIST=n the steps per launch.
+        // default: on for the shards of a multi-GPU run (tens of microseconds per step: the launch pair and the tail
+        // kernel are a large share).  On one GPU at cfg2 it measures 147.0 us per step against 149.7 us for the launch
+        // pair (profiles/r2_smallshard.jsonl), but its in-kernel shared-latent phases run in the kernel's precision and
+        // operation order, so a run split into several bb_step calls (or resumed from a checkpoint) would no longer be
+        // bitwise the uninterrupted one; the single-GPU default keeps that property.  BB_PERSIST=n opts in.
         const char *pe = getenv("BB_PERSIST");
-        int want = pe ? atoi(pe) : 256;
+        int want = pe ? atoi(pe) : (L.world > 1 ? 256 : 0);
         if (!coop || !g.step_persist) want = 0;
         if (L.world > 1 && !xchg_on_) want = 0;
         if (want > 1) {
@@ -841,7 +843,6 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
             a.hy_zeps = zeps_.p; a.H = L.H;
             a.part = gpart;
             a.pv = g.pv; a.sup = sup; a.nbuf = g.p1nbuf;
-            a.aw_d = aw_d_.p; a.aw_N = L.N;
             (m.sup ? g.ks_sup.pass1 : g.ks.pass1)<<<g.p1blocks, BLOCK, g.p1smem, stream_>>>(a);
             ++launches;
         }
@@ -855,6 +856,20 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
             reduce_kernel<<<cdiv((long long)nwarps * 32, 128), 128, 0, stream_>>>(ra, L.R);
             ++launches;
         }
+    }
+    if (L.as_written) {
+        // as-written neutral pairing (ragged replicate model): the neutral columns' log-ratio differences of this step
+        AwArgs<real> aw{};
+        for (const HostSeg &s : L.segs) {
+            if (!s.neutral) continue;
+            Seg g{};
+            g.col0 = s.col0; g.ncol = s.ncol; g.rep = s.rep; g.nt = s.nt; g.neutral = 1; g.colid0 = s.colid0; g.sh0 = s.sh0;
+            aw.segs.seg[aw.segs.nseg++] = g;
+        }
+        aw.cols = C; aw.K = L.K; aw.N = L.N; aw.key = pkey; aw.step = m.step; aw.sup = sup; aw.d = aw_d_.p;
+        if (m.sup) aw_export_kernel<real, true><<<L.K, BLOCK, 0, stream_>>>(aw);
+        else aw_export_kernel<real, false><<<L.K, BLOCK, 0, stream_>>>(aw);
+        ++launches;
     }
     XchgWaitArgs xw{};
     XchgPostArgs xp{};

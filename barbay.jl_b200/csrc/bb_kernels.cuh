@@ -214,7 +214,7 @@ __device__ __forceinline__ void flush_rows(const real *sacc, int nk, int pvs, in
 template <typename real, int NT, int NE, bool HIER>
 __device__ __forceinline__ void pass1_sample(const real *eps, const real *mu, const real *sg, const real *mub,
                                              const real *sgb, const real *zth, bool neutral, int nt, int ne,
-                                             const int *env_of_t, real *acc, real *neu_out = nullptr) {
+                                             const int *env_of_t, real *acc) {
     using S = Shape<NT, NE, HIER>;
     using r2 = vec2<real>;
     constexpr bool PAIRS = AccLayout<NT, NE>::PAIRS;
@@ -238,7 +238,6 @@ __device__ __forceinline__ void pass1_sample(const real *eps, const real *mu, co
             const real d = z[t + 1] - z[t];
             add(nt + t, d);
             add(2 * nt - 1 + t, d * d);
-            if (neu_out) neu_out[t] = d;          // as-written pairing: the tail pairs the ratios itself
         }
     } else {
         real zs[S::MAXE], w[S::MAXE];
@@ -400,11 +399,8 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
                 real eps[S::MAXC];
                 column_noise<real, S::MAXC, SUP>(eps, nclass, nt, colid, (uint32_t)k, a.step, a.key, strig,
                                                  a.sup, c, cpad, C.tmax, C.nj);
-                real *neu_out = nullptr;
-                if (a.aw_d && seg.neutral)
-                    neu_out = a.aw_d + (((size_t)seg.rep * a.K + k) * a.aw_N + i) * (C.tmax - 1);
                 pass1_sample<real, NT, NE, HIER>(eps, mu, sg, mub, sgb, zth, seg.neutral, nt, ne, a.env_of_t,
-                                                 sacc + (size_t)(k - kc0) * pva * BLOCK + (PAIRS ? 2 * tid : tid), neu_out);
+                                                 sacc + (size_t)(k - kc0) * pva * BLOCK + (PAIRS ? 2 * tid : tid));
             }
         }
         cp_async_wait<0>();
@@ -412,6 +408,46 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
         // block reduction of the private columns, in double, fixed order
         flush_rows<real, PAIRS>(sacc, kc1 - kc0, pvs, pva, kc0, pv, a.part);
         __syncthreads();
+    }
+}
+
+// As-written neutral pairing of the ragged replicate model (replicates.jl:599-605): the shared-latent kernel pairs the
+// neutral ratios itself (shared_body, bb_aux_kernels.cuh) and needs d[t] = z[t+1] - z[t] of every neutral column and
+// sample -- the same draws as pass 1 (same lattice call, or the same supplied noise).  A few hundred columns: a kernel
+// of its own (block k = sample k) keeps pass 1 exactly as it is for every other fit.
+template <typename real, bool SUP>
+__global__ void __launch_bounds__(BLOCK) aw_export_kernel(const AwArgs<real> a) {
+    using r2 = vec2<real>;
+    constexpr bool F32 = std::is_same<real, float>::value;
+    __shared__ float2 strig[F32 ? TRIG_N : 1];
+    if constexpr (F32) {
+        for (int i = threadIdx.x; i < TRIG_N; i += BLOCK) strig[i] = a.key.trig[i];
+        __syncthreads();
+    }
+    const ColArrays<real> &C = a.cols;
+    const int k = blockIdx.x;
+    for (int si = 0; si < a.segs.nseg; ++si) {
+        const Seg &seg = a.segs.seg[si];
+        const int nt = seg.nt;
+        for (int i = threadIdx.x; i < seg.ncol; i += BLOCK) {
+            const int c = seg.col0 + i;
+            const uint32_t colid = C.col_id ? C.col_id[c] : seg.colid0 + (uint32_t)i;
+            real eps[MAX_NT_DYN];
+            column_noise<real, MAX_NT_DYN, SUP>(eps, nt, nt, colid, (uint32_t)k, a.step, a.key, strig, a.sup, c, C.cpad,
+                                                C.tmax, C.nj);
+            real *out = a.d + (((size_t)seg.rep * a.K + k) * a.N + i) * (C.tmax - 1);
+            real zprev = real(0);
+#pragma unroll
+            for (int t = 0; t < MAX_NT_DYN; ++t) {
+                if (t >= nt) break;
+                const r2 th = C.lam_th[(size_t)t * C.cpad + c];
+                real mu = th.x, sg = softplus_only<real>(th.y);
+                if constexpr (SUP) if (a.sup.z_direct) { mu = real(0); sg = real(1); }
+                const real z = fma(sg, eps[t], mu);
+                if (t > 0) out[t - 1] = z - zprev;
+                zprev = z;
+            }
+        }
     }
 }
 

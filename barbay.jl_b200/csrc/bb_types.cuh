@@ -78,11 +78,18 @@ template <typename real> struct P1Args {
     double *part;          // [gridDim.x][K][pv] block partial sums (double)
     int pv;                // slots per sample: nt + 2 (nt - 1)
     int nbuf;              // staging buffers (2, or 1 when shared memory is short)
-    // as-written neutral pairing of the ragged replicate model (replicates.jl:599-605): every neutral column also
-    // stores its log-ratio differences d[t] = z[t+1] - z[t] per sample, [R][K][N][tmax-1]; nullptr otherwise
-    real *aw_d;
-    int aw_N;
     SupArgs<real> sup;
+};
+
+// As-written neutral pairing of the ragged replicate model (replicates.jl:599-605): arguments of aw_export_kernel
+template <typename real> struct AwArgs {
+    SegList segs;          // the neutral segments
+    ColArrays<real> cols;
+    int K, N;
+    PhiloxKey key;
+    uint32_t step;
+    SupArgs<real> sup;
+    real *d;               // [R][K][N][tmax-1] log-ratio differences d[t] = z[t+1] - z[t] per neutral column and sample
 };
 
 template <typename real> struct P2Args {
