@@ -84,6 +84,13 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
+    def wait_first(self, timeout: float = 8.0):
+        """nvidia-smi needs about a second before its first sample: block until it streams (the timed region of the
+        default run is 0.3 s long and would otherwise be over before the first row)."""
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < timeout and self.is_alive():
+            time.sleep(0.05)
+
     def stop(self):
         self._stop.set()
         if self.proc is not None:
@@ -383,6 +390,9 @@ def run_ours(args, emit):
 
     parity = parity_check(cx) if world > 1 else None
 
+    sampler = ClockSampler(cx.local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     mult = world if args.scaling == "weak" else 1
     model, da = make_workload(CFG, mult)
     (T, B), n_cells = count_shape(da)
@@ -390,9 +400,9 @@ def run_ours(args, emit):
     eng = cx.engine(da, model, K, args.dtype, args.opt)
     plane = eng.data_plane()
 
-    sampler = ClockSampler(cx.local_rank) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.wait_first()
+    cx.barrier()
     t_wall0 = time.time()
     ms, launches = cx.time_steps(eng, args.steps, args.warmup)
     t_wall1 = time.time()
