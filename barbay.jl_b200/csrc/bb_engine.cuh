@@ -600,13 +600,13 @@ template <typename real> void Engine<real>::size_pass2() {
 
         int coop = 0;
         BB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
-        // default: on for the shards of a multi-GPU run (tens of microseconds per step: the launch pair and the tail
-        // kernel are a large share).  On one GPU at cfg2 it measures 147.0 us per step against 149.7 us for the launch
-        // pair (profiles/r2_smallshard.jsonl), but its in-kernel shared-latent phases run in the kernel's precision and
-        // operation order, so a run split into several bb_step calls (or resumed from a checkpoint) would no longer be
-        // bitwise the uninterrupted one; the single-GPU default keeps that property.  BB_PERSIST=n opts in.
+        // default: on (256 steps per launch), on one GPU as on the shards of a multi-GPU run: 147 us per step at cfg2
+        // against 150-154 us for the launch pair (profiles/r2_smallshard.jsonl, r2_bench_n1.json), and every GPU count
+        // then runs the same code.  Its in-kernel shared-latent phases use the kernel's own precision and operation
+        // order, so a run split into several bb_step calls (or resumed from a checkpoint) agrees with the uninterrupted
+        // one to rounding, not bitwise; BB_PERSIST=0 selects the launch pair, which is bitwise split-invariant.
         const char *pe = getenv("BB_PERSIST");
-        int want = pe ? atoi(pe) : (L.world > 1 ? 256 : 0);
+        int want = pe ? atoi(pe) : 256;
         if (!coop || !g.step_persist) want = 0;
         if (L.world > 1 && !xchg_on_) want = 0;
         if (want > 1) {

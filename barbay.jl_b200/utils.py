@@ -231,6 +231,15 @@ class MeanFieldPosterior:
                    _Transform(list(ranges_out)))
 
 
+def _decode(codes: np.ndarray, categories) -> "pd.api.extensions.ExtensionArray":
+    """categories[codes] as a pandas ``str`` column, decoded by Arrow (an object array of 7 * 10^6 Python strings
+    costs pandas 0.8 s to ingest, the dictionary decode 0.1 s); categories may contain None (missing)."""
+    import pyarrow as pa
+    arr = pa.DictionaryArray.from_arrays(pa.array(np.asarray(codes, dtype=np.int32)),
+                                         pa.array(list(categories), type=pa.large_string()))
+    return pd.array(arr.cast(pa.large_string()), dtype="str")
+
+
 def _slice(rng) -> slice:
     return slice(rng.start - 1, rng.stop - 1)      # 1-based UnitRange -> 0-based slice
 
@@ -290,8 +299,8 @@ def add_environment_info(df, var_groups, var_range, output: DataArrays, env_col)
     df[str(env_col)] = col
 
 
-def add_barcode_info(df, var_groups, var_range, output: DataArrays, genotype_col=None) -> None:
-    """utils.jl:1194-1279."""
+def _add_barcode_info_objects(df, var_groups, var_range, output: DataArrays, genotype_col=None) -> None:
+    """utils.jl:1194-1279, ids of any type (kept as they are in an object column)."""
     col = np.empty(len(df), dtype=object)
     bc = np.asarray(output.bc_ids, dtype=object)
     for name, rng in zip(var_groups, var_range):
@@ -318,6 +327,43 @@ def add_barcode_info(df, var_groups, var_range, output: DataArrays, genotype_col
             else:
                 col[s] = np.tile(np.repeat(bc, output.n_env), output.n_rep)
     df["id"] = col
+
+
+def add_barcode_info(df, var_groups, var_range, output: DataArrays, genotype_col=None) -> None:
+    """utils.jl:1194-1279.  The column is assembled as integer codes into one table of ids
+    ("N/A" | barcodes | neutrals | genotypes) and decoded once (see _decode)."""
+    genos = list(_unique_list(output.genotypes)) if genotype_col is not None else []
+    bc_ids, neu_ids = list(output.bc_ids), list(output.neutral_ids)
+    if not all(isinstance(x, str) for x in bc_ids + neu_ids + genos):
+        return _add_barcode_info_objects(df, var_groups, var_range, output, genotype_col)
+    table = ["N/A"] + bc_ids + neu_ids + genos
+    o_bc, o_neu, o_gen = 1, 1 + len(bc_ids), 1 + len(bc_ids) + len(neu_ids)
+    bc = np.arange(o_bc, o_bc + len(bc_ids), dtype=np.int32)
+    all_ids = np.concatenate([np.arange(o_neu, o_neu + len(neu_ids), dtype=np.int32), bc])
+    col = np.zeros(len(df), dtype=np.int32)
+    for name, rng in zip(var_groups, var_range):
+        s = _slice(rng)
+        if _model.POP_MARK in name:
+            col[s] = 0
+        elif name == _model.V_THETA and genotype_col is None:
+            col[s] = bc if output.n_env == 1 else np.repeat(bc, output.n_env)
+        elif name == _model.V_THETA:
+            col[s] = np.arange(o_gen, o_gen + len(genos), dtype=np.int32)
+        elif name == _model.V_LOGLAM:
+            if output.n_rep == 1:
+                col[s] = np.repeat(all_ids, _n_time_of(output, 0))
+            else:
+                col[s] = np.concatenate([np.repeat(all_ids, _n_time_of(output, r)) for r in range(output.n_rep)])
+        else:
+            if output.n_rep == 1 and output.n_env == 1:
+                col[s] = bc
+            elif output.n_rep == 1:
+                col[s] = np.repeat(bc, output.n_env)
+            elif output.n_env == 1:
+                col[s] = np.tile(bc, output.n_rep)
+            else:
+                col[s] = np.tile(np.repeat(bc, output.n_env), output.n_rep)
+    df["id"] = _decode(col, table)
 
 
 def process_hierarchical_samples(df: pd.DataFrame, output: DataArrays, n_samples: int, genotype_col=None,
@@ -380,16 +426,20 @@ def advi_to_df(data: pd.DataFrame, dist: MeanFieldPosterior, vars: list, *, id_c
         output = data_to_arrays(data, id_col=id_col, time_col=time_col, count_col=count_col,
                                 neutral_col=neutral_col, rep_col=rep_col, env_col=env_col,
                                 genotype_col=genotype_col)
-    vars = list(vars)
-    var_groups = [v.replace("[1]", "") for v in vars if "[1]" in str(v)]      # :1046
     var_range = dist.transform.ranges_out                                     # :1049
     df = pd.DataFrame({"mean": dist.dist.m, "std": dist.dist.σ})              # :1060
-    df["varname"] = vars
-    vartype = np.empty(len(df), dtype=object)
-    vartype[:] = "tmp"
+    if isinstance(vars, _model.VarNames):          # the names the engine's layout hands out: no Python string per row
+        var_groups = vars.groups
+        df["varname"] = vars.to_pandas()
+    else:
+        vars = list(vars)
+        var_groups = [v.replace("[1]", "") for v in vars if "[1]" in str(v)]  # :1046
+        df["varname"] = vars
+    types = ["tmp"] + sorted(set(_model.VARNAME_TO_VARTYPE.values()))
+    code = np.zeros(len(df), dtype=np.int32)
     for name, rng in zip(var_groups, var_range):                              # :1083-1093
-        vartype[_slice(rng)] = _model.VARNAME_TO_VARTYPE[name]
-    df["vartype"] = vartype
+        code[_slice(rng)] = types.index(_model.VARNAME_TO_VARTYPE[name])
+    df["vartype"] = _decode(code, types)
     if rep_col is not None:
         add_replicate_info(df, var_groups, var_range, output, rep_col)
     if env_col is not None:
