@@ -92,11 +92,7 @@ __device__ __forceinline__ Pack<double, 1> pk_exp(Pack<double, 1> x) { return {e
 __device__ __forceinline__ Pack<double, 2> pk_exp(Pack<double, 2> x) { return {exp(x.a), exp(x.b)}; }
 __device__ __forceinline__ Pack<float, 2> pk_exp(Pack<float, 2> x) {
     const Pack<float, 2> y = x * pk_bc<float, 2>(1.4426950408889634f);
-#ifdef BB_EXPERIMENT_NOEXP      /* timing experiment only (wrong numbers): is the step bound by the XU pipe? */
-    return y * y;
-#else
     return pk_make(fast_ex2(pk_get<0>(y)), fast_ex2(pk_get<1>(y)));
-#endif
 }
 // e^(s x) with the scale folded into the log2(e) multiply
 __device__ __forceinline__ Pack<float, 1> pk_exp_scaled(Pack<float, 1> x, float s) {

@@ -365,11 +365,13 @@ def roofline_of(cx: Ctx, eng, steps_ms_per_step, n_prof, peak, peak_src, key, no
     return r
 
 
-def sub_measure(cx: Ctx, cfg, K, dtype, opt, peak, steps=200):
-    """One extra configuration on one GPU: step time, algorithmic GB/s of the whole step, fraction of peak."""
+def sub_measure(cx: Ctx, cfg, K, dtype, opt, peak, steps=200, sharded=False):
+    """One extra configuration: step time, algorithmic GB/s of the whole step, fraction of peak.  sharded=False: on one
+    GPU; sharded=True (multi-GPU runs): the same total problem sharded over all ranks (strong scaling), time = max over
+    ranks, bytes and fraction per GPU."""
     model, da = make_workload(cfg)
     shape, n_units = count_shape(da)
-    eng = cx.engine(da, model, K, dtype, opt, sharded=False)
+    eng = cx.engine(da, model, K, dtype, opt, sharded=sharded)
     ms, _ = cx.time_steps(eng, steps, 10)
     alg = eng.algorithmic_bytes_per_step
     plane = eng.data_plane()
@@ -452,6 +454,9 @@ def run_ours(args, emit):
                         "breakdown_us": weng.persist_stats() if weng.data_plane()["persistent"] else None}
         weng.close()
         del wda
+        # the other BASELINE configurations (round-1 kernels, exchange inside tail_kernel), sharded over the same ranks
+        extras["configs_sharded"] = {f"cfg{c}": sub_measure(cx, c, K, args.dtype, args.opt, peak, sharded=True)
+                                     for c in (3, 4, 5)}
 
     # ---- end to end through the public API with HOST buffers: one complete advi()-equivalent call
     # (bb_create: pack + H2D of counts / maps -> [comm] -> init -> optimiser -> n steps -> ELBO read-back ->

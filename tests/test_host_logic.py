@@ -149,3 +149,34 @@ def test_synthetic_configs_shapes(bb):
     df = bb.synth.to_tidy(bb.synth.config(2, scale=0.0005)[1])
     back = bb.utils.data_to_arrays(df)
     assert np.array_equal(back.bc_count, bb.synth.config(2, scale=0.0005)[1].bc_count)
+
+
+@pytest.mark.parametrize("model", list(FIXTURES))
+def test_lazy_variable_names_equal_the_list_the_reference_builds(bb, model):
+    """`layout.var_names` is a lazy sequence (7 * 10^6 Python strings at BASELINE size cost more than the fit): it must
+    behave like the list of src/vi.jl:184-198, and `advi_to_df` must produce the same frame -- values and dtypes --
+    from it (vectorised Arrow path) as from the plain list (generic path); integer ids keep their type."""
+    df, cols = load_fixture(model)
+    da = bb.utils.data_to_arrays(df, **cols)
+    lay = _layout(bb, model, da)
+    names = lay.var_names
+    plain = [f"{g.name}[{i}]" for g in lay.groups for i in range(1, g.length + 1)]
+    assert len(names) == len(plain) == lay.n_latent and names == plain and list(names) == plain
+    assert names[0] == plain[0] and names[-1] == plain[-1] and names[3:9] == plain[3:9]
+    assert names.groups == [g.name for g in lay.groups]
+    assert list(names.to_pandas()) == plain
+    with pytest.raises(IndexError):
+        names[len(plain)]
+    q = _fake_q(bb, lay, np.random.default_rng(2))
+    fast = bb.utils.advi_to_df(df, q, names, n_samples=100, seed=3, **cols)
+    slow = bb.utils.advi_to_df(df, q, plain, n_samples=100, seed=3, **cols)
+    assert fast.equals(slow) and list(fast.dtypes) == list(slow.dtypes)
+    # integer barcode ids: the id column keeps the objects as they are
+    df_int = df.copy()
+    codes = {b: i for i, b in enumerate(sorted(df_int["barcode"].unique()))}
+    df_int["barcode"] = df_int["barcode"].map(codes)
+    da_i = bb.utils.data_to_arrays(df_int, **cols)
+    out_i = bb.utils.advi_to_df(df_int, q, names, n_samples=50, seed=3, output=da_i, **cols)
+    ids = [x for x in out_i["id"] if not (isinstance(x, str) and x == "N/A")]
+    assert any(isinstance(x, (int, np.integer)) for x in ids)                       # barcode rows: still integers
+    assert not any(isinstance(x, str) and x.isdigit() for x in ids)                 # ... none turned into a string
