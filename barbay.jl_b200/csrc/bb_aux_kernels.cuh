@@ -305,8 +305,9 @@ __device__ __forceinline__ void shared_body(const SharedArgs<real> &a, double *s
             ctx[2 * a.tmax + t] = (real)wbar;
         }
     }
-    // ---- phase 1
-    for (int j = tid; j < a.R * a.K * a.tmax && !a.aw_d; j += nthr) {
+    // ---- phase 1 (ratio (n, t) paired with population latent t; nothing to do when the as-written branch above ran)
+    const int n_phase1 = a.aw_d ? 0 : a.R * a.K * a.tmax;
+    for (int j = tid; j < n_phase1; j += nthr) {
         const int t = j % a.tmax, k = (j / a.tmax) % a.K, r = j / (a.tmax * a.K);
         const int nt = a.nt[r];
         u_t[j] = 0.0; lp_t[j] = 0.0;
