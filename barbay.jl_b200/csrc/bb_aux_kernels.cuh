@@ -472,6 +472,8 @@ template <typename real> struct HyperArgs {
     vec2<real> *gout;            // [H]
     double *epart;               // [gridDim.x][K+1] or nullptr
     OptArgsT<real> opt;
+    int prep_next;               // hyper_update_kernel: also draw (z, eps) of step + 1 from the updated theta (saves the
+                                 // hyper_prep launch of the next step)
 };
 
 template <typename real>
@@ -549,6 +551,16 @@ __global__ void __launch_bounds__(BLOCK) hyper_update_kernel(const HyperArgs<rea
         finish_latent<real>(a.opt, invK, sg, sge, th, a.hy_acc[h], a.hy_th + h, a.hy_acc + h,
                             a.hy_ring ? a.hy_ring + h : nullptr,
                             a.gout ? a.gout + h : nullptr);
+        if (a.prep_next) {
+            // what hyper_prep_kernel would do at the head of the next step, from the theta just written (this thread has
+            // read all of zeps[.][h] above; nobody else touches column h)
+            const vec2<real> tn = a.hy_th[h];
+            const real sn = softplus_only<real>(tn.y);
+            for (int k = 0; k < a.K; ++k) {
+                const real e = stream_normal<real>(STREAM_HYPER, a.gid0 + (uint32_t)h, (uint32_t)k, a.step + 1u, a.key);
+                a.zeps[(size_t)k * a.H + h] = mk2<real>(fma(sn, e, tn.x), e);
+            }
+        }
     }
     if (want_elbo) {
         __syncthreads();

@@ -241,6 +241,7 @@ template <typename real> class Engine : public EngineBase {
     int ring_slot_ = 0;
     bool fused_ok_ = false;        // every launch group has a fused step kernel that fits
     long long part_step_ = -1;     // step whose pass-1 partials already sit in part_ (fused layout) / xpart_, or -1
+    long long hy_zeps_step_ = -1;  // step whose hyper-latent draws already sit in zeps_ (made by hyper_update_kernel), or -1
     bool part_is_x_ = false;       // ... in xpart_ (written by the step kernel)
     bool stepk_ok_ = false;        // every launch group (there is one: R == 1) has a step kernel that fits
     int persist_chunk_ = 0;        // steps per persistent launch (0: persistent mode off)
@@ -621,6 +622,7 @@ template <typename real> void Engine<real>::size_pass2() {
         }
     }
     part_step_ = -1;
+    hy_zeps_step_ = -1;
 }
 
 template <typename real> ColArrays<real> Engine<real>::col_arrays(bool ring_base) const {
@@ -642,6 +644,7 @@ template <typename real> ColArrays<real> Engine<real>::col_arrays(bool ring_base
 // ------------------------------------------------------------------ parameters
 template <typename real> void Engine<real>::init_params(uint64_t seed) {
     part_step_ = -1;
+    hy_zeps_step_ = -1;
     const PhiloxKey ikey = philox_key(seed);
     auto run = [&](r2 *dst, const int *map, size_t n) {
         if (!n) return;
@@ -670,6 +673,7 @@ template <typename real> void Engine<real>::init_params(uint64_t seed) {
 
 template <typename real> void Engine<real>::set_params(const double *mu, const double *omega) {
     part_step_ = -1;
+    hy_zeps_step_ = -1;
     hostvec_a_.ensure(L.D); hostvec_b_.ensure(L.D);
     BB_CUDA(cudaMemcpyAsync(hostvec_a_.p, mu, sizeof(double) * L.D, cudaMemcpyHostToDevice, stream_));
     BB_CUDA(cudaMemcpyAsync(hostvec_b_.p, omega, sizeof(double) * L.D, cudaMemcpyHostToDevice, stream_));
@@ -816,10 +820,14 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         ha.gout = m.gout ? gout_hy_.p : nullptr;
         ha.epart = m.want_elbo ? hy_epart_.p : nullptr;
         ha.opt = opt_args<real>(m.update);
-        if (L.H > 0) {
+        // the draws of this step are already there when the previous step's hyper_update_kernel made them
+        const bool have_zeps = !m.sup && hy_zeps_step_ == (long long)m.step;
+        ha.prep_next = (m.update && !m.sup && !m.z_direct && !getenv("BB_NO_HYPER_MERGE")) ? 1 : 0;
+        if (L.H > 0 && !have_zeps) {
             hyper_prep_kernel<real><<<hyblocks_, BLOCK, 0, stream_>>>(ha);
             ++launches;
         }
+        hy_zeps_step_ = ha.prep_next ? (long long)m.step + 1 : -1;
     }
     // ---- pass 1
     if (tev_pos_ >= 0) BB_CUDA(cudaEventRecord(tev_[tev_pos_++], stream_));
@@ -1303,6 +1311,7 @@ template <typename real> void Engine<real>::set_state(const double *s) {
     step_count = (long long)s[0];
     ring_slot_ = (int)s[1];
     part_step_ = -1;
+    hy_zeps_step_ = -1;
 }
 
 // ------------------------------------------------------------------ comm
@@ -1449,6 +1458,7 @@ template <typename real> void Engine<real>::check_step_sync() {
         if (step_sync_.p) BB_CUDA(cudaMemset(step_sync_.p, 0, sizeof(StepSync)));
         if (xchg_err_.p) BB_CUDA(cudaMemset(xchg_err_.p, 0, sizeof(int)));
         part_step_ = -1;
+    hy_zeps_step_ = -1;
         throw std::runtime_error("peer-memory exchange timed out: a rank did not post its partial sums; the steps of "
                                  "this call are incomplete");
     }
