@@ -1018,9 +1018,18 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
             cfg.attrs = at; cfg.numAttrs = 1;
             BB_CUDA(cudaLaunchKernelEx(&cfg, g.ks.pass2_fused, a));
         } else {
+            // also a programmatic dependent of the kernel ahead of it (the tail kernel triggers early): its prologue
+            // -- direction table, first tile of theta -- runs beside the shared-latent phases (hierarchical models:
+            // -2 us per step)
             const KernelSet<real> &ks = m.sup ? g.ks_sup : g.ks;
-            if (elbo) ks.pass2_elbo<<<g.p2blocks, BLOCK, g.p2smem_elbo, stream_>>>(a);
-            else ks.pass2<<<g.p2blocks, BLOCK, g.p2smem, stream_>>>(a);
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(g.p2blocks); cfg.blockDim = dim3(BLOCK); cfg.stream = stream_;
+            cfg.dynamicSmemBytes = elbo ? g.p2smem_elbo : g.p2smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = getenv("BB_NO_PDL") ? 0 : 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            BB_CUDA(cudaLaunchKernelEx(&cfg, elbo ? ks.pass2_elbo : ks.pass2, a));
         }
         ++launches;
     }
