@@ -108,6 +108,16 @@ def test_product_layout_probe_validation_messages():
         bb.Engine(rag, "replicate_fitness_normal", rank=0, world=2, probe_only=True)
     bb.Engine(rag, "replicate_fitness_normal", probe_only=True)
     bb.Engine(rag, "replicate_fitness_normal", rank=1, world=2, probe_only=True, corrected_ragged=True)
+    # multienv x replicate with unequal T: one environment list per replicate (…replicates.jl:449-472)
+    m5 = "multienv_replicate_fitness_normal"
+    envs = [["a", "b", "a", "c"], ["a", "c", "b"]]
+    rag5, _ = bb.synth.simulate(m5, n_neutral=4, n_bc=9, n_time=[4, 3], envs=envs, seed=1)
+    pr = bb.Engine(rag5, m5, {"envs": envs}, probe_only=True)
+    assert pr.owned.min() == 1 and pr.owned.max() == 1 and pr.D == 2 * 5 + 3 * 9 + 3 * 3 * 9 * 2 + 7 * 13
+    with pytest.raises(bb.BarBayError, match="one environment list per replicate"):
+        bb.Engine(rag5, m5, {"envs": ["a", "b", "a", "c"]}, probe_only=True)
+    with pytest.raises(bb.BarBayError, match="for all replicates"):
+        bb.Engine(rag5, m5, {"envs": [["a", "b", "a", "c"], ["a", "c"]]}, probe_only=True)
     da, _ = bb.synth.simulate("fitness_normal", n_neutral=4, n_bc=9, n_time=4, seed=1)
     with pytest.raises(bb.BarBayError, match="rank, world"):
         bb.Engine(da, "fitness_normal", rank=3, world=2, probe_only=True)
