@@ -38,6 +38,30 @@ def test_advi_uneven_replicates(bb):
     assert isinstance(out, pd.DataFrame)
 
 
+def test_advi_uneven_replicates_pairings_and_multienv(bb):
+    """Unequal T per replicate through the public call: the reference's neutral pairing as written (default) and the
+    corrected one give different fits; the multienv x replicate model takes the per-replicate environment lists that
+    data_to_arrays builds, and the frame labels the population rows with every replicate's own envs[2:end]."""
+    df, cols = load_fixture("replicate_fitness_normal")
+    df = uneven_replicates(df)
+    kw = dict(model=bb.model.replicate_fitness_normal, advi=bb.ADVI(2, 300), opt=bb.DecayedADAGrad(), verbose=False,
+              n_posterior_samples=100, seed=5, **cols)
+    a = bb.advi(data=df, **kw)
+    b = bb.advi(data=df, corrected_ragged=True, **kw)
+    assert a.shape == b.shape and np.isfinite(a["mean"]).all() and np.isfinite(b["mean"]).all()
+    pa, pb = a[a.vartype == "pop_mean_fitness"]["mean"].to_numpy(), b[b.vartype == "pop_mean_fitness"]["mean"].to_numpy()
+    assert np.max(np.abs(pa - pb)) > 1e-6          # same data, same noise lattice: only the pairing differs
+    with pytest.raises(bb.BarBayError, match="single shard"):
+        bb.Engine(bb.utils.data_to_arrays(df, **cols), "replicate_fitness_normal", rank=0, world=2)
+    dfe = df.assign(env=df.time.map({1: "A", 2: "A", 3: "B", 4: "C", 5: "B"}))
+    out = bb.advi(data=dfe, model=bb.model.multienv_replicate_fitness_normal, advi=bb.ADVI(1, 50), verbose=False,
+                  n_posterior_samples=100, env_col="env", **cols)
+    pop = out[out.vartype == "pop_mean_fitness"]
+    assert list(pop["env"]) == ["A", "B", "C", "B", "A", "B", "C"]       # R1: envs[2:5], R2 (4 time points): envs[2:4]
+    assert set(out["vartype"]) >= {"bc_hyperfitness", "bc_fitness", "pop_std", "log_poisson"}
+    assert np.isfinite(out["mean"]).all() and (out["std"] > 0).all()
+
+
 def test_advi_csv_output(bb, tmp_path):
     """test/vi_tests.jl:213-236: with outputname the call returns nothing and writes <name>.csv."""
     df, _ = load_fixture("fitness_normal")
