@@ -86,6 +86,8 @@ SYMBOLS = [
     ("bb_data_plane", C.c_int, [_P, C.POINTER(C.c_int32)]),
     ("bb_derived_fitness", C.c_int, [_P, C.c_int32, C.c_uint64, _D, _D]),
     ("bb_n_derived", C.c_int64, [_P]),
+    ("bb_naive_prior", C.c_int, [C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                 C.c_int32, _D, _D, _D]),
     ("bb_peer_handle", C.c_int, [_P, C.c_char * 64]),
     ("bb_peer_attach", C.c_int, [_P, C.c_char_p, C.c_int32]),
     ("bb_comm_unique_id", C.c_int, [C.c_char * 128]),

@@ -7,6 +7,7 @@
 
 #include "../../include/barbay_b200.h"
 #include "bb_multi.cuh"
+#include "bb_naive.cuh"
 
 struct bb_handle {
     bb::EngineBase *eng = nullptr;
@@ -233,6 +234,26 @@ int bb_peer_attach(bb_handle *h, const char *handles, int32_t n) {
         if (!handles) throw std::runtime_error("bb_peer_attach: NULL argument");
         e.peer_attach(handles, n);
     });
+}
+int bb_naive_prior(const int64_t *bc_count, int32_t n_rep, const int32_t *n_time, int32_t n_neutral, int32_t n_bc,
+                   int32_t device, double *s_pop_prior, double *logsig_pop_prior, double *loglam_prior) {
+    try {
+        int ndev = 0;
+        cudaError_t ce = cudaGetDeviceCount(&ndev);
+        if (ce != cudaSuccess || ndev == 0)
+            throw std::runtime_error(std::string("no CUDA device available (") + cudaGetErrorString(ce) +
+                                     "); barbay_b200 has no CPU fallback");
+        if (device >= ndev) throw std::runtime_error("bb_naive_prior: no such device");
+        DeviceGuard g(device);
+        bb::naive_prior_device(bc_count, n_rep, n_time, n_neutral, n_bc, s_pop_prior, logsig_pop_prior, loglam_prior,
+                               nullptr);
+        g_create_error.clear();
+        return 0;
+    } catch (const std::exception &e) {
+        g_create_error = e.what();
+        cudaGetLastError();
+        return 1;
+    }
 }
 int bb_comm_unique_id(char id[128]) {
     try {

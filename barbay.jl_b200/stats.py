@@ -29,10 +29,12 @@ def _finite_mean_std(x: np.ndarray, axis: int):
 
 
 def naive_prior(data: pd.DataFrame, *, id_col="barcode", time_col="time", count_col="count",
-                neutral_col="neutral", rep_col=None, pseudocount: int = 1, mutate: bool = True) -> dict:
+                neutral_col="neutral", rep_col=None, pseudocount: int = 1, mutate: bool = True,
+                device: int | None = None) -> dict:
     """Returns ``{"s_pop_prior", "logσ_pop_prior", "logλ_prior"}`` -- vectors of prior means in the
     latent order of the models (population vectors: time fastest, then replicate; logλ: ``vec`` of the
-    count array)."""
+    count array).  ``device`` (a CUDA ordinal, -1 = current): the arithmetic runs on the GPU from the
+    packed count array (``bb_naive_prior``, csrc/bb_naive.cuh) instead of in numpy."""
     if mutate:
         data[count_col] = data[count_col] + pseudocount                     # stats.jl:1185 (mutates the caller's frame)
         frame = data
@@ -40,6 +42,8 @@ def naive_prior(data: pd.DataFrame, *, id_col="barcode", time_col="time", count_
         frame = data.assign(**{count_col: data[count_col] + pseudocount})
     da = _utils.data_to_arrays(frame, id_col=id_col, time_col=time_col, count_col=count_col,
                                neutral_col=neutral_col, rep_col=rep_col)
+    if device is not None:
+        return naive_prior_packed(da, device=device)
     N = da.n_neutral
     if isinstance(da.bc_count, list):                                       # unequal T per replicate :1227-1249
         means, stds, loglam = [], [], []
@@ -61,6 +65,35 @@ def naive_prior(data: pd.DataFrame, *, id_col="barcode", time_col="time", count_
         Rf = np.log(R.astype(np.float64))
         logl = Rf.T.reshape(-1) if R.ndim == 2 else Rf.transpose(2, 1, 0).reshape(-1)
     return {"s_pop_prior": -mean, "logσ_pop_prior": -std, "logλ_prior": logl}
+
+
+def naive_prior_packed(da, *, device: int = -1) -> dict:
+    """``naive_prior`` of already packed data (``utils.data_to_arrays`` of the frame WITH the pseudocount
+    added) on the GPU: one H2D copy of the counts, three kernels (exact integer totals, ``log`` of every
+    count, mean / sd of the neutral log-frequency ratios), three D2H copies.  No CPU fallback."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load()
+    if isinstance(da.bc_count, (list, tuple)):
+        mats = [np.asarray(m, dtype=np.int64) for m in da.bc_count]
+        n_time = [m.shape[0] for m in mats]
+        flat = np.concatenate([m.T.reshape(-1) for m in mats])              # each T_r x B column-major
+    else:
+        R = np.asarray(da.bc_count, dtype=np.int64)
+        n_time = [R.shape[0]] * (1 if R.ndim == 2 else R.shape[2])
+        flat = R.T.reshape(-1) if R.ndim == 2 else R.transpose(2, 1, 0).reshape(-1)
+    flat = np.ascontiguousarray(flat)
+    nt = np.asarray(n_time, dtype=np.int32)
+    n_pop = int(nt.sum()) - nt.size
+    s_pop, lsig, logl = np.empty(n_pop), np.empty(n_pop), np.empty(flat.size)
+    D = C.POINTER(C.c_double)
+    rc = lib.bb_naive_prior(flat.ctypes.data_as(C.POINTER(C.c_int64)), nt.size, nt.ctypes.data_as(C.POINTER(C.c_int32)),
+                            int(da.n_neutral), int(da.n_bc), int(device), s_pop.ctypes.data_as(D),
+                            lsig.ctypes.data_as(D), logl.ctypes.data_as(D))
+    if rc != 0:
+        raise _lib.BarBayError(lib.bb_last_error(None).decode())
+    return {"s_pop_prior": s_pop, "logσ_pop_prior": lsig, "logλ_prior": logl}
 
 
 def prior_matrices(prior: dict, s_pop_std: float = 0.05, logsig_pop_std: float = 1.0, loglam_std: float = 3.0) -> dict:

@@ -189,6 +189,17 @@ int bb_persist_stats(bb_handle *h, double out[16]);
 int bb_derived_fitness(bb_handle *h, int32_t n_samples, uint64_t seed, double *median, double *sd);
 int64_t bb_n_derived(const bb_handle *h);
 
+/* BarBay.stats.naive_prior (src/stats.jl:1175-1359) on the device, from the packed counts: the empirical priors the
+ * documented workflow computes before every fit (docs/src/examples.md:121-140).  bc_count / n_rep / n_time /
+ * n_neutral / n_bc as in bb_desc, the counts ALREADY incremented by the pseudocount (the reference adds it to the
+ * caller's frame before packing, stats.jl:1185).  Outputs (caller-allocated): s_pop_prior and logsig_pop_prior,
+ * sum_r (n_time[r] - 1) entries each, time fastest then replicate (-mean and -sd of the neutral log-frequency ratios
+ * without their +-Inf entries, :1298, :1338); loglam_prior = log.(bc_count)[:], sum_r n_time[r] * (n_neutral + n_bc)
+ * entries in the memory order of bc_count (:1345-1352).  device: CUDA ordinal, -1 = current.  No handle is needed;
+ * errors are reported through bb_last_error(NULL). */
+int bb_naive_prior(const int64_t *bc_count, int32_t n_rep, const int32_t *n_time, int32_t n_neutral, int32_t n_bc,
+                   int32_t device, double *s_pop_prior, double *logsig_pop_prior, double *loglam_prior);
+
 /* Which kernels / data plane this handle runs: out = {packed step kernel in use, steps per persistent launch
  * (0: one launch pair per step), NVLink peer-memory exchange on, NCCL communicator present, resident CTAs per SM of
  * the step kernel, its staging buffers (1 / 2), accumulators staged (0 / 1), its grid size}. */
