@@ -456,7 +456,8 @@ template <typename real> struct HyperArgs {
     uint32_t gid0;               // global hyper index of local hyper 0 (noise lattice slot)
     vec2<real> *hy_th, *hy_acc, *hy_ring;   // [H]; ring [n][H]
     const vec2<real> *hy_pr;     // (mean, 1/var) [H]
-    vec2<real> *zeps;            // [K][H] (z, eps)
+    vec2<real> *zeps;            // (z, eps) of hyper latent h, sample k at [k * hz_k + h * hz_h]
+    int hz_k, hz_h;              // (H, 1): sample-major -- (1, K): a latent's K draws contiguous (scattered member columns)
     PhiloxKey key;
     uint32_t step;
     const real *eps_hy;          // supplied noise [K][H] or nullptr
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(BLOCK) hyper_prep_kernel(const HyperArgs<real>
                                 : stream_normal<real>(STREAM_HYPER, a.gid0 + (uint32_t)h, (uint32_t)k, a.step,
                                                       a.key);
         const real z = a.z_direct ? e : fma(sigma, e, th.x);
-        a.zeps[(size_t)k * a.H + h] = mk2<real>(z, e);
+        a.zeps[(size_t)k * a.hz_k + (size_t)h * a.hz_h] = mk2<real>(z, e);
     }
 }
 
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(BLOCK) hyper_update_kernel(const HyperArgs<rea
             }
         }
         for (int k = 0; k < a.K; ++k) {
-            const vec2<real> ze = a.zeps[(size_t)k * a.H + h];
+            const vec2<real> ze = a.zeps[(size_t)k * a.hz_k + (size_t)h * a.hz_h];
             const real dz = ze.x - pr.x;
             const real gp = -dz * pr.y;
             sg += gp; sge = fma(gp, ze.y, sge);
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(BLOCK) hyper_update_kernel(const HyperArgs<rea
             const real sn = softplus_only<real>(tn.y);
             for (int k = 0; k < a.K; ++k) {
                 const real e = stream_normal<real>(STREAM_HYPER, a.gid0 + (uint32_t)h, (uint32_t)k, a.step + 1u, a.key);
-                a.zeps[(size_t)k * a.H + h] = mk2<real>(fma(sn, e, tn.x), e);
+                a.zeps[(size_t)k * a.hz_k + (size_t)h * a.hz_h] = mk2<real>(fma(sn, e, tn.x), e);
             }
         }
     }

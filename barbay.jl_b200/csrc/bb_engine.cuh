@@ -241,6 +241,7 @@ template <typename real> class Engine : public EngineBase {
     int ring_slot_ = 0;
     bool fused_ok_ = false;        // every launch group has a fused step kernel that fits
     long long part_step_ = -1;     // step whose pass-1 partials already sit in part_ (fused layout) / xpart_, or -1
+    int hz_k_ = 0, hz_h_ = 1;      // strides of the hyper-latent draws in zeps_: sample-major [K][H] unless BB_HZ_TRANSPOSE=1 ([H][K])
     long long hy_zeps_step_ = -1;  // step whose hyper-latent draws already sit in zeps_ (made by hyper_update_kernel), or -1
     bool part_is_x_ = false;       // ... in xpart_ (written by the step kernel)
     bool stepk_ok_ = false;        // every launch group (there is one: R == 1) has a step kernel that fits
@@ -348,6 +349,7 @@ template <typename real> Engine<real>::Engine(const bb_desc &d) {
         hgroup_.upload(L.hgroup);
         csr_off_.upload(L.csr_off); csr_mem_.upload(L.csr_mem);
         zeps_.alloc((size_t)L.K * std::max(L.H, 1));
+        if (getenv("BB_HZ_TRANSPOSE")) { hz_k_ = 1; hz_h_ = L.K; } else { hz_k_ = std::max(L.H, 1); hz_h_ = 1; }
         hcontrib_.alloc((size_t)L.E * L.cpad);
         hyblocks_ = cdiv(std::max(L.H, 1), BLOCK);
         hy_epart_.alloc((size_t)hyblocks_ * (L.K + 1));
@@ -812,7 +814,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         ha.H = L.H; ha.K = L.K; ha.gid0 = L.hy_gid0;
         ha.hy_th = hy_th_.p; ha.hy_acc = hy_acc_.p;
         ha.hy_ring = hy_ring_.p ? hy_ring_.p + (size_t)ring_slot_ * L.H : nullptr; ha.hy_pr = hy_pr_.p;
-        ha.zeps = zeps_.p; ha.key = pkey; ha.step = m.step;
+        ha.zeps = zeps_.p; ha.hz_k = hz_k_; ha.hz_h = hz_h_; ha.key = pkey; ha.step = m.step;
         ha.eps_hy = m.sup ? sup_hy_.p : nullptr; ha.z_direct = m.z_direct ? 1 : 0;
         ha.csr_off = csr_off_.p; ha.csr_mem = csr_mem_.p; ha.hcontrib = hcontrib_.p;
         ha.dump_hcontrib = m.dump ? dump_hc_.p : nullptr; ha.dump_stride = (long long)L.E * L.cpad;
@@ -848,7 +850,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
             a.segs = g.p1segs; a.cols = C; a.K = L.K; a.acc_slots = g.kchunk; a.ne = L.E;
             for (int t = 0; t < MAX_NT_DYN; ++t) a.env_of_t[t] = g.env_of_t[t];
             a.key = pkey; a.step = m.step;
-            a.hy_zeps = zeps_.p; a.H = L.H;
+            a.hy_zeps = zeps_.p; a.H = L.H; a.hz_k = hz_k_; a.hz_h = hz_h_;
             a.part = gpart;
             a.pv = g.pv; a.sup = sup; a.nbuf = g.p1nbuf;
             (m.sup ? g.ks_sup.pass1 : g.ks.pass1)<<<g.p1blocks, BLOCK, g.p1smem, stream_>>>(a);
@@ -938,7 +940,7 @@ template <typename real> void Engine<real>::run_pipeline(const RunMode &m) {
         a.segs = g.p2segs; a.cols = C; a.K = L.K; a.ne = L.E;
         for (int t = 0; t < MAX_NT_DYN; ++t) a.env_of_t[t] = g.env_of_t[t];
         a.key = pkey; a.step = m.step;
-        a.hy_zeps = zeps_.p; a.H = L.H;
+        a.hy_zeps = zeps_.p; a.H = L.H; a.hz_k = hz_k_; a.hz_h = hz_h_;
         a.ctx = ctx_.p; a.tmax_ctx = L.tmax;
         a.opt = opt_args<real>(m.update);
         a.gout_lam = m.gout ? gout_lam_.p : nullptr; a.gout_bc = m.gout ? gout_bc_.p : nullptr;

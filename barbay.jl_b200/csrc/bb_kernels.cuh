@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(BLOCK) pass1_kernel(const P1Args<real> a) {
 #pragma unroll
                         for (int e = 0; e < S::MAXE; ++e) {
                             if (e >= ne) break;
-                            zth_nxt[e] = a.hy_zeps[(size_t)k * a.H + hbase + e].x;
+                            zth_nxt[e] = a.hy_zeps[(size_t)k * a.hz_k + (size_t)(hbase + e) * a.hz_h].x;
                         }
                     }
                 }
@@ -865,7 +865,7 @@ pass2_kernel(const P2Args<real> a) {
 #pragma unroll
                     for (int e = 0; e < S::MAXE; ++e) {
                         if (e >= ne) break;
-                        hz_nxt[e] = a.hy_zeps[(size_t)k * a.H + hbase + e];
+                        hz_nxt[e] = a.hy_zeps[(size_t)k * a.hz_k + (size_t)(hbase + e) * a.hz_h];
                     }
                 }
             }

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 #include <stdexcept>
 #include <thread>
@@ -159,8 +160,12 @@ void build_layout(const bb_desc &d, Layout &L) {
     L.mperm.resize(L.M);
     std::iota(L.mperm.begin(), L.mperm.end(), 0);
     L.perm_identity = true;
-    if (genotype && L.world > 1) {
-        // make every genotype group contiguous and cut shards on group boundaries, so theta_g needs no exchange
+    // genotype model: make every genotype group contiguous -- shards are cut on group boundaries, so theta_g needs no
+    // exchange, and on one GPU too the lanes of a warp then share one or two groups: the per-sample fetch of the
+    // hyper latent's draw is a broadcast instead of 32 scattered sectors, and the member gather walks consecutive
+    // columns (BB_GENO_SORT=0 keeps the caller's order on one GPU: A/B measurements)
+    const char *gs = getenv("BB_GENO_SORT");
+    if (genotype && (L.world > 1 || !(gs && gs[0] == '0'))) {
         std::stable_sort(L.mperm.begin(), L.mperm.end(), [&](int a, int b) { return g0[a] < g0[b]; });
         for (int p = 0; p < L.M; ++p)
             if (L.mperm[p] != p) { L.perm_identity = false; break; }

@@ -73,8 +73,8 @@ template <typename real> struct P1Args {
     int env_of_t[MAX_NT_DYN];   // 0-based environment of time point t
     PhiloxKey key;
     uint32_t step;
-    const vec2<real> *hy_zeps;  // [K][H] (z, eps) of the hyper latents (hier)
-    int H;
+    const vec2<real> *hy_zeps;  // (z, eps) of hyper latent h, sample k at [k * hz_k + h * hz_h] (hier)
+    int H, hz_k, hz_h;
     double *part;          // [gridDim.x][K][pv] block partial sums (double)
     int pv;                // slots per sample: nt + 2 (nt - 1)
     int nbuf;              // staging buffers (2, or 1 when shared memory is short)
@@ -101,7 +101,7 @@ template <typename real> struct P2Args {
     PhiloxKey key;
     uint32_t step;
     const vec2<real> *hy_zeps;
-    int H;
+    int H, hz_k, hz_h;
     const real *ctx;       // [R][K][3][tmax]: (c_t - sbar_t), G_Lambda_t, wbar_t
     int tmax_ctx;
     OptArgsT<real> opt;
