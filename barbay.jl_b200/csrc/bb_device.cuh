@@ -61,27 +61,27 @@ __device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ft
 __device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// One 32-bit Philox word feeds one Box-Muller pair: the top 21 bits give the radius uniform
-// u = (j + 0.5) / 2^21 (largest radius 5.5 sigma), the low 11 bits the angle v = (a + 0.5) / 2^11.
-// With 2048 equispaced angles every trigonometric moment up to order 2047 equals that of a continuous
-// angle, so the pair is exactly uncorrelated with exact second and fourth moments; one Philox4x32-10
+// One 32-bit Philox word feeds one Box-Muller pair: the top 22 bits give the radius uniform
+// u = (j + 0.5) / 2^22 (largest radius 5.65 sigma), the low 10 bits the direction (cos, sin)(2 pi (a + 0.5) / 1024).
+// With 1024 equispaced directions every trigonometric moment up to order 1023 equals that of a continuous
+// angle, so the pair is exactly uncorrelated with exact second and fourth moments; one Philox4x32-7
 // call therefore yields eight standard normals.  Identical definition in fp32 and fp64.
-// fp32: the 2048 directions (cos, sin)(2 pi (a + 0.5) / 2048) come from a table instead of two MUFU ops
-// (the XU pipe is the scarce one in the column kernels): TRIG_N = 1024 entries sqrt(2 ln 2) (cos, sin),
-// rounded once from double, cover the half turn a & 1023; bit 10 of the word flips the sign of the radius.  `tab` is the table -- the
-// column kernels pass their shared-memory copy, everything else the global one of the key.
+// fp32: the directions come from a table instead of two MUFU ops (the step is dispatch-bound): TRIG_N = 1024
+// entries sqrt(2 ln 2) (cos, sin), rounded once from double, indexed by the low bits of the word as they are -- no
+// sign or quadrant fix-up (a half-turn table with a sign bit cost two more ALU instructions per word, 8 words per
+// column and sample: 4 % of the K = 8 step).  `tab` is the table -- the column kernels pass their shared-memory copy,
+// everything else the global one of the key.
 constexpr int TRIG_N = 1024;
 __device__ __forceinline__ void box_muller(uint32_t x, float &n0, float &n1, const float2 *tab) {
-    // j = x >> 11 dropped into the mantissa of 4.0f by one funnel shift: 4 + j 2^-21, minus (4 - 2^-22) -> (j + 0.5) / 2^21, exact
-    const float u = __uint_as_float(__funnelshift_r(x, 0x204u, 11)) - 3.9999997615814208984375f;
+    // j = x >> 10 dropped into the mantissa of 2.0f by one funnel shift: 2 + j 2^-22, minus (2 - 2^-23) -> (j + 0.5) / 2^22, exact
+    const float u = __uint_as_float(__funnelshift_r(x, 0x100u, 10)) - 1.99999988079071044921875f;
     const float radius = fast_sqrt(-fast_lg2(u));   // sqrt(-2 ln u) / sqrt(2 ln 2): the table carries the factor
-    const float rs = __uint_as_float(__float_as_uint(radius) | ((x << 21) & 0x80000000u));
     const float2 d = tab[x & (TRIG_N - 1)];
-    n0 = rs * d.x; n1 = rs * d.y;
+    n0 = radius * d.x; n1 = radius * d.y;
 }
 __device__ __forceinline__ void box_muller(uint32_t x, double &n0, double &n1, const float2 *) {
-    const double u = (static_cast<double>(x >> 11) + 0.5) * (1.0 / 2097152.0);
-    const double v = (static_cast<double>(x & 0x7ffu) + 0.5) * (1.0 / 2048.0);
+    const double u = (static_cast<double>(x >> 10) + 0.5) * (1.0 / 4194304.0);
+    const double v = (static_cast<double>(x & 0x3ffu) + 0.5) * (1.0 / 1024.0);
     const double radius = sqrt(-2.0 * log(u));
     double s, c;
     sincospi(2.0 * v, &s, &c);

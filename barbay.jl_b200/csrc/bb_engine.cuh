@@ -312,12 +312,12 @@ template <typename real> Engine<real>::Engine(const bb_desc &d) {
     for (auto &e : ev_) BB_CUDA(cudaEventCreate(&e));
 
     {
-        // directions sqrt(2 ln 2) (cos, sin)(2 pi (a + 0.5) / 2048), a < TRIG_N, rounded once to fp32
+        // directions sqrt(2 ln 2) (cos, sin)(2 pi (a + 0.5) / TRIG_N), a < TRIG_N (the full turn), rounded once to fp32
         // (the kernel's radius is sqrt(-log2 u); the factor turns it into sqrt(-2 ln u))
         std::vector<float2> t(TRIG_N);
         const double scale = std::sqrt(2.0 * std::log(2.0));
         for (int a = 0; a < TRIG_N; ++a) {
-            const double ang = 6.283185307179586476925286766559 * ((double)a + 0.5) / 2048.0;
+            const double ang = 6.283185307179586476925286766559 * ((double)a + 0.5) / (double)TRIG_N;
             t[a] = make_float2((float)(scale * std::cos(ang)), (float)(scale * std::sin(ang)));
         }
         trig_.upload(t);

@@ -166,12 +166,10 @@ __device__ __forceinline__ void column_noise_pack(Pack<real, W> (&eps)[MAXC], in
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
                 // box_muller (bb_device.cuh) of both samples; the uniform's offset is one packed add
-                const Pack<float, 2> u = pk_make(__uint_as_float(__funnelshift_r(xa[w], 0x204u, 11)),
-                                                 __uint_as_float(__funnelshift_r(xb[w], 0x204u, 11))) +
-                                         pk_bc<float, 2>(-3.9999997615814208984375f);
-                const float ra = fast_sqrt(-fast_lg2(pk_get<0>(u))), rb = fast_sqrt(-fast_lg2(pk_get<1>(u)));
-                const float sa = __uint_as_float(__float_as_uint(ra) | ((xa[w] << 21) & 0x80000000u));
-                const float sb = __uint_as_float(__float_as_uint(rb) | ((xb[w] << 21) & 0x80000000u));
+                const Pack<float, 2> u = pk_make(__uint_as_float(__funnelshift_r(xa[w], 0x100u, 10)),
+                                                 __uint_as_float(__funnelshift_r(xb[w], 0x100u, 10))) +
+                                         pk_bc<float, 2>(-1.99999988079071044921875f);
+                const float sa = fast_sqrt(-fast_lg2(pk_get<0>(u))), sb = fast_sqrt(-fast_lg2(pk_get<1>(u)));
                 const float2 da = tab[xa[w] & (TRIG_N - 1)], db = tab[xb[w] & (TRIG_N - 1)];
                 eps[8 * q + 2 * w] = pk_make(sa * da.x, sb * db.x);
                 eps[8 * q + 2 * w + 1] = pk_make(sa * da.y, sb * db.y);
@@ -871,21 +869,25 @@ __global__ void __launch_bounds__(BLOCK, BB_STEP_MIN_BLOCKS) step_kernel(const S
             double2 th = s_sh_th[tid], ac = s_sh_acc[tid];
             const real sigma = s_sig[tid], invK = real(1) / real(a.K);
             const real g0 = -(sg * invK), g1 = -((sge * invK + real(1) / sigma) * bb_exp((real)th.y - sigma));
-            const real q0 = g0 * g0, q1 = g1 * g1;
-            real d0, d1;
+            // the accumulators and the update itself in double, like shared_body (the tail kernel): the population
+            // latents' first gradients are ~1e6 (they sum over every barcode), and TruncatedADAGrad's running window sum
+            // in fp32 kept the cancellation residue of `sum - evicted` (~ulp(1e12)) for the rest of the run -- step
+            // sizes of the log-sigma latents off by large factors from the fourth step on (tests/_debug_trunc.py)
+            const double q0 = (double)g0 * (double)g0, q1 = (double)g1 * (double)g1;
+            double d0, d1;
             if (a.sa.opt.kind == 1) {
-                ac.x = fma((real)a.sa.opt.post, (real)ac.x, (real)a.sa.opt.tau * q0);
-                ac.y = fma((real)a.sa.opt.post, (real)ac.y, (real)a.sa.opt.tau * q1);
-                d0 = bb_sqrt((real)ac.x) + real(1e-8); d1 = bb_sqrt((real)ac.y) + real(1e-8);
+                ac.x = fma(a.sa.opt.post, ac.x, a.sa.opt.tau * q0);
+                ac.y = fma(a.sa.opt.post, ac.y, a.sa.opt.tau * q1);
+                d0 = sqrt(ac.x) + 1e-8; d1 = sqrt(ac.y) + 1e-8;
             } else {
-                ac.x = fmax((real)ac.x - (real)ring_old.x, real(0)) + q0;
-                ac.y = fmax((real)ac.y - (real)ring_old.y, real(0)) + q1;
-                if (blockIdx.x == 0) ring_wr[tid] = make_double2((double)q0, (double)q1);
-                d0 = (real)a.sa.opt.tau + bb_sqrt((real)ac.x) + real(1e-8);
-                d1 = (real)a.sa.opt.tau + bb_sqrt((real)ac.y) + real(1e-8);
+                ac.x = fmax(ac.x - ring_old.x, 0.0) + q0;
+                ac.y = fmax(ac.y - ring_old.y, 0.0) + q1;
+                if (blockIdx.x == 0) ring_wr[tid] = make_double2(q0, q1);
+                d0 = a.sa.opt.tau + sqrt(ac.x) + 1e-8;
+                d1 = a.sa.opt.tau + sqrt(ac.y) + 1e-8;
             }
-            th.x = (double)((real)th.x - (real)a.sa.opt.eta * g0 / d0);
-            th.y = (double)((real)th.y - (real)a.sa.opt.eta * g1 / d1);
+            th.x = th.x - a.sa.opt.eta * (double)g0 / d0;
+            th.y = th.y - a.sa.opt.eta * (double)g1 / d1;
             s_sh_th[tid] = th; s_sh_acc[tid] = ac;
             s_sig[tid] = softplus_only<real>((real)th.y);
         }

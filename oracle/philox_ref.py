@@ -54,9 +54,9 @@ def philox4x32(c0, c1, c2, c3, k0: int, k1: int, rounds: int = 10):
 
 
 def word_uniforms(x: np.ndarray):
-    """One Philox word -> (radius uniform from the top 21 bits, angle uniform from the low 11 bits)."""
-    u = ((x >> np.uint32(11)).astype(np.float64) + 0.5) / 2097152.0
-    v = ((x & np.uint32(0x7FF)).astype(np.float64) + 0.5) / 2048.0
+    """One Philox word -> (radius uniform from the top 22 bits, angle uniform from the low 10 bits)."""
+    u = ((x >> np.uint32(10)).astype(np.float64) + 0.5) / 4194304.0
+    v = ((x & np.uint32(0x3FF)).astype(np.float64) + 0.5) / 1024.0
     return u, v
 
 

@@ -194,8 +194,15 @@ def test_device_derived_fitness_rows_match_host_sampler(bb, model):
     assert len(a) > 0 and (a["varname"] == b["varname"]).all() and (a["id"] == b["id"]).all()
     sd = b["std"].to_numpy()
     assert np.max(np.abs(a["mean"].to_numpy() - b["mean"].to_numpy()) / sd) < 0.08
-    # exp(logτ) makes the draws heavy-tailed where the fit is still wide: the sample sd itself is noisy there
-    assert np.max(np.abs(a["std"].to_numpy() / sd - 1.0)) < 0.15 and np.median(np.abs(a["std"].to_numpy() / sd - 1.0)) < 0.03
+    # exp(logτ) makes the draws heavy-tailed where the fit is still wide and the sample sd itself noisy: its relative
+    # standard error is sqrt((kurtosis - 1) / 4n), kurtosis <= 3 exp(4 sd(logτ)^2) for a lognormal-scaled normal
+    # (0.7 % for a normal, 6 % at sd(logτ) = 1).  Two independent samplers, four standard errors, never below 15 %:
+    sd_tau = host.loc[host.vartype == "bc_deviations", "std"].to_numpy()
+    assert sd_tau.shape == sd.shape
+    se = np.sqrt((3.0 * np.exp(np.minimum(4.0 * sd_tau ** 2, 20.0)) - 1.0) / 4.0e4)
+    dev_sd = np.abs(a["std"].to_numpy() / sd - 1.0)
+    assert (dev_sd < np.maximum(0.15, 4.0 * np.sqrt(2.0) * se)).all(), (dev_sd, se)
+    assert np.median(dev_sd) < 0.03
     # the fitted rows themselves are untouched by the choice
     fa, fb = dev[dev.vartype != "bc_fitness"], host[host.vartype != "bc_fitness"]
     assert np.array_equal(fa["mean"].to_numpy(), fb["mean"].to_numpy())

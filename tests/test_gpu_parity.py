@@ -294,10 +294,11 @@ def test_truncated_adagrad_unstaged_ring_fp32_k8(bb, monkeypatch):
     model, K, n_steps = "fitness_normal", 8, 6
     res = {}
     for mode in ("fused", "unfused"):
-        if mode == "unfused":
+        for k in ("BB_NO_FUSE", "BB_NO_STEPK"):
+            monkeypatch.delenv(k, raising=False)
+        if mode == "unfused":                       # round-1 pass 1 + pass 2 pair: neither the step kernel nor the fused pass 2
             monkeypatch.setenv("BB_NO_FUSE", "1")
-        else:
-            monkeypatch.delenv("BB_NO_FUSE", raising=False)
+            monkeypatch.setenv("BB_NO_STEPK", "1")
         da, eng = _setup(bb, model, K, "f32")
         eng.init_params(5)
         mu0, om0 = eng.get_params()
@@ -308,4 +309,5 @@ def test_truncated_adagrad_unstaged_ring_fp32_k8(bb, monkeypatch):
     assert rel_err(res["fused"][0], res["unfused"][0]) < 2e-4 and rel_err(res["fused"][1], res["unfused"][1]) < 2e-4
     tr = advi_ref.advi_run(model, oracle_problem(da, model), n_steps, K, advi_ref.TruncatedADAGrad(0.1, 1.0, 3),
                            mu0, om0, seed=1234)
-    assert rel_err(res["fused"][0], tr.mu) < 2e-3 and rel_err(res["fused"][1], tr.omega) < 2e-3
+    # measured 2.5e-6 / 1.9e-5 (fp32 window sums); 2e-3 before the population latents' update moved to double
+    assert rel_err(res["fused"][0], tr.mu) < 3e-4 and rel_err(res["fused"][1], tr.omega) < 3e-4

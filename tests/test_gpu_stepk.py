@@ -56,9 +56,10 @@ def test_step_kernel_follows_oracle(bb, model, dtype, K, opt, monkeypatch):
         assert eng.step_count == n_steps
         eng.close()
     tr = advi_ref.advi_run(model, oracle_problem(da, model), n_steps, K, ref_opt, mu0, om0, seed=1234)
-    # fp32: AdaGrad's first steps are sign-like (delta ~ eta sign(g)), so a latent whose gradient is within rounding of
-    # zero moves visibly; TruncatedADAGrad (no decay of the window) shows it most
-    tol = 1e-8 if dtype == "f64" else (3e-3 if opt == "decayed" else 1e-2)
+    # fp32 (measured over these cases, tests/_debug_trunc.py): DecayedADAGrad <= 2.3e-7; TruncatedADAGrad <= 4.5e-5 -- the
+    # fp32 running window sum of the column latents keeps a cancellation residue of the evicted first steps.
+    # (Until the population latents' update moved to double in the persistent kernel this needed 1e-2.)
+    tol = 1e-8 if dtype == "f64" else (2e-6 if opt == "decayed" else 3e-4)
     for mode, (mu, om) in res.items():
         assert rel_err(mu, tr.mu) < tol and rel_err(om, tr.omega) < tol, (mode, rel_err(mu, tr.mu), rel_err(om, tr.omega))
     cross = 1e-10 if dtype == "f64" else tol
@@ -91,7 +92,7 @@ def test_step_kernel_many_tiles_and_groups(bb, dtype, monkeypatch):
             assert st["tails"] == 4, st          # (3 - 1) + (3 - 1) + 0 in-kernel tails
         eng.close()
     tr = advi_ref.advi_run(model, oracle_problem(da, model), n_steps, K, advi_ref.DecayedADAGrad(), mu0, om0, seed=99)
-    tol = 1e-8 if dtype == "f64" else 3e-3
+    tol = 1e-8 if dtype == "f64" else 1e-4
     for mode, (mu, om) in res.items():
         assert rel_err(mu, tr.mu) < tol and rel_err(om, tr.omega) < tol, (mode, rel_err(mu, tr.mu), rel_err(om, tr.omega))
 
