@@ -604,6 +604,24 @@ __global__ void scatter_pairs_kernel(vec2<real> *dst, const int *map, long long 
     dst[i] = m >= 0 ? mk2<real>((real)x[m], (real)y[m]) : mk2<real>((real)fill_x, (real)fill_y);
 }
 
+// TruncatedADAGrad, fp32: the running window sums rebuilt exactly from the window itself -- acc[i] = sum over the
+// n_slots ring slots of (g_mu^2, g_omega^2), in double and in slot order.  The running form s <- max(s - evicted, 0) + g^2
+// keeps, in fp32, a cancellation residue of size ulp(s) of every eviction; after the large squared gradients of the
+// first steps have left the window that residue can exceed the true sum.  The engine runs this at
+// window wraps (Engine::maybe_resum); upstream sums the window afresh at every step.
+template <typename real>
+__global__ void __launch_bounds__(256) ring_resum_kernel(const vec2<real> *ring, vec2<real> *acc, long long n_items,
+                                                          int n_slots) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    double sx = 0.0, sy = 0.0;
+    for (int s = 0; s < n_slots; ++s) {
+        const vec2<real> v = ring[(size_t)s * (size_t)n_items + (size_t)i];
+        sx += (double)v.x; sy += (double)v.y;
+    }
+    acc[i] = mk2<real>((real)sx, (real)sy);
+}
+
 template <typename real>
 __global__ void gather_pairs_kernel(const vec2<real> *src, const int *map, long long n, double *x, double *y,
                                     int softplus_y) {

@@ -251,6 +251,8 @@ template <typename real> class Engine : public EngineBase {
     int step_gsize_ = 32;
     void alloc_xchg();
     void check_step_sync();
+    bool resum_active() const;
+    void maybe_resum();
     std::vector<Group> groups_;
     int p1blocks_total_ = 0, p2blocks_total_ = 0, hyblocks_ = 0;
 
@@ -1163,6 +1165,28 @@ template <typename real> void Engine<real>::get_noise(long long step, double *ep
     BB_CUDA(cudaGetLastError());
 }
 
+// fp32 TruncatedADAGrad: rebuild the window sums of the column and hyper latents from the ring at window wraps -- the
+// first four wraps (the large first gradients leave the window there) and every eighth after them: n ring reads per
+// latent, amortised below 1 % of a step.  Depends on the step counter only, so split, resumed and sharded runs re-sum
+// at the same steps.  BB_NO_RESUM=1: off (the behaviour until the last build of round 2).
+template <typename real> bool Engine<real>::resum_active() const {
+    return std::is_same<real, float>::value && opt_.kind == BB_OPT_TRUNCATED_ADAGRAD && lam_ring_.p != nullptr &&
+           !getenv("BB_NO_RESUM");
+}
+template <typename real> void Engine<real>::maybe_resum() {
+    if (!resum_active() || step_count <= 0 || step_count % opt_.n != 0) return;
+    const long long wraps = step_count / opt_.n;
+    if (wraps > 4 && wraps % 8 != 0) return;
+    auto run = [&](const DBuf<r2> &ring, DBuf<r2> &acc) {
+        if (!ring.p || !acc.p || acc.n == 0) return;
+        ring_resum_kernel<real><<<cdiv((long long)acc.n, 256), 256, 0, stream_>>>(ring.p, acc.p, (long long)acc.n, opt_.n);
+        ++launches;
+    };
+    run(lam_ring_, lam_acc_); run(bc_ring_, bc_acc_);
+    if (L.hier) run(hy_ring_, hy_acc_);
+    BB_CUDA(cudaGetLastError());
+}
+
 template <typename real> void Engine<real>::step(int n, double *trace) {
     if (!opt_ready_) set_optimizer(opt_);
     if (trace) trace_.ensure((size_t)n * (L.K + 1));
@@ -1171,12 +1195,15 @@ template <typename real> void Engine<real>::step(int n, double *trace) {
     const bool can_persist = use_stepk && persist_chunk_ > 1 && !(comm_ && !xchg_on_) && !getenv("BB_NO_TAIL");
     bool persisted = false;
     for (int i = 0; i < n;) {
+        maybe_resum();
         RunMode m; m.update = true; m.want_elbo = trace != nullptr; m.step = (uint32_t)step_count;
         if (use_stepk) {
             m.fuse = true; m.stepk = true;
             m.have_xpart = part_step_ == step_count && part_is_x_;
             m.have_part = part_step_ == step_count && !part_is_x_;
             m.nsteps = can_persist ? std::min(persist_chunk_, n - i) : 1;
+            // a persistent launch ends at the window wrap, where the sums are rebuilt between launches
+            if (resum_active()) m.nsteps = (int)std::min<long long>(m.nsteps, opt_.n - step_count % opt_.n);
             persisted = persisted || m.nsteps > 1;
         } else {
             // software-pipelined step: pass 2 of this step also produces the partial sums of the next one
@@ -1218,6 +1245,7 @@ template <typename real> void Engine<real>::step_with_noise(const double *eps) {
     if (!opt_ready_) set_optimizer(opt_);
     ensure_supplied(false);
     upload_supplied(eps, L.K);
+    maybe_resum();
     RunMode m; m.sup = true; m.update = true; m.step = (uint32_t)step_count;
     run_pipeline(m);
     ++step_count;

@@ -311,3 +311,42 @@ def test_truncated_adagrad_unstaged_ring_fp32_k8(bb, monkeypatch):
                            mu0, om0, seed=1234)
     # measured 2.5e-6 / 1.9e-5 (fp32 window sums); 2e-3 before the population latents' update moved to double
     assert rel_err(res["fused"][0], tr.mu) < 3e-4 and rel_err(res["fused"][1], tr.omega) < 3e-4
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_fp32_truncated_adagrad_window_resum(bb, model, monkeypatch):
+    """fp32 TruncatedADAGrad: the running window sums are rebuilt from the ring at window wraps (Engine::maybe_resum),
+    so the fp32 trajectories stay on the oracle's, which sums the window afresh at every step like upstream
+    (tests/_debug_hier32.py).  The rebuild depends on the step
+    counter only: one call of 12 steps and 12 calls of one step agree bitwise on the launch-pair path."""
+    from oracle import advi_ref
+    n_steps, K = 12, 4
+    monkeypatch.setenv("BB_PERSIST", "0")
+    res = {}
+    for mode in ("one_call", "split", "no_resum"):
+        monkeypatch.delenv("BB_NO_RESUM", raising=False)
+        if mode == "no_resum":
+            monkeypatch.setenv("BB_NO_RESUM", "1")
+        da, eng = _setup(bb, model, K, "f32")
+        eng.init_params(5)
+        mu0, om0 = eng.get_params()
+        eng.set_optimizer("truncated", eta=0.1, tau=1.0, n=3)
+        launches0 = eng.launch_count
+        if mode == "split":
+            for _ in range(n_steps):
+                eng.step(1)
+        else:
+            eng.step(n_steps)
+        res[mode] = eng.get_params() + (eng.launch_count - launches0,)
+        eng.close()
+    tr = advi_ref.advi_run(model, oracle_problem(da, model), n_steps, K, advi_ref.TruncatedADAGrad(0.1, 1.0, 3),
+                           mu0, om0, seed=1234)
+    # between two rebuilds the residue of an eviction lives on for at most n steps: measured 2.6e-6 / 7.7e-6 / 9.0e-7 and,
+    # for the genotype fixture (hyper latents: gradients summed over the members), 3.5e-4 (1.6e-3 without the rebuild)
+    tol = 1e-3 if model == "genotype_fitness_normal" else 1e-4
+    assert rel_err(res["one_call"][0], tr.mu) < tol and rel_err(res["one_call"][1], tr.omega) < tol, \
+        (rel_err(res["one_call"][0], tr.mu), rel_err(res["one_call"][1], tr.omega))
+    assert np.array_equal(res["one_call"][0], res["split"][0]) and np.array_equal(res["one_call"][1], res["split"][1])
+    assert res["one_call"][2] > res["no_resum"][2]            # the rebuild kernels ran (wraps at steps 3, 6, 9)
+    # without the rebuild the run is still a bounded AdaGrad run near the oracle's
+    assert rel_err(res["no_resum"][0], tr.mu) < 1e-2 and rel_err(res["no_resum"][1], tr.omega) < 1e-2
