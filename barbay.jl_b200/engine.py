@@ -203,8 +203,15 @@ class Engine:
                                                _c_doubles(logp), _c_doubles(grad)))
         return logp, grad
 
-    def elbo_grad(self, eps=None, step: int = 0):
+    def elbo_grad(self, eps=None, step: int = 0, want_grad: bool = True):
+        """ELBO estimate and its gradient w.r.t. (mu, omega) at the current parameters (no update).
+        ``want_grad=False``: the gradient stays on the device (returns ``(elbo, None, None)``) -- what bench.py times
+        as the pure ELBO-gradient evaluation."""
         elbo = C.c_double()
+        if not want_grad:
+            p = None if eps is None else _c_doubles(np.ascontiguousarray(eps, dtype=np.float64).reshape(self.n_samples, self.D))
+            self._check(self._lib.bb_elbo_grad(self._h, p, int(step), C.byref(elbo), None))
+            return elbo.value, None, None
         grad = np.empty(2 * self.D)
         if eps is not None:
             eps = np.ascontiguousarray(eps, dtype=np.float64).reshape(self.n_samples, self.D)

@@ -118,7 +118,7 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def make_workload(cfg: int, mult: int = 1, scale: float = 1.0):
+def make_workload(cfg: int, mult: int = 1, scale: float = 1.0, seed_offset: int = 0):
     """BASELINE configs[cfg - 1]; mult > 1 multiplies the barcode axis (weak scaling: 10^6 barcodes per GPU)."""
     import barbay_b200 as bb
     spec = dict(bb.synth.CONFIGS[cfg])
@@ -127,7 +127,7 @@ def make_workload(cfg: int, mult: int = 1, scale: float = 1.0):
         spec[key] = max(8, int(round(spec[key] * mult * scale)))
     if "n_geno" in spec and scale != 1.0:
         spec["n_geno"] = max(2, int(round(spec["n_geno"] * scale)))
-    da, _ = bb.synth.simulate(model, seed=bb.synth.BASE_SEED + cfg, **spec)
+    da, _ = bb.synth.simulate(model, seed=bb.synth.BASE_SEED + cfg + seed_offset, **spec)
     return model, da
 
 
@@ -437,6 +437,32 @@ def run_ours(args, emit):
             extras["value_f64"] = units_step / (ms64 / n_prof * 1e-3)
             extras["roofline_f64"] = r64
             e64.close()
+        # the pure ELBO-gradient evaluation (K draws + log-joint + analytic gradient, NO optimiser update;
+        # bb_elbo_grad with the gradient left on the device: pass 1 + tail + pass 2 with the ELBO terms, gradients
+        # written to their own arrays) -- CUDA events around `n_eg` calls, each ending with the 8-byte ELBO read-back
+        eg = cx.engine(da, model, K, args.dtype, args.opt, sharded=False)
+        for s_ in range(3):
+            eg.elbo_grad(step=s_, want_grad=False)
+        n_eg = 100
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(cx.stream)
+        for s_ in range(n_eg):
+            eg.elbo_grad(step=3 + s_, want_grad=False)
+        ev1.record(cx.stream); torch.cuda.synchronize()
+        eg_us = ev0.elapsed_time(ev1) / n_eg * 1e3
+        eg_bytes = 4 * (4 if args.dtype != "f64" else 8) * eg.D + 4 * n_cells      # 4 w D + 4 T B R
+        extras["elbo_grad_only"] = {"call_us": eg_us, "value": units_step / (eg_us * 1e-6), "unit": UNIT,
+                                    "algorithmic_bytes": eg_bytes, "achieved": eg_bytes / (eg_us * 1e-6) / 1e9,
+                                    "frac": eg_bytes / (eg_us * 1e-6) / 1e9 / peak,
+                                    "what": "bb_elbo_grad(eps = NULL, grad = NULL): no update, gradient left on the device, ELBO read back"}
+        eg.close()
+        # throughput is data-independent (no data-dependent branch in any kernel): the same step on counts simulated
+        # from another seed
+        model_a, da_a = make_workload(CFG, seed_offset=1000)
+        ea = cx.engine(da_a, model_a, K, args.dtype, args.opt, sharded=False)
+        ms_a, _ = cx.time_steps(ea, 400, 20)
+        extras["alt_seed"] = {"seed_offset": 1000, "step_us": ms_a / 400 * 1e3, "value": units_step / (ms_a / 400 * 1e-3), "unit": UNIT}
+        ea.close(); del da_a
         if args.opt != "truncated":
             # fp32 TruncatedADAGrad rebuilds its window sums from the ring at the first four window wraps (n = 100 steps)
             # and at every eighth after them: time 800 steps past the fourth wrap, i.e. the steady state with one
