@@ -62,6 +62,27 @@ struct BBDesc
     env_per_rep::Int32   # 1: env_idx holds one environment list per replicate
 end
 
+"""
+    naive_prior(da; device=-1) -> Dict
+
+`BarBay.stats.naive_prior` (src/stats.jl:1175-1359) on the GPU from the packed counts `da = data_to_arrays(data; ...)`
+of the frame WITH the pseudocount added (the reference adds it at stats.jl:1185 before packing, :1189): the
+replacement for the arithmetic of stats.jl:1199-1352, same keys and vector orders.
+"""
+function naive_prior(da; device::Integer=-1)
+    counts = da.bc_count isa Vector ? reduce(vcat, vec.(da.bc_count)) : vec(da.bc_count)
+    n_time = Int32.(da.bc_count isa Vector ? size.(da.bc_count, 1) :
+                    fill(size(da.bc_count, 1), ndims(da.bc_count) == 3 ? size(da.bc_count, 3) : 1))
+    n_pop = sum(n_time) - length(n_time)
+    s_pop, logσ_pop = Vector{Float64}(undef, n_pop), Vector{Float64}(undef, n_pop)
+    logλ = Vector{Float64}(undef, length(counts))
+    rc = ccall((:bb_naive_prior, LIB), Cint,
+               (Ptr{Int64}, Int32, Ptr{Int32}, Int32, Int32, Int32, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+               counts, length(n_time), n_time, da.n_neutral, da.n_bc, device, s_pop, logσ_pop, logλ)
+    rc == 0 || error(unsafe_string(ccall((:bb_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    return Dict(:s_pop_prior => s_pop, :logσ_pop_prior => logσ_pop, :logλ_prior => logλ)
+end
+
 # model function name -> bb_model (the reference dispatches on the name too, src/vi.jl:111-169)
 function model_id(model::Function)
     name = "$(model)"
