@@ -350,3 +350,14 @@ def test_fp32_truncated_adagrad_window_resum(bb, model, monkeypatch):
     assert res["one_call"][2] > res["no_resum"][2]            # the rebuild kernels ran (wraps at steps 3, 6, 9)
     # without the rebuild the run is still a bounded AdaGrad run near the oracle's
     assert rel_err(res["no_resum"][0], tr.mu) < 1e-2 and rel_err(res["no_resum"][1], tr.omega) < 1e-2
+
+
+def test_elbo_grad_without_gradient_readback(bb):
+    """bb_elbo_grad(grad = NULL): same ELBO estimate, gradient left on the device (what bench.py times as the pure
+    ELBO-gradient evaluation)."""
+    da, eng = _setup(bb, "fitness_normal", 3, "f64")
+    eng.init_params(2)
+    e1, gm, go = eng.elbo_grad(step=4)
+    e0, n1, n2 = eng.elbo_grad(step=4, want_grad=False)
+    assert n1 is None and n2 is None and e0 == e1 and np.isfinite(gm).all() and np.isfinite(go).all()
+    eng.close()
