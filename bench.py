@@ -327,6 +327,38 @@ def parity_check(cx: Ctx, K=2, n_barcodes=30_000, n_steps=4):
     return out
 
 
+def parity_check_f32(cx: Ctx, K=K_MC, n_barcodes=120_000, n_steps=24):
+    """The MEASURED path -- fp32 persistent step kernel with the in-kernel NVLink exchange -- sharded over all ranks
+    against the same kernel on one GPU: one call of `n_steps` steps, same seed.  The column arithmetic is identical;
+    only the order in which the per-thread fp32 partial sums enter the double totals differs with the tile split."""
+    torch = cx.torch
+    model, da = make_workload(CFG, 1, scale=n_barcodes / 1e6)
+    out = {}
+    eng = cx.engine(da, model, K, "f32", "decayed", sharded=True, seed=7)
+    eng.step(n_steps)
+    plane = eng.data_plane()
+    m, s = eng.get_posterior()
+    eng.close()
+    t = torch.from_numpy(np.stack([m, s])).cuda()
+    cx.dist.all_reduce(t)
+    m, s = t.cpu().numpy()
+    if cx.rank == 0:
+        ref = cx.engine(da, model, K, "f32", "decayed", sharded=False, seed=7)
+        ref.step(n_steps)
+        m1, s1 = ref.get_posterior()
+        ref.close()
+        out = {"mean_rel": float(np.max(np.abs(m - m1)) / np.max(np.abs(m1))),
+               "sd_rel": float(np.max(np.abs(s - s1) / s1)),
+               "sd_rel_median": float(np.median(np.abs(s - s1) / s1)),
+               "step_kernel": plane["step_kernel"], "persistent": plane["persistent"],
+               "peer_exchange": plane["peer_exchange"],
+               "what": f"{cx.world}-GPU sharded vs 1-GPU run of the measured fp32 path, fitness_normal {n_barcodes} "
+                       f"barcodes x 5, K={K}, one call of {n_steps} steps, same Philox seed"}
+        out["ok"] = bool(out["mean_rel"] < 1e-5 and out["sd_rel"] < 1e-4)
+    cx.barrier()
+    return out
+
+
 def roofline_of(cx: Ctx, eng, steps_ms_per_step, n_prof, peak, peak_src, key, note=None):
     ms_tot, ms_p1, ms_p2 = eng.time_steps(n_prof)
     cx.barrier()
@@ -391,6 +423,7 @@ def run_ours(args, emit):
     peak, peak_src = measured_peak_gbs()
 
     parity = parity_check(cx) if world > 1 else None
+    parity_f32 = parity_check_f32(cx) if world > 1 and args.dtype == "f32" else None
 
     sampler = ClockSampler(cx.local_rank) if rank == 0 else None
     if sampler:
@@ -604,6 +637,8 @@ def run_ours(args, emit):
             line["breakdown_us"] = breakdown
         if parity is not None:
             line["parity"] = parity
+        if parity_f32 is not None:
+            line["parity_f32"] = parity_f32
         if scaling_weak is not None:
             line["scaling_weak"] = scaling_weak
         line.update(extras)
