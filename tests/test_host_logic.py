@@ -127,6 +127,17 @@ def test_c_abi_exports_every_declared_symbol(bb):
     assert lib.bb_n_latent(None) == -1 and lib.bb_last_error(None) is not None
 
 
+def test_device_naive_prior_fails_loudly_without_a_gpu(bb):
+    """stats.naive_prior(device=...) is the CUDA path (bb_naive_prior): no silent numpy fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine WITHOUT a GPU")
+    df, _ = load_fixture("fitness_normal")
+    with pytest.raises(bb.BarBayError, match="no CPU fallback"):
+        bb.stats.naive_prior(df, mutate=False, device=0)
+    assert bb.stats.naive_prior(df, mutate=False)["s_pop_prior"].size == 4     # the host mirror is a separate, explicit call
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "barbay.jl_b200")
     for dirpath, _, files in os.walk(pkg):
